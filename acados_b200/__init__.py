@@ -1,0 +1,8 @@
+"""acados_b200 -- B200-native batched OCP-QP interior-point solver (cuipm) behind acados' ocp_qp plugin surface.
+
+Only what the hot path needs lives here: ``csrc/`` (CUDA kernels + the C ABI of include/cuipm.h),
+``plugin/`` (the plain-C acados qp_solver plugin that calls the C ABI), ``binding`` (ctypes), ``problems``
+(shapes, record layout, synthetic batches) and ``ocp_qp`` (host-side mirror of the reference's
+AcadosOcpQp / AcadosOcpQpSolver interface for this path).
+"""
+from .problems import Batch, Layout, Shape  # noqa: F401

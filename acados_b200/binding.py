@@ -1,0 +1,191 @@
+"""ctypes binding of the C ABI in ``include/cuipm.h`` (libcuipm.so, built in-tree by ``__graft_entry__.build``).
+
+The library is the product: hand-written sm_100a CUDA kernels behind plain-C entry points.  There is no
+CPU fallback -- if the shared object is missing, or no CUDA device is present, the solve calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from .problems import Batch, Layout, Shape
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libcuipm.so")
+
+STAT_M = 20
+STATUS_NAMES = {0: "SUCCESS", 1: "MAX_ITER", 2: "MIN_STEP", 3: "NAN_SOL", 4: "INCONS_EQ"}
+MODES = {"SPEED_ABS": 0, "SPEED": 1, "BALANCE": 2, "ROBUST": 3}
+
+
+class CuipmOpts(C.Structure):
+    """Mirror of ``struct cuipm_opts``."""
+    _fields_ = [("mode", C.c_int), ("iter_max", C.c_int), ("stat_max", C.c_int), ("mu0", C.c_double),
+                ("alpha_min", C.c_double), ("res_g_max", C.c_double), ("res_b_max", C.c_double),
+                ("res_d_max", C.c_double), ("res_m_max", C.c_double), ("dual_gap_max", C.c_double),
+                ("reg_prim", C.c_double), ("lam_min", C.c_double), ("t_min", C.c_double), ("tau_min", C.c_double),
+                ("lam0_min", C.c_double), ("t0_min", C.c_double), ("pred_corr", C.c_int), ("cond_pred_corr", C.c_int),
+                ("itref_pred_max", C.c_int), ("itref_corr_max", C.c_int), ("lq_fact", C.c_int), ("warm_start", C.c_int),
+                ("abs_form", C.c_int), ("comp_dual_sol_eq", C.c_int), ("comp_res_exit", C.c_int),
+                ("split_step", C.c_int), ("var_init_scheme", C.c_int), ("t_lam_min", C.c_int), ("t0_init", C.c_int),
+                ("m_relax", C.c_double)]
+
+
+class CuipmInfo(C.Structure):
+    """Mirror of ``struct cuipm_info``."""
+    _fields_ = [("status", C.c_int), ("iter", C.c_int), ("res_max", C.c_double * 4), ("mu", C.c_double),
+                ("obj", C.c_double), ("dual_gap", C.c_double), ("lq_count", C.c_int), ("reserved", C.c_int)]
+
+
+INFO_DTYPE = np.dtype([("status", np.int32), ("iter", np.int32), ("res_max", np.float64, (4,)), ("mu", np.float64),
+                       ("obj", np.float64), ("dual_gap", np.float64), ("lq_count", np.int32), ("reserved", np.int32)],
+                      align=True)
+assert INFO_DTYPE.itemsize == C.sizeof(CuipmInfo)
+
+_lib: Optional[C.CDLL] = None
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    """Loads libcuipm.so; raises if the extension has not been built (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; "
+                           "g.build()'); the cuipm solver has no CPU fallback")
+    lib = C.CDLL(path)
+    vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.c_int
+    lib.cuipm_opts_set_default.argtypes = [C.POINTER(CuipmOpts), ip]
+    lib.cuipm_opts_set_default_acados.argtypes = [C.POINTER(CuipmOpts), ip]
+    lib.cuipm_opts_set.argtypes = [C.POINTER(CuipmOpts), C.c_char_p, vp]
+    lib.cuipm_opts_set.restype = ip
+    lib.cuipm_opts_get.argtypes = [C.POINTER(CuipmOpts), C.c_char_p, vp]
+    lib.cuipm_opts_get.restype = ip
+    lib.cuipm_layout_create.argtypes = [vp]
+    lib.cuipm_layout_create.restype = vp
+    lib.cuipm_layout_destroy.argtypes = [vp]
+    lib.cuipm_create.argtypes = [vp, ip, ip]
+    lib.cuipm_create.restype = vp
+    lib.cuipm_destroy.argtypes = [vp]
+    lib.cuipm_get_layout.argtypes = [vp]
+    lib.cuipm_get_layout.restype = vp
+    lib.cuipm_last_error.restype = C.c_char_p
+    lib.cuipm_solve_host.argtypes = [vp, ip, vp, vp, vp, vp, C.POINTER(CuipmOpts)]
+    lib.cuipm_solve_host.restype = ip
+    lib.cuipm_solve_device.argtypes = [vp, ip, vp, vp, vp, vp, C.POINTER(CuipmOpts), ip]
+    lib.cuipm_solve_device.restype = ip
+    for name in ("cuipm_device_qp_buffer", "cuipm_device_sol_buffer", "cuipm_device_info_buffer", "cuipm_stream"):
+        getattr(lib, name).argtypes = [vp]
+        getattr(lib, name).restype = vp
+    lib.cuipm_get_ric.argtypes = [vp, ip, C.c_char_p, ip, vp, ip, ip]
+    lib.cuipm_get_ric.restype = ip
+    lib.cuipm_last_launch_count.argtypes = [vp]
+    lib.cuipm_last_launch_count.restype = ip
+    lib.cuipm_last_kernel_ms.argtypes = [vp]
+    lib.cuipm_last_kernel_ms.restype = C.c_float
+    lib.cuipm_set_tuning.argtypes = [vp, C.c_char_p, ip]
+    lib.cuipm_set_tuning.restype = ip
+    _lib = lib
+    return lib
+
+
+def default_opts(mode: str = "BALANCE", acados: bool = True, **overrides) -> CuipmOpts:
+    """Options as the reference's plugin would hold them (``acados=True``: HPIPM mode defaults plus the acados
+    overrides, i.e. what PARTIAL_CONDENSING_HPIPM runs with; keyword overrides use the struct field names)."""
+    lib = load_library()
+    o = CuipmOpts()
+    (lib.cuipm_opts_set_default_acados if acados else lib.cuipm_opts_set_default)(C.byref(o), MODES[mode])
+    for k, v in overrides.items():
+        if not hasattr(o, k):
+            raise KeyError(k)
+        setattr(o, k, v)
+    if o.stat_max < o.iter_max:
+        o.stat_max = o.iter_max
+    return o
+
+
+class _CLayout(C.Structure):
+    _fields_ = ([("N", C.c_int), ("qp_stride", C.c_size_t)]
+                + [(n, C.POINTER(C.c_size_t)) for n in ("qp_stage", "off_BAt", "off_RSQ", "off_DCt", "off_b", "off_rq",
+                                                          "off_d", "off_dmask", "off_Z", "off_z")]
+                + [("sol_stride", C.c_size_t)]
+                + [(n, C.POINTER(C.c_size_t)) for n in ("sol_stage", "off_ux", "off_pi", "off_lam", "off_t")])
+
+
+def c_layout_as_dict(ptr: int, N: int) -> dict:
+    """Reads a ``cuipm_layout*`` into python lists (used to cross-check the numpy Layout)."""
+    l = C.cast(ptr, C.POINTER(_CLayout)).contents
+    out = {"qp_stride": l.qp_stride, "sol_stride": l.sol_stride}
+    for n, _ in _CLayout._fields_:
+        if n in ("N", "qp_stride", "sol_stride"):
+            continue
+        cnt = N + 2 if n.endswith("_stage") else N + 1
+        out[n] = [getattr(l, n)[i] for i in range(cnt)]
+    return out
+
+
+class CuipmSolver:
+    """Batched OCP-QP solver on one CUDA device (thin object wrapper over the C ABI)."""
+
+    def __init__(self, shape: Shape, max_batch: int, device: int = 0):
+        self.lib = load_library()
+        self.shape = shape
+        self.layout = Layout(shape)
+        self.max_batch = max_batch
+        self._cshape = shape.as_ctypes()
+        self.handle = self.lib.cuipm_create(C.byref(self._cshape), max_batch, device)
+        if not self.handle:
+            raise RuntimeError("cuipm_create failed: " + self.lib.cuipm_last_error().decode())
+
+    def close(self):
+        if self.handle:
+            self.lib.cuipm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"cuipm error {rc}: " + self.lib.cuipm_last_error().decode())
+
+    def solve(self, qp: np.ndarray, opts: Optional[CuipmOpts] = None, sol0: Optional[np.ndarray] = None,
+              want_stat: bool = False):
+        """Host-buffer solve (H2D, kernel, D2H inside): returns (sol, info[, stat])."""
+        opts = opts or default_opts()
+        nb = qp.shape[0]
+        assert qp.dtype == np.float64 and qp.flags.c_contiguous and qp.shape[1] == self.layout.qp_stride
+        sol = np.zeros((nb, self.layout.sol_stride)) if sol0 is None else np.ascontiguousarray(sol0, dtype=np.float64).copy()
+        info = np.zeros(nb, dtype=INFO_DTYPE)
+        stat = np.zeros((nb, opts.stat_max + 1, STAT_M)) if want_stat else None
+        rc = self.lib.cuipm_solve_host(self.handle, nb, qp.ctypes.data, sol.ctypes.data, info.ctypes.data,
+                                       stat.ctypes.data if want_stat else None, C.byref(opts))
+        self._check(rc)
+        return (sol, info, stat) if want_stat else (sol, info)
+
+    def solve_device(self, nbatch: int, d_qp: int, d_sol: int, d_info: int, opts: CuipmOpts, sync: bool = True,
+                     d_stat: int = 0):
+        self._check(self.lib.cuipm_solve_device(self.handle, nbatch, d_qp, d_sol, d_info, d_stat or None,
+                                                C.byref(opts), 1 if sync else 0))
+
+    def set_tuning(self, key: str, value: int):
+        self._check(self.lib.cuipm_set_tuning(self.handle, key.encode(), value))
+
+    @property
+    def last_kernel_ms(self) -> float:
+        return float(self.lib.cuipm_last_kernel_ms(self.handle))
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self.lib.cuipm_last_launch_count(self.handle))
+
+    def get_ric(self, iqp: int, field: str, stage: int, shape2):
+        out = np.zeros(shape2[::-1])  # column-major (size1 x size2)
+        self._check(self.lib.cuipm_get_ric(self.handle, iqp, field.encode(), stage, out.ctypes.data, shape2[0], shape2[1]))
+        return out.T

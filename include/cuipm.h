@@ -1,0 +1,201 @@
+/*
+ * cuipm.h -- C ABI of the B200-native batched OCP-QP interior-point solver.
+ *
+ * This is the drop-in boundary for acados' `qp_solver` plugin slot: everything the reference's
+ * `ocp_qp_hpipm()` (acados/ocp_qp/ocp_qp_hpipm.c:314-405) obtains from HPIPM's
+ * `d_ocp_qp_ipm_solve()` (external/hpipm/ocp_qp/x_ocp_qp_ipm.c:2684-3120) is obtained through the
+ * entry points below instead.  Plain pointers and sizes only: no torch / CUDA types in signatures, so
+ * the plugin source that lives inside libacados (acados_b200/plugin/ocp_qp_cuipm.c) stays plain C.
+ *
+ * Batch model: all QPs of one batch share a SHAPE (horizon, per-stage dimensions, box/soft index maps)
+ * and differ in their numerical DATA.  One QP's data is one contiguous "QP record" of doubles; one
+ * QP's primal-dual solution is one contiguous "solution record".  Record layouts are described by
+ * cuipm_layout (offsets in doubles), computed by cuipm_layout_create().
+ *
+ * Conventions are HPIPM's (external/hpipm/include/hpipm_d_ocp_qp.h:54-71, ocp_qp/x_ocp_qp.c:1035-1267):
+ *   stage k = 0..N, v_k = [u_k; x_k] (nu_k + nx_k), dynamics x_{k+1} = BAt_k' v_k + b_k,
+ *   cost 1/2 v'RSQ v + rq'v (+ slacks: 1/2 s'Z s + z's), constraints
+ *     lb <= v[idxb] (+ sl) , v[idxb] (- su) <= ub ; lg <= DCt' v (+ sl), DCt' v (- su) <= ug ; sl >= lls, su >= lus
+ *   d = [lb, lg, -ub, -ug, lls, lus]  (UPPER BOUNDS STORED NEGATED, x_ocp_qp.c:1228-1267)
+ *   lam, t ordered (lb, lg, ub, ug, ls, us); d_mask in {0.0, 1.0} disables single constraints.
+ *   idxs_rev[k][i] = slack index softening constraint i (i over nb+ng), or -1.
+ */
+#ifndef CUIPM_H_
+#define CUIPM_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUIPM_STAT_M 20  /* columns of the per-iteration statistics table (x_ocp_qp_ipm.c:801) */
+
+/* return / status codes: HPIPM's (external/hpipm/include/hpipm_common.h:57-64) */
+enum cuipm_status {
+    CUIPM_SUCCESS = 0,
+    CUIPM_MAX_ITER = 1,
+    CUIPM_MIN_STEP = 2,
+    CUIPM_NAN_SOL = 3,
+    CUIPM_INCONS_EQ = 4
+};
+
+/* error codes of the API calls themselves (not solver status) */
+enum cuipm_error {
+    CUIPM_OK = 0,
+    CUIPM_ERR_INVALID = -1,     /* bad argument / unsupported option value */
+    CUIPM_ERR_CUDA = -2,        /* CUDA runtime error (message via cuipm_last_error) */
+    CUIPM_ERR_NO_DEVICE = -3,   /* no CUDA device: there is NO CPU fallback */
+    CUIPM_ERR_TOO_LARGE = -4    /* stage dimensions exceed what the kernel supports */
+};
+
+/* modes: external/hpipm/include/hpipm_common.h (enum hpipm_mode) */
+enum cuipm_mode { CUIPM_SPEED_ABS = 0, CUIPM_SPEED = 1, CUIPM_BALANCE = 2, CUIPM_ROBUST = 3 };
+
+/* Shape shared by all QPs of a batch (mirrors struct d_ocp_qp_dim + idxb/idxs_rev of struct d_ocp_qp). */
+typedef struct cuipm_shape {
+    int N;                        /* horizon length; stages 0..N */
+    const int *nx;                /* [N+1] */
+    const int *nu;                /* [N+1] */
+    const int *nb;                /* [N+1] box constraints on v=[u;x] */
+    const int *ng;                /* [N+1] general constraints */
+    const int *ns;                /* [N+1] soft-constraint slack pairs */
+    const int *const *idxb;       /* [N+1][nb_k]      index into v_k */
+    const int *const *idxs_rev;   /* [N+1][nb_k+ng_k] slack index or -1 (may be NULL if all ns==0) */
+} cuipm_shape;
+
+/* Solver options: the subset of struct d_ocp_qp_ipm_arg (hpipm_d_ocp_qp_ipm.h) that the reference's
+ * plugin can reach through ocp_qp_hpipm_opts_set (acados/ocp_qp/ocp_qp_hpipm.c:142-183). */
+typedef struct cuipm_opts {
+    int mode;             /* enum cuipm_mode the defaults were taken from */
+    int iter_max;
+    int stat_max;         /* rows of the statistics table kept (>= iter_max) */
+    double mu0;
+    double alpha_min;
+    double res_g_max;     /* tol_stat */
+    double res_b_max;     /* tol_eq   */
+    double res_d_max;     /* tol_ineq */
+    double res_m_max;     /* tol_comp */
+    double dual_gap_max;
+    double reg_prim;
+    double lam_min;
+    double t_min;
+    double tau_min;
+    double lam0_min;
+    double t0_min;
+    int pred_corr;
+    int cond_pred_corr;
+    int itref_pred_max;
+    int itref_corr_max;
+    int lq_fact;          /* 0: Cholesky only; 1: Cholesky, LQ when inaccurate; 2: always LQ */
+    int warm_start;       /* 0 cold; 1 keep ux guess (acados zeroes it); 2/3 keep lam,t (clipped) */
+    int abs_form;         /* must be 0 (delta formulation) */
+    int comp_dual_sol_eq; /* must be 1 */
+    int comp_res_exit;    /* must be 1 */
+    int split_step;       /* must be 0 */
+    int var_init_scheme;  /* 0 or 1 */
+    int t_lam_min;        /* 0,1,2 */
+    int t0_init;          /* 0,1,2 */
+    double m_relax;       /* acados "tau_min": if >0, complementarity target m_i = m_relax (ocp_qp_hpipm.c:338-342) */
+} cuipm_opts;
+
+/* Offsets (in doubles) inside one QP record / one solution record.  All sub-arrays start on an even
+ * offset (16-byte aligned) and the records are a multiple of 2 doubles long.  Arrays of length N+1
+ * are indexed by stage; entries for BAt/b/pi at stage N are unused (no dynamics after the last stage). */
+typedef struct cuipm_layout {
+    int N;
+    /* QP record */
+    size_t qp_stride;      /* doubles per QP record */
+    size_t *qp_stage;      /* [N+2] start of stage k's sub-record; qp_stage[N+1] == qp_stride */
+    size_t *off_BAt;       /* (nu+nx) x nx_next, column-major, ld = nu+nx : [B'; A'] */
+    size_t *off_RSQ;       /* (nu+nx) x (nu+nx), column-major, ld = nu+nx, LOWER triangle referenced: [R S'; S Q] */
+    size_t *off_DCt;       /* (nu+nx) x ng, column-major : [D'; C'] */
+    size_t *off_b;         /* nx_next */
+    size_t *off_rq;        /* nu+nx */
+    size_t *off_d;         /* 2nb+2ng+2ns : lb, lg, -ub, -ug, lls, lus */
+    size_t *off_dmask;     /* 2nb+2ng+2ns */
+    size_t *off_Z;         /* 2ns : Zl, Zu (diagonals) */
+    size_t *off_z;         /* 2ns : zl, zu */
+    /* solution record */
+    size_t sol_stride;     /* doubles per solution record */
+    size_t *sol_stage;     /* [N+2] */
+    size_t *off_ux;        /* nu+nx+2ns : u, x, sl, su */
+    size_t *off_pi;        /* nx_next */
+    size_t *off_lam;       /* 2nb+2ng+2ns */
+    size_t *off_t;         /* 2nb+2ng+2ns */
+} cuipm_layout;
+
+/* Per-QP result summary written next to each solution record. */
+typedef struct cuipm_info {
+    int status;            /* enum cuipm_status */
+    int iter;              /* IPM iterations taken */
+    double res_max[4];     /* inf-norms: stationarity, equality, inequality, complementarity */
+    double mu;             /* duality measure at exit */
+    double obj;            /* objective value at exit */
+    double dual_gap;
+    int lq_count;          /* iterations in which the Cholesky accuracy test (x_ocp_qp_ipm.c:2299-2310) failed */
+    int reserved;
+} cuipm_info;
+
+typedef struct cuipm_solver cuipm_solver;  /* opaque: device buffers, stream, compiled-shape tables */
+
+/* ---- options ------------------------------------------------------------------------------------ */
+/* HPIPM mode defaults (x_ocp_qp_ipm.c:69-260). */
+void cuipm_opts_set_default(cuipm_opts *opts, int mode);
+/* HPIPM mode defaults + the overrides acados applies after every mode switch (ocp_qp_hpipm.c:101-129):
+ * this is what PARTIAL_CONDENSING_HPIPM runs with out of the box. */
+void cuipm_opts_set_default_acados(cuipm_opts *opts, int mode);
+/* String-keyed setter with the reference's field names (ocp_qp_hpipm.c:142-183; x_ocp_qp_ipm.c:264-384):
+ * iter_max, tol_stat, tol_eq, tol_ineq, tol_comp, tol_dual_gap, mu0, alpha_min, reg_prim, warm_start,
+ * pred_corr, cond_pred_corr, split_step, t_lam_min, t0_init, var_init_scheme, lam_min, t_min, tau_min,
+ * lam0_min, t0_min, ric_alg, comp_res_exit, comp_dual_sol_eq, hpipm_mode (value = const char*).
+ * Returns CUIPM_ERR_INVALID for an unknown field (the plugin turns that into printf+exit(1) like the reference). */
+int cuipm_opts_set(cuipm_opts *opts, const char *field, const void *value);
+int cuipm_opts_get(const cuipm_opts *opts, const char *field, void *value);
+
+/* ---- layout ------------------------------------------------------------------------------------- */
+cuipm_layout *cuipm_layout_create(const cuipm_shape *shape);
+void cuipm_layout_destroy(cuipm_layout *layout);
+
+/* ---- solver lifetime ---------------------------------------------------------------------------- */
+/* Creates a solver bound to CUDA device `device` able to hold up to `max_batch` QPs of `shape`.
+ * Returns NULL on failure (cuipm_last_error() tells why).  There is no CPU fallback. */
+cuipm_solver *cuipm_create(const cuipm_shape *shape, int max_batch, int device);
+void cuipm_destroy(cuipm_solver *s);
+const cuipm_layout *cuipm_get_layout(const cuipm_solver *s);
+const char *cuipm_last_error(void);
+
+/* ---- solve -------------------------------------------------------------------------------------- */
+/* Host-buffer entry (what the acados plugin / batch function calls):
+ *   qp    : nbatch QP records, host memory (pinned memory makes the copies asynchronous)
+ *   sol   : nbatch solution records, host memory.  With opts->warm_start >= 1 it is also an INPUT.
+ *   info  : nbatch summaries
+ *   stat  : optional nbatch x (stat_max+1) x CUIPM_STAT_M table (row-per-iteration, HPIPM's column meaning); may be NULL
+ * Copies H2D, solves on the device, copies D2H, synchronises.  Returns enum cuipm_error. */
+int cuipm_solve_host(cuipm_solver *s, int nbatch, const double *qp, double *sol, cuipm_info *info,
+                     double *stat, const cuipm_opts *opts);
+
+/* Device-buffer entry: all pointers are device pointers on the solver's device; asynchronous on the
+ * solver's stream unless `sync` != 0. */
+int cuipm_solve_device(cuipm_solver *s, int nbatch, const double *d_qp, double *d_sol, cuipm_info *d_info,
+                       double *d_stat, const cuipm_opts *opts, int sync);
+
+/* Device memory owned by the solver, for callers that stage data themselves (bench, multi-GPU scatter). */
+double *cuipm_device_qp_buffer(cuipm_solver *s);       /* max_batch * qp_stride doubles  */
+double *cuipm_device_sol_buffer(cuipm_solver *s);      /* max_batch * sol_stride doubles */
+cuipm_info *cuipm_device_info_buffer(cuipm_solver *s); /* max_batch */
+void *cuipm_stream(cuipm_solver *s);                   /* cudaStream_t */
+
+/* Riccati quantities of the last factorisation (reference: ocp_qp_hpipm_solver_get, ocp_qp_hpipm.c:417-478).
+ * field in {"P","p","K","k","Lr"}; copies column-major data of QP `iqp`, stage `stage` into `value`. */
+int cuipm_get_ric(cuipm_solver *s, int iqp, const char *field, int stage, double *value, int size1, int size2);
+
+/* number of kernels the last solve call launched (bench.py's gpu_launches claim) */
+int cuipm_last_launch_count(const cuipm_solver *s);
+/* device time in milliseconds of the main kernel of the last cuipm_solve_* call with sync (CUDA events) */
+float cuipm_last_kernel_ms(const cuipm_solver *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUIPM_H_ */

@@ -1,0 +1,87 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes access to the CPU checkers under oracle/.
+
+``oracle_solve``  : our plain-C restatement (oracle/liboracle_ipm.so, built by ``make -C oracle port``).
+``ref_solve``     : the unmodified reference (HPIPM+BLASFEO behind acados' qp_solver vtable) compiled into
+                    oracle/_ref/ by ``make -C oracle ref`` where /root/reference exists; the prebuilt .so files
+                    travel to the GPU box.
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from acados_b200.binding import INFO_DTYPE, STAT_M, CuipmOpts
+from acados_b200.problems import Batch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_LIB = os.path.join(_HERE, "liboracle_ipm.so")
+REF_LIB = os.path.join(_HERE, "_ref", "libref_harness.so")
+_libs = {}
+
+
+def _load(path):
+    if path not in _libs:
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} missing: run `make -C oracle` (needs /root/reference for the _ref part)")
+        _libs[path] = C.CDLL(path)
+    return _libs[path]
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_LIB)
+
+
+def oracle_solve(batch: Batch, opts: CuipmOpts, sol0=None, want_stat=False, nthreads=0):
+    lib = _load(ORACLE_LIB)
+    nb = batch.nbatch
+    sol = batch.layout.new_sol(nb) if sol0 is None else np.ascontiguousarray(sol0).copy()
+    info = np.zeros(nb, dtype=INFO_DTYPE)
+    stat = np.zeros((nb, opts.stat_max + 1, STAT_M)) if want_stat else None
+    lib.oracle_solve.restype = C.c_int
+    rc = lib.oracle_solve(C.byref(batch.shape.as_ctypes()), C.c_int(nb), C.c_void_p(batch.qp.ctypes.data),
+                          C.c_void_p(sol.ctypes.data), C.c_void_p(info.ctypes.data),
+                          C.c_void_p(stat.ctypes.data if want_stat else None), C.byref(opts), C.c_int(nthreads))
+    if rc != 0:
+        raise RuntimeError(f"oracle_solve: unsupported options ({rc})")
+    return (sol, info, stat) if want_stat else (sol, info)
+
+
+def oracle_residuals(batch: Batch, sol):
+    lib = _load(ORACLE_LIB)
+    info = np.zeros(batch.nbatch, dtype=INFO_DTYPE)
+    sol = np.ascontiguousarray(sol)
+    lib.oracle_residuals(C.byref(batch.shape.as_ctypes()), C.c_int(batch.nbatch), C.c_void_p(batch.qp.ctypes.data),
+                         C.c_void_p(sol.ctypes.data), C.c_void_p(info.ctypes.data))
+    return info
+
+
+def oracle_layout(shape):
+    from acados_b200.binding import c_layout_as_dict
+    lib = _load(ORACLE_LIB)
+    lib.oracle_layout_create.restype = C.c_void_p
+    p = lib.oracle_layout_create(C.byref(shape.as_ctypes()))
+    d = c_layout_as_dict(p, shape.N)
+    lib.oracle_layout_destroy(C.c_void_p(p))
+    return d
+
+
+def ref_solve(batch: Batch, opts: CuipmOpts, sol0=None, want_stat=False, nthreads=0, nrep=1):
+    """Returns (sol, info[, stat], timing) with timing = dict(solve_s=max over threads of time inside the
+    reference's evaluate(), wall_s, threads)."""
+    lib = _load(REF_LIB)
+    nb = batch.nbatch
+    sol = batch.layout.new_sol(nb) if sol0 is None else np.ascontiguousarray(sol0).copy()
+    info = np.zeros(nb, dtype=INFO_DTYPE)
+    stat = np.zeros((nb, opts.stat_max + 1, STAT_M)) if want_stat else None
+    ts, tw = C.c_double(0), C.c_double(0)
+    lib.ref_num_procs.restype = C.c_int
+    lib.ref_solve(C.byref(batch.shape.as_ctypes()), C.c_int(nb), C.c_void_p(batch.qp.ctypes.data),
+                  C.c_void_p(sol.ctypes.data), C.c_void_p(info.ctypes.data),
+                  C.c_void_p(stat.ctypes.data if want_stat else None), C.byref(opts), C.c_int(nthreads), C.c_int(nrep),
+                  C.byref(ts), C.byref(tw))
+    timing = {"solve_s": ts.value, "wall_s": tw.value,
+              "threads": nthreads if nthreads > 0 else int(lib.ref_num_procs())}
+    return (sol, info, stat, timing) if want_stat else (sol, info, timing)
