@@ -1,0 +1,327 @@
+// cuipm_api.cu -- solver lifetime and the solve entry points of the C ABI (include/cuipm.h).
+//
+// Replaces, for a whole batch at once, what ocp_qp_hpipm() does per instance in the reference
+// (acados/ocp_qp/ocp_qp_hpipm.c:314-405): hand the QP to the IPM, collect status / iteration count /
+// statistics.  All device memory is owned by the solver object (the reference's plugin reports sizes and is
+// handed raw host memory, which cannot hold device allocations -- SURVEY.md section 8(b)).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cuipm.h"
+#include "cuipm_device.h"
+#include "cuipm_internal.h"
+
+using namespace cuipm;
+
+struct cuipm_solver
+{
+    int device = 0;
+    int max_batch = 0;
+    int warps = 1;
+    cuipm_layout *layout = nullptr;
+    ProbDesc P{};
+    std::vector<StageDesc> sd_host;
+    StageDesc *d_sd = nullptr;
+    int *d_ipool = nullptr;
+    double *d_qp = nullptr, *d_sol = nullptr, *d_work = nullptr, *d_stat = nullptr;
+    size_t stat_cap = 0;
+    cuipm_info *d_info = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int last_launches = 0;
+    float last_ms = 0.f;
+    cuipm_opts last_opts{};
+};
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+        {                                                                                               \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                              \
+            return CUIPM_ERR_CUDA;                                                                      \
+        }                                                                                               \
+    } while (0)
+
+static inline unsigned ev2u(size_t n) { return (unsigned) ((n + 1) & ~(size_t) 1); }
+
+static int build_desc(cuipm_solver *s, const cuipm_shape *sh)
+{
+    const int N = sh->N;
+    const cuipm_layout *l = s->layout;
+    std::vector<int> ipool;
+    s->sd_host.assign(N + 1, StageDesc{});
+    ProbDesc &P = s->P;
+    P = ProbDesc{};
+    P.N = N;
+    size_t w = 0;
+    for (int k = 0; k <= N; k++)
+    {
+        StageDesc &d = s->sd_host[k];
+        d.nx = sh->nx[k]; d.nu = sh->nu[k]; d.n = d.nx + d.nu; d.nb = sh->nb[k]; d.ng = sh->ng[k]; d.ns = sh->ns[k];
+        d.nbg = d.nb + d.ng; d.nc = 2 * (d.nbg + d.ns);
+        d.nx1 = k < N ? sh->nx[k + 1] : 0; d.nu1 = k < N ? sh->nu[k + 1] : 0; d.n1 = d.nx1 + d.nu1;
+        if (d.nx < 0 || d.nu < 0 || d.nb < 0 || d.ng < 0 || d.ns < 0) { set_error("negative dimension"); return CUIPM_ERR_INVALID; }
+        if (d.ns > 0 && !sh->idxs_rev) { set_error("ns>0 needs idxs_rev"); return CUIPM_ERR_INVALID; }
+        d.idx_off = (int) ipool.size();
+        d.dup_idxb = 0;
+        for (int i = 0; i < d.nb; i++)
+        {
+            const int ix = sh->idxb[k][i];
+            if (ix < 0 || ix >= d.n) { set_error("idxb out of range"); return CUIPM_ERR_INVALID; }
+            for (int j = 0; j < i; j++) d.dup_idxb |= sh->idxb[k][j] == ix;
+            ipool.push_back(ix);
+        }
+        for (int i = 0; i < d.nbg; i++)
+        {
+            const int r = (d.ns > 0 && sh->idxs_rev) ? sh->idxs_rev[k][i] : -1;
+            if (r < -1 || r >= d.ns) { set_error("idxs_rev out of range"); return CUIPM_ERR_INVALID; }
+            ipool.push_back(r);
+        }
+        d.q_BAt = (unsigned) l->off_BAt[k]; d.q_RSQ = (unsigned) l->off_RSQ[k]; d.q_DCt = (unsigned) l->off_DCt[k];
+        d.q_b = (unsigned) l->off_b[k]; d.q_rq = (unsigned) l->off_rq[k]; d.q_d = (unsigned) l->off_d[k];
+        d.q_dmask = (unsigned) l->off_dmask[k]; d.q_Z = (unsigned) l->off_Z[k]; d.q_z = (unsigned) l->off_z[k];
+        d.sol = VOff{(unsigned) l->off_ux[k], (unsigned) l->off_pi[k], (unsigned) l->off_lam[k], (unsigned) l->off_t[k]};
+        const size_t nvs = (size_t) d.n + 2 * d.ns;
+        auto take = [&](size_t n) { unsigned o = (unsigned) w; w += ev2u(n); return o; };
+        // factor first (read by two sweeps per solve), then the vectors
+        d.w_L = take((size_t) d.n * d.n); d.w_Linv = take(d.n); d.w_lrow = take(d.n); d.w_Pb = take(d.nx1); d.w_Zsi = take(2 * d.ns);
+        d.step = VOff{take(nvs), take(d.nx1), take(d.nc), take(d.nc)};
+        d.res = ROff{take(nvs), take(d.nx1), take(d.nc), take(d.nc)};
+        d.w_rmb = take(d.nc);
+        d.ires = ROff{take(nvs), take(d.nx1), take(d.nc), take(d.nc)};
+        d.itref = VOff{take(nvs), take(d.nx1), take(d.nc), take(d.nc)};
+        P.nmax = std::max(P.nmax, d.n); P.nxmax = std::max(P.nxmax, std::max(d.nx, d.nx1)); P.ngmax = std::max(P.ngmax, d.ng);
+        P.nsmax = std::max(P.nsmax, d.ns); P.nbgmax = std::max(P.nbgmax, d.nbg); P.ncmax = std::max(P.ncmax, d.nc);
+        P.nvsmax = std::max(P.nvsmax, (int) nvs);
+        P.nct += d.nc;
+    }
+    if (w >= (size_t) 1 << 32 || l->qp_stride >= (size_t) 1 << 32) { set_error("QP record too large for 32-bit offsets"); return CUIPM_ERR_TOO_LARGE; }
+    P.qp_stride = l->qp_stride; P.sol_stride = l->sol_stride; P.work_stride = w;
+    auto e = [](int n) { return (n + 1) & ~1; };
+    P.sm_M = e(P.nmax * P.nmax);
+    P.sm_A = e(P.nmax * P.nxmax);
+    P.sm_AL = e(std::max((P.nmax + 1) * P.nxmax, P.nmax * P.nmax));
+    P.sm_C = e(P.nmax * P.ngmax);
+    P.sm_V = 3 * e(P.nvsmax) + 6 * e(P.nxmax) + 8 * e(P.ncmax) + 6 * e(P.nbgmax) + 6 * e(P.nmax + 1) + 8 * e(2 * P.nsmax) + 16;
+    P.sm_total = P.sm_M + P.sm_A + P.sm_AL + P.sm_C + P.sm_V;
+    if (smem_bytes(P) > 227 * 1024) { set_error("stage dimensions need more than 227 KB of shared memory"); return CUIPM_ERR_TOO_LARGE; }
+    CK(cudaMalloc(&s->d_sd, sizeof(StageDesc) * (N + 1)));
+    CK(cudaMemcpy(s->d_sd, s->sd_host.data(), sizeof(StageDesc) * (N + 1), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&s->d_ipool, sizeof(int) * (ipool.size() + 1)));
+    if (!ipool.empty()) CK(cudaMemcpy(s->d_ipool, ipool.data(), sizeof(int) * ipool.size(), cudaMemcpyHostToDevice));
+    return CUIPM_OK;
+}
+
+extern "C" cuipm_solver *cuipm_create(const cuipm_shape *shape, int max_batch, int device)
+{
+    if (!shape || max_batch <= 0) { set_error("cuipm_create: bad arguments"); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+        set_error("no CUDA device available (cuipm has no CPU fallback)");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) { set_error("cuipm_create: no such device"); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); return nullptr; }
+    cuipm_solver *s = new cuipm_solver();
+    s->device = device;
+    s->max_batch = max_batch;
+    s->layout = cuipm_layout_create(shape);
+    auto fail = [&]() { cuipm_destroy(s); return (cuipm_solver *) nullptr; };
+    if (build_desc(s, shape) != CUIPM_OK) return fail();
+    auto alloc = [&](void **p, size_t bytes) {
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return false; }
+        return true;
+    };
+    if (!alloc((void **) &s->d_qp, sizeof(double) * s->P.qp_stride * max_batch)) return fail();
+    if (!alloc((void **) &s->d_sol, sizeof(double) * s->P.sol_stride * max_batch)) return fail();
+    if (!alloc((void **) &s->d_work, sizeof(double) * s->P.work_stride * max_batch)) return fail();
+    if (!alloc((void **) &s->d_info, sizeof(cuipm_info) * max_batch)) return fail();
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(); }
+    cudaEventCreate(&s->ev0);
+    cudaEventCreate(&s->ev1);
+    cudaMemsetAsync(s->d_work, 0, sizeof(double) * s->P.work_stride * max_batch, s->stream);
+    cudaMemsetAsync(s->d_sol, 0, sizeof(double) * s->P.sol_stride * max_batch, s->stream);
+    cudaStreamSynchronize(s->stream);
+    // default warps per QP: one warp owns one QP unless the stage block is large
+    s->warps = s->P.nmax > 40 ? 4 : 1;
+    return s;
+}
+
+extern "C" void cuipm_destroy(cuipm_solver *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->d_sd); cudaFree(s->d_ipool); cudaFree(s->d_qp); cudaFree(s->d_sol); cudaFree(s->d_work);
+    cudaFree(s->d_stat); cudaFree(s->d_info);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    cuipm_layout_destroy(s->layout);
+    delete s;
+}
+
+extern "C" const cuipm_layout *cuipm_get_layout(const cuipm_solver *s) { return s->layout; }
+extern "C" double *cuipm_device_qp_buffer(cuipm_solver *s) { return s->d_qp; }
+extern "C" double *cuipm_device_sol_buffer(cuipm_solver *s) { return s->d_sol; }
+extern "C" cuipm_info *cuipm_device_info_buffer(cuipm_solver *s) { return s->d_info; }
+extern "C" void *cuipm_stream(cuipm_solver *s) { return (void *) s->stream; }
+extern "C" int cuipm_last_launch_count(const cuipm_solver *s) { return s->last_launches; }
+extern "C" float cuipm_last_kernel_ms(const cuipm_solver *s) { return s->last_ms; }
+
+extern "C" int cuipm_set_tuning(cuipm_solver *s, const char *key, int value)
+{
+    if (!std::strcmp(key, "warps"))
+    {
+        if (value != 1 && value != 2 && value != 4) { set_error("warps must be 1, 2 or 4"); return CUIPM_ERR_INVALID; }
+        s->warps = value;
+        return CUIPM_OK;
+    }
+    set_error("unknown tuning key");
+    return CUIPM_ERR_INVALID;
+}
+
+extern "C" int cuipm_solve_device(cuipm_solver *s, int nbatch, const double *d_qp, double *d_sol, cuipm_info *d_info,
+                                  double *d_stat, const cuipm_opts *opts, int sync)
+{
+    if (!s || nbatch < 0 || nbatch > s->max_batch || !d_qp || !d_sol || !d_info || !opts)
+    {
+        set_error("cuipm_solve_device: bad arguments (nbatch must be <= max_batch)");
+        return CUIPM_ERR_INVALID;
+    }
+    int rc = opts_check(opts);
+    if (rc != CUIPM_OK) return rc;
+    CK(cudaSetDevice(s->device));
+    s->last_launches = 0;
+    if (nbatch == 0) return CUIPM_OK;
+    LaunchArgs a;
+    a.P = s->P; a.sd = s->d_sd; a.ipool = s->d_ipool; a.qp = d_qp; a.sol = d_sol; a.work = s->d_work; a.info = d_info;
+    a.stat = d_stat; a.o = *opts; a.nbatch = nbatch;
+    s->last_opts = *opts;
+    CK(cudaEventRecord(s->ev0, s->stream));
+    int e = launch_solve(a, s->warps, (void *) s->stream);
+    if (e != 0) { set_error(std::string("kernel launch: ") + cudaGetErrorString((cudaError_t) e)); return CUIPM_ERR_CUDA; }
+    s->last_launches = 1;
+    CK(cudaEventRecord(s->ev1, s->stream));
+    if (sync)
+    {
+        CK(cudaStreamSynchronize(s->stream));
+        cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1);
+    }
+    return CUIPM_OK;
+}
+
+extern "C" int cuipm_solve_host(cuipm_solver *s, int nbatch, const double *qp, double *sol, cuipm_info *info, double *stat,
+                                const cuipm_opts *opts)
+{
+    if (!s || nbatch < 0 || nbatch > s->max_batch || !qp || !sol || !info || !opts)
+    {
+        set_error("cuipm_solve_host: bad arguments (nbatch must be <= max_batch)");
+        return CUIPM_ERR_INVALID;
+    }
+    int rc = opts_check(opts);
+    if (rc != CUIPM_OK) return rc;
+    CK(cudaSetDevice(s->device));
+    if (nbatch == 0) return CUIPM_OK;
+    const size_t stat_n = (size_t) nbatch * CUIPM_STAT_M * (opts->stat_max + 1);
+    if (stat && s->stat_cap < stat_n)
+    {
+        cudaFree(s->d_stat);
+        s->d_stat = nullptr;
+        CK(cudaMalloc(&s->d_stat, sizeof(double) * stat_n));
+        s->stat_cap = stat_n;
+    }
+    CK(cudaMemcpyAsync(s->d_qp, qp, sizeof(double) * s->P.qp_stride * nbatch, cudaMemcpyHostToDevice, s->stream));
+    if (opts->warm_start >= 1)
+        CK(cudaMemcpyAsync(s->d_sol, sol, sizeof(double) * s->P.sol_stride * nbatch, cudaMemcpyHostToDevice, s->stream));
+    rc = cuipm_solve_device(s, nbatch, s->d_qp, s->d_sol, s->d_info, stat ? s->d_stat : nullptr, opts, 0);
+    if (rc != CUIPM_OK) return rc;
+    CK(cudaMemcpyAsync(sol, s->d_sol, sizeof(double) * s->P.sol_stride * nbatch, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaMemcpyAsync(info, s->d_info, sizeof(cuipm_info) * nbatch, cudaMemcpyDeviceToHost, s->stream));
+    if (stat) CK(cudaMemcpyAsync(stat, s->d_stat, sizeof(double) * stat_n, cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1);
+    return CUIPM_OK;
+}
+
+// Riccati quantities of the last factorisation of QP iqp (reference getters: ocp_qp_hpipm_solver_get,
+// acados/ocp_qp/ocp_qp_hpipm.c:417-478 -> d_ocp_qp_ipm_get_ric_*, external/hpipm/ocp_qp/x_ocp_qp_ipm.c:1384-1610).
+//   Lr : nu x nu lower Cholesky factor of the reduced input Hessian  (L[0:nu,0:nu])
+//   P  : nx x nx cost-to-go Hessian  Lxx Lxx'
+//   K  : nu x nx feedback matrix     -(Lxu Luu^{-1})'
+//   p  : nx      cost-to-go gradient Lxx * l_x    (valid after a factorisation: uses lrow)
+//   k  : nu      feed-forward        -Luu^{-T} l_u
+extern "C" int cuipm_get_ric(cuipm_solver *s, int iqp, const char *field, int stage, double *value, int size1, int size2)
+{
+    if (!s || iqp < 0 || iqp >= s->max_batch || stage < 0 || stage > s->P.N || !value) { set_error("cuipm_get_ric: bad arguments"); return CUIPM_ERR_INVALID; }
+    const StageDesc &d = s->sd_host[stage];
+    const int n = d.n, nu = d.nu, nx = d.nx;
+    std::vector<double> L((size_t) n * n + 1), lrow(n + 1);
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    const double *wk = s->d_work + (size_t) iqp * s->P.work_stride;
+    CK(cudaMemcpy(L.data(), wk + d.w_L, sizeof(double) * n * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(lrow.data(), wk + d.w_lrow, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    auto Lel = [&](int i, int j) { return L[(size_t) i + (size_t) n * j]; };
+    if (!std::strcmp(field, "Lr"))
+    {
+        if (size1 != nu || size2 != nu) { set_error("Lr: wrong size"); return CUIPM_ERR_INVALID; }
+        for (int j = 0; j < nu; j++) for (int i = 0; i < nu; i++) value[i + nu * j] = i >= j ? Lel(i, j) : 0.0;
+    }
+    else if (!std::strcmp(field, "P"))
+    {
+        if (size1 != nx || size2 != nx) { set_error("P: wrong size"); return CUIPM_ERR_INVALID; }
+        for (int j = 0; j < nx; j++)
+            for (int i = 0; i < nx; i++)
+            {
+                double acc = 0.0;
+                for (int c = 0; c <= (i < j ? i : j); c++) acc += Lel(nu + i, nu + c) * Lel(nu + j, nu + c);
+                value[i + nx * j] = acc;
+            }
+    }
+    else if (!std::strcmp(field, "p"))
+    {
+        if (size1 * size2 != nx) { set_error("p: wrong size"); return CUIPM_ERR_INVALID; }
+        for (int i = 0; i < nx; i++)
+        {
+            double acc = 0.0;
+            for (int c = 0; c <= i; c++) acc += Lel(nu + i, nu + c) * lrow[nu + c];
+            value[i] = acc;
+        }
+    }
+    else if (!std::strcmp(field, "K"))
+    {
+        if (size1 != nu || size2 != nx) { set_error("K: wrong size"); return CUIPM_ERR_INVALID; }
+        // K = -(Lxu Luu^{-1})' : solve X Luu = Lxu row by row, K[j,i] = -X[i,j]
+        for (int i = 0; i < nx; i++)
+        {
+            std::vector<double> x(nu);
+            for (int j = nu - 1; j >= 0; j--)
+            {
+                double acc = Lel(nu + i, j);
+                for (int c = j + 1; c < nu; c++) acc -= x[c] * Lel(c, j);
+                x[j] = acc / Lel(j, j);
+            }
+            for (int j = 0; j < nu; j++) value[j + nu * i] = -x[j];
+        }
+    }
+    else if (!std::strcmp(field, "k"))
+    {
+        if (size1 * size2 != nu) { set_error("k: wrong size"); return CUIPM_ERR_INVALID; }
+        for (int j = nu - 1; j >= 0; j--)
+        {
+            double acc = -lrow[j];
+            for (int c = j + 1; c < nu; c++) acc -= Lel(c, j) * value[c];
+            value[j] = acc / Lel(j, j);
+        }
+    }
+    else { set_error("cuipm_get_ric: unknown field"); return CUIPM_ERR_INVALID; }
+    return CUIPM_OK;
+}

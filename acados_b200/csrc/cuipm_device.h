@@ -1,0 +1,63 @@
+// cuipm_device.h -- device-visible problem description shared by the API (host) and the kernels.
+#ifndef CUIPM_DEVICE_H_
+#define CUIPM_DEVICE_H_
+
+#include <cstddef>
+
+#include "cuipm.h"
+
+namespace cuipm {
+
+struct VOff { unsigned ux, pi, lam, t; };   // offsets (doubles) of a primal-dual point / step
+struct ROff { unsigned g, b, d, m; };       // offsets (doubles) of a residual / right-hand side
+
+// One horizon stage: dimensions and the offsets of its arrays inside the QP record (q_*), the solution
+// record (sol) and the per-QP work record (everything else).
+struct StageDesc
+{
+    int nx, nu, n, nb, ng, ns, nbg, nc;   // n = nu+nx, nbg = nb+ng, nc = 2*(nb+ng+ns)
+    int nx1, nu1, n1;                     // dims of stage k+1 (0 at the last stage)
+    int idx_off;                          // ipool[idx_off .. +nb) = idxb, then [.. +nbg) = idxs_rev
+    int dup_idxb;                         // idxb has repeated entries: scatter serially
+    int pad_;
+    unsigned q_BAt, q_RSQ, q_DCt, q_b, q_rq, q_d, q_dmask, q_Z, q_z;
+    VOff sol, step, itref;
+    ROff res, ires;
+    unsigned w_rmb, w_L, w_Linv, w_lrow, w_Pb, w_Zsi;
+};
+
+struct ProbDesc
+{
+    int N;
+    int nmax, nxmax, ngmax, nsmax, nbgmax, ncmax, nvsmax;  // maxima over stages (nvs = n + 2 ns)
+    int nct;                                               // total constraint count
+    int pad_;
+    size_t qp_stride, sol_stride, work_stride;
+    // shared-memory carve (doubles)
+    int sm_M, sm_A, sm_AL, sm_C, sm_V;
+    int sm_total;
+};
+
+struct LaunchArgs
+{
+    ProbDesc P;
+    const StageDesc *sd;
+    const int *ipool;
+    const double *qp;
+    double *sol;
+    double *work;
+    cuipm_info *info;
+    double *stat;      // may be null
+    cuipm_opts o;
+    int nbatch;
+};
+
+// launches the solve kernel with `warps` warps per QP on `stream`; returns cudaError_t as int
+int launch_solve(const LaunchArgs &a, int warps, void *stream);
+// dynamic shared memory (bytes) the kernel needs for P
+size_t smem_bytes(const ProbDesc &P);
+// largest warps-per-QP value compiled
+int max_warps();
+
+}  // namespace cuipm
+#endif

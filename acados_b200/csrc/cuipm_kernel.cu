@@ -1,0 +1,1330 @@
+// cuipm_kernel.cu -- the batched OCP-QP interior-point kernel (sm_100a).
+//
+// One CTA of W warps owns one QP for the whole solve: Mehrotra predictor-corrector iterations around a
+// square-root Riccati factorisation / substitution, with residuals, step length, centring and the
+// termination test evaluated inside the same launch (reference hot path: HPIPM d_ocp_qp_ipm_solve,
+// external/hpipm/ocp_qp/x_ocp_qp_ipm.c:2684-3120, reached from acados/ocp_qp/ocp_qp_hpipm.c:347).
+// Stage blocks (Hessian block, dynamics block, Cholesky factor) are staged through shared memory with
+// coalesced loads of this QP's contiguous record; the batch of QPs is the grid.
+//
+// This file is the generic path: any per-stage dimensions, box / general / soft constraints, masks.
+#include <cuda_runtime.h>
+
+#include <cmath>
+
+#include "cuipm_device.h"
+
+namespace cuipm {
+
+namespace {
+
+#define tid ((int) threadIdx.x)
+
+__device__ __forceinline__ int ev(int n) { return (n + 1) & ~1; }
+
+template <int W>
+struct Ker
+{
+    static constexpr int NT = 32 * W;
+
+    ProbDesc P;
+    const StageDesc *__restrict__ SD;
+    const int *__restrict__ ipool;
+    const double *__restrict__ qp;   // this QP's record (read-only for the whole kernel)
+    double *sol;                     // this QP's solution record
+    double *wk;                      // this QP's work record
+    double *sM, *sA, *sAL, *sC, *sV, *sred;
+    cuipm_opts o;
+    int mask_constr;
+    double nc_mask_inv;
+
+    // ---- CTA primitives -------------------------------------------------------------------------
+    __device__ __forceinline__ void sync()
+    {
+        if (W == 1) __syncwarp();
+        else __syncthreads();
+    }
+    __device__ __forceinline__ double wsum(double v)
+    {
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+        return v;
+    }
+    __device__ double rsum(double v)
+    {
+        v = wsum(v);
+        if (W > 1)
+        {
+            if ((tid & 31) == 0) sred[tid >> 5] = v;
+            __syncthreads();
+            v = 0.0;
+#pragma unroll
+            for (int w = 0; w < W; w++) v += sred[w];
+            __syncthreads();
+        }
+        return v;
+    }
+    __device__ double rmin(double v)
+    {
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, m));
+        if (W > 1)
+        {
+            if ((tid & 31) == 0) sred[tid >> 5] = v;
+            __syncthreads();
+            v = sred[0];
+#pragma unroll
+            for (int w = 1; w < W; w++) v = fmin(v, sred[w]);
+            __syncthreads();
+        }
+        return v;
+    }
+    // max of non-negative values; NaN is propagated (BLASFEO VECNRM_INF semantics, d_aux_lib4.c:4893-4995)
+    __device__ double rmax_nan(double v, int isnan_)
+    {
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1)
+        {
+            v = fmax(v, __shfl_xor_sync(0xffffffffu, v, m));
+            isnan_ |= __shfl_xor_sync(0xffffffffu, isnan_, m);
+        }
+        if (W > 1)
+        {
+            if ((tid & 31) == 0) sred[tid >> 5] = isnan_ ? NAN : v;
+            __syncthreads();
+            v = 0.0;
+            isnan_ = 0;
+#pragma unroll
+            for (int w = 0; w < W; w++)
+            {
+                double x = sred[w];
+                if (x != x) isnan_ = 1;
+                else v = fmax(v, x);
+            }
+            __syncthreads();
+        }
+        return isnan_ ? NAN : v;
+    }
+    __device__ __forceinline__ void cp(double *dst, const double *src, int n)
+    {
+        for (int i = tid; i < n; i += NT) dst[i] = src[i];
+    }
+
+    // ---- addressing -------------------------------------------------------------------------------
+    // vector sets: 0 = current iterate (solution record), 1 = step, 2 = iterative-refinement step
+    __device__ __forceinline__ double *vux(int set, const StageDesc &s) const
+    {
+        return set == 0 ? sol + s.sol.ux : wk + (set == 1 ? s.step.ux : s.itref.ux);
+    }
+    __device__ __forceinline__ double *vpi(int set, const StageDesc &s) const
+    {
+        return set == 0 ? sol + s.sol.pi : wk + (set == 1 ? s.step.pi : s.itref.pi);
+    }
+    __device__ __forceinline__ double *vlam(int set, const StageDesc &s) const
+    {
+        return set == 0 ? sol + s.sol.lam : wk + (set == 1 ? s.step.lam : s.itref.lam);
+    }
+    __device__ __forceinline__ double *vt(int set, const StageDesc &s) const
+    {
+        return set == 0 ? sol + s.sol.t : wk + (set == 1 ? s.step.t : s.itref.t);
+    }
+    // residual sets: 0 = res, 1 = res_itref
+    __device__ __forceinline__ double *rg(int set, const StageDesc &s) const { return wk + (set == 0 ? s.res.g : s.ires.g); }
+    __device__ __forceinline__ double *rb(int set, const StageDesc &s) const { return wk + (set == 0 ? s.res.b : s.ires.b); }
+    __device__ __forceinline__ double *rd(int set, const StageDesc &s) const { return wk + (set == 0 ? s.res.d : s.ires.d); }
+    __device__ __forceinline__ double *rm(int set, const StageDesc &s) const { return wk + (set == 0 ? s.res.m : s.ires.m); }
+
+    // iterate over the lower triangle (i >= j, i < n) plus the extra row i == n of an (n+1) x n array,
+    // perfectly balanced: column p is paired with column n-1-p (n+3 entries per pair).
+    template <class F>
+    __device__ __forceinline__ void for_lower_plus_row(int n, F f)
+    {
+        const int np = (n + 1) >> 1, rows = n + 3, tot = np * rows;
+        for (int e = tid; e < tot; e += NT)
+        {
+            int p = e / rows, r = e - p * rows;
+            int len0 = n - p + 1;
+            if (r < len0) f(p + r, p);
+            else
+            {
+                int q = n - 1 - p;
+                if (q != p) f(q + (r - len0), q);
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // residuals (restates OCP_QP_RES_COMPUTE / _LIN, external/hpipm/ocp_qp/x_ocp_qp_res.c:345-683)
+    // lin==0: KKT residuals of the QP at point set `pset` -> residual set `out`; returns mu, obj, gap.
+    // lin==1: residual of the Newton system with rhs set `rhs` at step `pset`, linearised at the iterate.
+    // nrm[4] = inf-norms of (g, b, d, m).
+    // ---------------------------------------------------------------------------------------------
+    __device__ __noinline__ void res_pass(int lin, int pset, int rhs, int out, double &mu, double &obj, double &gap, double nrm[4])
+    {
+        const int N = P.N;
+        double a_mu = 0.0, a_obj = 0.0, a_gap = 0.0;
+        double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+        int f0 = 0, f1 = 0, f2 = 0, f3 = 0;
+        double *ux = sV, *x1 = ux + ev(P.nvsmax), *pi = x1 + ev(P.nxmax), *pim = pi + ev(P.nxmax);
+        double *lam = pim + ev(P.nxmax), *lamr = lam + ev(P.ncmax), *t = lamr + ev(P.ncmax), *msk = t + ev(P.ncmax);
+        double *tmp0 = msk + ev(P.ncmax), *tmp1 = tmp0 + ev(P.nbgmax), *g_ = tmp1 + ev(P.nbgmax);
+        for (int k = 0; k <= N; k++)
+        {
+            const StageDesc s = SD[k];
+            const int n = s.n, nu = s.nu, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1;
+            const int *idxb = ipool + s.idx_off, *rev = idxb + nb;
+            const double *qk = qp;
+            // ---- stage data to shared memory
+            cp(ux, vux(pset, s), n + 2 * ns);
+            if (k < N)
+            {
+                const StageDesc s1 = SD[k + 1];
+                cp(x1, vux(pset, s1) + s1.nu, nx1);
+                cp(pi, vpi(pset, s), nx1);
+                cp(sA, qk + s.q_BAt, n * nx1);
+            }
+            if (k > 0) cp(pim, vpi(pset, SD[k - 1]), s.nx);
+            {
+                const double *gl = vlam(pset, s), *gt = vt(pset, s), *gm = qk + s.q_dmask;
+                for (int i = tid; i < nc; i += NT)
+                {
+                    double l = gl[i], mk = mask_constr ? gm[i] : 1.0;
+                    lamr[i] = l;
+                    lam[i] = mask_constr ? l * mk : l;
+                    t[i] = gt[i];
+                    msk[i] = mk;
+                }
+            }
+            cp(sM, qk + s.q_RSQ, n * n);
+            if (ng > 0) cp(sC, qk + s.q_DCt, n * ng);
+            sync();
+            for (int i = tid; i < nbg; i += NT) tmp0[i] = lam[nbg + i] - lam[i];
+            sync();
+            // ---- rows of res_g, res_b and C'ux
+            const double *gvec = rhs < 0 ? qk + s.q_rq : rg(rhs, s);
+            const double *bvec = rhs < 0 ? qk + s.q_b : rb(rhs, s);
+            double *ob = rb(out, s);
+            for (int oo = tid; oo < n + nx1 + ng; oo += NT)
+            {
+                if (oo < n)
+                {
+                    const int i = oo;
+                    double acc = 0.0;
+                    for (int j = 0; j <= i; j++) acc += sM[i + n * j] * ux[j];
+                    for (int j = i + 1; j < n; j++) acc += sM[j + n * i] * ux[j];
+                    const double gv = gvec[i];
+                    double r;
+                    if (!lin)
+                    {
+                        r = acc + 2.0 * gv;
+                        a_obj += 0.5 * r * ux[i];
+                        r -= gv;
+                        a_gap += r * ux[i];
+                    }
+                    else
+                        r = acc + gv;
+                    if (k > 0 && i >= nu) r -= pim[i - nu];
+                    for (int j = 0; j < nx1; j++) r += sA[i + n * j] * pi[j];
+                    for (int g = 0; g < ng; g++) r += sC[i + n * g] * tmp0[nb + g];
+                    g_[i] = r;
+                }
+                else if (oo < n + nx1)
+                {
+                    const int j = oo - n;
+                    double acc = 0.0;
+                    for (int i = 0; i < n; i++) acc += sA[i + n * j] * ux[i];
+                    const double bv = bvec[j];
+                    const double r = bv - x1[j] + acc;
+                    ob[j] = r;
+                    const double a = fabs(r);
+                    m1 = fmax(m1, a);
+                    f1 |= (a != a);
+                    if (!lin) a_gap -= bv * pi[j];
+                }
+                else
+                {
+                    const int g = oo - n - nx1;
+                    double acc = 0.0;
+                    for (int i = 0; i < n; i++) acc += sC[i + n * g] * ux[i];
+                    tmp1[nb + g] = acc;
+                }
+            }
+            sync();
+            // ---- box scatter, slack rows
+            if (!s.dup_idxb)
+                for (int i = tid; i < nb; i += NT)
+                {
+                    const int ix = idxb[i];
+                    tmp1[i] = ux[ix];
+                    g_[ix] += tmp0[i];
+                }
+            else if (tid == 0)
+                for (int i = 0; i < nb; i++)
+                {
+                    const int ix = idxb[i];
+                    tmp1[i] = ux[ix];
+                    g_[ix] += tmp0[i];
+                }
+            if (ns > 0)
+            {
+                const double *Z = qk + s.q_Z, *zvec = rhs < 0 ? qk + s.q_z : rg(rhs, s) + n;
+                for (int j = tid; j < 2 * ns; j += NT)
+                {
+                    const double sj = ux[n + j], zz = zvec[j];
+                    double r;
+                    if (!lin)
+                    {
+                        r = Z[j] * sj + 2.0 * zz;
+                        a_obj += 0.5 * r * sj;
+                        r -= zz;
+                        a_gap += r * sj;
+                    }
+                    else
+                        r = Z[j] * sj + zz;
+                    r -= lam[2 * nbg + j];
+                    const int jj = j < ns ? j : j - ns, offl = j < ns ? 0 : nbg;
+                    for (int i = 0; i < nbg; i++)
+                        if (rev[i] == jj) r -= lam[offl + i];
+                    g_[n + j] = r;
+                }
+            }
+            sync();
+            // ---- res_d, res_m
+            {
+                const double *dvec = rhs < 0 ? qk + s.q_d : rd(rhs, s);
+                double *od = rd(out, s), *om = rm(out, s);
+                const double *mv = lin ? rm(rhs, s) : nullptr;
+                const double *Lam = lin ? sol + s.sol.lam : nullptr, *T = lin ? sol + s.sol.t : nullptr;
+                for (int i = tid; i < nc; i += NT)
+                {
+                    const double dv = dvec[i];
+                    double r;
+                    if (i < 2 * nbg)
+                    {
+                        const int up = i >= nbg, ii = up ? i - nbg : i;
+                        const double v = tmp1[ii];
+                        r = t[i] + dv + (up ? v : -v);
+                        if (ns > 0 && rev[ii] >= 0) r -= ux[n + (up ? ns : 0) + rev[ii]];
+                    }
+                    else
+                        r = t[i] - ux[n + (i - 2 * nbg)] + dv;
+                    if (mask_constr) r *= msk[i];
+                    od[i] = r;
+                    double a = fabs(r);
+                    m2 = fmax(m2, a);
+                    f2 |= (a != a);
+                    double mm;
+                    if (!lin)
+                    {
+                        a_gap -= dv * lam[i];
+                        mm = lam[i] * t[i];
+                        if (mask_constr) mm *= msk[i];
+                        a_mu += fabs(mm);
+                    }
+                    else
+                    {
+                        mm = mv[i] + Lam[i] * t[i] + lamr[i] * T[i];
+                        if (mask_constr) mm *= msk[i];
+                    }
+                    om[i] = mm;
+                    a = fabs(mm);
+                    m3 = fmax(m3, a);
+                    f3 |= (a != a);
+                }
+                double *og = rg(out, s);
+                for (int i = tid; i < n + 2 * ns; i += NT)
+                {
+                    const double r = g_[i];
+                    og[i] = r;
+                    const double a = fabs(r);
+                    m0 = fmax(m0, a);
+                    f0 |= (a != a);
+                }
+            }
+            sync();
+        }
+        nrm[0] = rmax_nan(m0, f0);
+        nrm[1] = rmax_nan(m1, f1);
+        nrm[2] = rmax_nan(m2, f2);
+        nrm[3] = rmax_nan(m3, f3);
+        if (!lin)
+        {
+            mu = rsum(a_mu) * nc_mask_inv;
+            obj = rsum(a_obj);
+            gap = rsum(a_gap);
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // slack elimination (x_ocp_qp_kkt.c:220-335, 431-520): tmp0/tmp1 = effective Gamma / gamma of the
+    // softened constraints; ds = slack part of the step rhs; Zi = inverse of the slack Hessian.
+    // Parallel over slacks (a slack may soften several constraints).
+    // ---------------------------------------------------------------------------------------------
+    __device__ __noinline__ void cond_slacks(const StageDesc &s, int fact, const double *Gam, const double *gam, const double *rgs,
+                                double *Zi, double *ds, double *tmp0, double *tmp1)
+    {
+        const int nb = s.nb, ns = s.ns, nbg = s.nbg;
+        const int *rev = ipool + s.idx_off + nb;
+        const double *Z = qp + s.q_Z;
+        for (int j = tid; j < 2 * ns; j += NT)
+        {
+            const int jj = j < ns ? j : j - ns, offc = j < ns ? 0 : nbg;
+            double zi = 0.0, d = rgs[j] + gam[2 * nbg + j];
+            if (fact) zi = Z[j] + o.reg_prim + Gam[2 * nbg + j];
+            for (int i = 0; i < nbg; i++)
+                if (rev[i] == jj)
+                {
+                    if (fact) zi += Gam[offc + i];
+                    d += gam[offc + i];
+                }
+            if (fact) Zi[j] = 1.0 / zi;
+            ds[j] = d;
+        }
+        sync();
+        for (int i = tid; i < nbg; i += NT)
+        {
+            const int j = rev[i];
+            double t0l, t0u, t1l, t1u;
+            if (j != -1)
+            {
+                t0l = Gam[i] - Gam[i] * Zi[j] * Gam[i];
+                t0u = Gam[nbg + i] - Gam[nbg + i] * Zi[ns + j] * Gam[nbg + i];
+                t1l = gam[i] - Gam[i] * Zi[j] * ds[j];
+                t1u = gam[nbg + i] - Gam[nbg + i] * Zi[ns + j] * ds[ns + j];
+            }
+            else
+            {
+                t0l = Gam[i]; t0u = Gam[nbg + i]; t1l = gam[i]; t1u = gam[nbg + i];
+            }
+            if (fact) tmp0[i] = t0l + t0u;
+            tmp1[i] = t1l - t1u;
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // backward Riccati sweep with factorisation (OCP_QP_FACT_SOLVE_KKT_STEP, x_ocp_qp_kkt.c:880-966)
+    // rhs = residual set 0.  Writes L, Linv, lrow, Pb, Zs_inv (and the slack part of the step rhs).
+    // ---------------------------------------------------------------------------------------------
+    __device__ __noinline__ void fact_backward()
+    {
+        const int N = P.N;
+        double *Gam = sV, *gam = Gam + ev(P.ncmax), *tmp0 = gam + ev(P.ncmax), *tmp1 = tmp0 + ev(P.nbgmax);
+        double *row = tmp1 + ev(P.nbgmax), *Linv = row + ev(P.nmax), *lrow1 = Linv + ev(P.nmax);
+        double *bvec = lrow1 + ev(P.nmax), *Zi = bvec + ev(P.nxmax), *ds = Zi + ev(2 * P.nsmax);
+        double *tcol = ds + ev(2 * P.nsmax);
+        for (int k = N; k >= 0; k--)
+        {
+            const StageDesc s = SD[k];
+            const int n = s.n, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1, nu1 = s.nu1, n1 = s.n1;
+            const int *idxb = ipool + s.idx_off;
+            const int ldal = n + 1;
+            // ---- Gamma, gamma (COMPUTE_GAMMA_GAMMA_QP, x_core_qp_ipm_aux.c:38-86)
+            {
+                const double *gl = sol + s.sol.lam, *gt = sol + s.sol.t, *grd = rd(0, s), *grm = rm(0, s);
+                const double t_min_inv = o.t_min > 0 ? 1.0 / o.t_min : 1e30;
+                for (int i = tid; i < nc; i += NT)
+                {
+                    const double l = gl[i], tt = gt[i], ti = 1.0 / tt;
+                    if (o.t_lam_min == 1)
+                        Gam[i] = (tt < o.t_min ? t_min_inv : ti) * (l < o.lam_min ? o.lam_min : l);
+                    else
+                        Gam[i] = ti * l;
+                    gam[i] = ti * (grm[i] - l * grd[i]);
+                }
+            }
+            if (k < N)
+            {
+                // sM still holds L_{k+1}, lrow1 its last row
+                cp(sA, qp + s.q_BAt, n * nx1);
+                cp(bvec, rb(0, s), nx1);
+                sync();
+                // AL = [A; b'] * Lxx  (TRMM_RLNN)
+                for (int e = tid; e < ldal * nx1; e += NT)
+                {
+                    const int j = e / ldal, i = e - j * ldal;
+                    double acc = 0.0;
+                    const double *Lc = sM + nu1 + n1 * (nu1 + j);
+                    if (i < n)
+                        for (int c = j; c < nx1; c++) acc += sA[i + n * c] * Lc[c];
+                    else
+                        for (int c = j; c < nx1; c++) acc += bvec[c] * Lc[c];
+                    sAL[e] = acc;
+                }
+                sync();
+                // Pb = Lxx * (Lxx' b)
+                {
+                    double *Pb = wk + s.w_Pb;
+                    for (int i = tid; i < nx1; i += NT)
+                    {
+                        double acc = 0.0;
+                        for (int j = 0; j <= i; j++) acc += sM[(nu1 + i) + n1 * (nu1 + j)] * sAL[n + ldal * j];
+                        Pb[i] = acc;
+                    }
+                }
+                sync();
+                for (int j = tid; j < nx1; j += NT) sAL[n + ldal * j] += lrow1[nu1 + j];
+                sync();
+            }
+            else
+                sync();
+            // ---- M = tril(H) + reg I, row = res_g
+            {
+                const double *H = qp + s.q_RSQ;
+                for (int e = tid; e < n * n; e += NT)
+                {
+                    const int j = e / n, i = e - j * n;
+                    sM[e] = i > j ? H[e] : (i == j ? H[e] + o.reg_prim : 0.0);
+                }
+                cp(row, rg(0, s), n);
+                if (ng > 0) cp(sC, qp + s.q_DCt, n * ng);
+            }
+            if (ns > 0)
+            {
+                sync();
+                cond_slacks(s, 1, Gam, gam, rg(0, s) + n, Zi, ds, tmp0, tmp1);
+                sync();
+                cp(wk + s.w_Zsi, Zi, 2 * ns);
+                cp(wk + s.step.ux + n, ds, 2 * ns);
+            }
+            else
+            {
+                sync();
+                for (int i = tid; i < nbg; i += NT)
+                {
+                    tmp0[i] = Gam[i] + Gam[nbg + i];
+                    tmp1[i] = gam[i] - gam[nbg + i];
+                }
+            }
+            sync();
+            if (!s.dup_idxb)
+                for (int i = tid; i < nb; i += NT)
+                {
+                    const int ix = idxb[i];
+                    sM[ix + n * ix] += tmp0[i];
+                    row[ix] += tmp1[i];
+                }
+            else if (tid == 0)
+                for (int i = 0; i < nb; i++)
+                {
+                    const int ix = idxb[i];
+                    sM[ix + n * ix] += tmp0[i];
+                    row[ix] += tmp1[i];
+                }
+            sync();
+            // ---- M += AL AL' + C diag(tmp0) C' (lower), row += ALrow AL' + tmp1' C'   (SYRK part of SYRK_POTRF_LN_MN)
+            {
+                const int kc = k < N ? nx1 : 0;
+                for_lower_plus_row(n, [&](int i, int j) {
+                    double acc = 0.0;
+                    for (int c = 0; c < kc; c++) acc += sAL[i + ldal * c] * sAL[j + ldal * c];
+                    if (i < n)
+                    {
+                        for (int g = 0; g < ng; g++) acc += sC[i + n * g] * tmp0[nb + g] * sC[j + n * g];
+                        sM[i + n * j] += acc;
+                    }
+                    else
+                    {
+                        for (int g = 0; g < ng; g++) acc += tmp1[nb + g] * sC[j + n * g];
+                        row[j] += acc;
+                    }
+                });
+            }
+            sync();
+            // ---- Cholesky with the extra row carried along (POTRF part; pivot rule blasfeo_ref/x_lapack_ref.c:84-91)
+            for (int j = 0; j < n; j++)
+            {
+                for (int i = j + tid; i <= n; i += NT)
+                {
+                    double acc;
+                    if (i < n)
+                    {
+                        acc = sM[i + n * j];
+                        for (int c = 0; c < j; c++) acc -= sM[i + n * c] * sM[j + n * c];
+                    }
+                    else
+                    {
+                        acc = row[j];
+                        for (int c = 0; c < j; c++) acc -= row[c] * sM[j + n * c];
+                    }
+                    tcol[i] = acc;
+                }
+                sync();
+                const double piv = tcol[j];
+                const double inv = piv > 0.0 ? 1.0 / sqrt(piv) : 0.0;
+                for (int i = j + tid; i <= n; i += NT)
+                {
+                    const double v = tcol[i] * inv;
+                    if (i < n) sM[i + n * j] = v;
+                    else row[j] = v;
+                }
+                if (tid == 0) Linv[j] = inv;
+                sync();
+            }
+            // ---- keep the factor
+            cp(wk + s.w_L, sM, n * n);
+            cp(wk + s.w_Linv, Linv, n);
+            cp(wk + s.w_lrow, row, n);
+            for (int i = tid; i < n; i += NT) lrow1[i] = row[i];
+            sync();
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // backward substitution with an existing factorisation (OCP_QP_SOLVE_KKT_STEP, x_ocp_qp_kkt.c:1582-1680)
+    // rhs residual set `rhs`, result (backward quantities) into step set `dst`.
+    // ---------------------------------------------------------------------------------------------
+    __device__ __noinline__ void solve_backward(int rhs, int dst, int use_Pb)
+    {
+        const int N = P.N;
+        double *v = sV, *gam = v + ev(P.nvsmax), *Gam = gam + ev(P.ncmax), *tmp0 = Gam + ev(P.ncmax);
+        double *tmp1 = tmp0 + ev(P.nbgmax), *Zi = tmp1 + ev(P.nbgmax), *ds = Zi + ev(2 * P.nsmax);
+        double *xprev = ds + ev(2 * P.nsmax), *tmpx = xprev + ev(P.nxmax), *tmpl = tmpx + ev(P.nxmax);
+        double *Linv = tmpl + ev(P.nxmax);
+        double *Lcur = sM, *Lnext = sAL;   // two factor buffers (Lnext only needed when !use_Pb)
+        for (int k = N; k >= 0; k--)
+        {
+            const StageDesc s = SD[k];
+            const int n = s.n, nu = s.nu, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1, nu1 = s.nu1, n1 = s.n1;
+            const int *idxb = ipool + s.idx_off;
+            const int nsolve = k == 0 ? n : nu;
+            if (!use_Pb && k < N)
+            {   // previous stage's factor becomes "next"
+                double *tt = Lcur; Lcur = Lnext; Lnext = tt;
+            }
+            cp(v, rg(rhs, s), n);
+            {
+                const double *gl = sol + s.sol.lam, *gt = sol + s.sol.t, *grd = rd(rhs, s), *grm = rm(rhs, s);
+                for (int i = tid; i < nc; i += NT)
+                {
+                    const double l = gl[i], ti = 1.0 / gt[i];
+                    Gam[i] = ti * l;      // t_lam_min==1 clipping only enters through the factorisation (COMPUTE_GAMMA_QP)
+                    gam[i] = ti * (grm[i] - l * grd[i]);
+                }
+            }
+            cp(Lcur, wk + s.w_L, n * nsolve);
+            cp(Linv, wk + s.w_Linv, n);
+            if (k < N) cp(sA, qp + s.q_BAt, n * nx1);
+            if (ng > 0) cp(sC, qp + s.q_DCt, n * ng);
+            if (ns > 0) cp(Zi, wk + s.w_Zsi, 2 * ns);
+            sync();
+            if (ns > 0)
+            {
+                if (o.t_lam_min == 1)
+                {   // Gamma used by the slack elimination must be the (clipped) one of the factorisation
+                    const double *gl = sol + s.sol.lam, *gt = sol + s.sol.t;
+                    const double t_min_inv = o.t_min > 0 ? 1.0 / o.t_min : 1e30;
+                    for (int i = tid; i < nc; i += NT)
+                    {
+                        const double l = gl[i], tt = gt[i];
+                        Gam[i] = (tt < o.t_min ? t_min_inv : 1.0 / tt) * (l < o.lam_min ? o.lam_min : l);
+                    }
+                    sync();
+                }
+                cond_slacks(s, 0, Gam, gam, rg(rhs, s) + n, Zi, ds, tmp0, tmp1);
+                sync();
+                cp(vux(dst, s) + n, ds, 2 * ns);
+            }
+            else
+                for (int i = tid; i < nbg; i += NT) tmp1[i] = gam[i] - gam[nbg + i];
+            sync();
+            if (!s.dup_idxb)
+                for (int i = tid; i < nb; i += NT) v[idxb[i]] += tmp1[i];
+            else if (tid == 0)
+                for (int i = 0; i < nb; i++) v[idxb[i]] += tmp1[i];
+            if (k < N)
+            {
+                if (use_Pb)
+                    for (int j = tid; j < nx1; j += NT) tmpx[j] = xprev[j] + (wk + s.w_Pb)[j];
+                else
+                {
+                    const double *b_ = rb(rhs, s);
+                    for (int j = tid; j < nx1; j += NT)
+                    {
+                        double acc = 0.0;
+                        for (int i = j; i < nx1; i++) acc += Lnext[(nu1 + i) + n1 * (nu1 + j)] * b_[i];
+                        tmpl[j] = acc;
+                    }
+                    sync();
+                    for (int i = tid; i < nx1; i += NT)
+                    {
+                        double acc = 0.0;
+                        for (int j = 0; j <= i; j++) acc += Lnext[(nu1 + i) + n1 * (nu1 + j)] * tmpl[j];
+                        tmpx[i] = acc + xprev[i];
+                    }
+                }
+            }
+            sync();
+            for (int i = tid; i < n; i += NT)
+            {
+                double acc = v[i];
+                for (int g = 0; g < ng; g++) acc += sC[i + n * g] * tmp1[nb + g];
+                for (int j = 0; j < nx1; j++) acc += sA[i + n * j] * tmpx[j];
+                v[i] = acc;
+            }
+            sync();
+            // TRSV_LNN(_MN): forward substitution on the first nsolve columns
+            if (tid < 32)
+            {
+                for (int j = 0; j < nsolve; j++)
+                {
+                    double part = 0.0;
+                    for (int c = tid; c < j; c += 32) part += Lcur[j + n * c] * v[c];
+                    part = wsum(part);
+                    if (tid == 0) v[j] = (v[j] - part) * Linv[j];
+                    __syncwarp();
+                }
+            }
+            sync();
+            for (int i = nsolve + tid; i < n; i += NT)
+            {
+                double acc = v[i];
+                for (int c = 0; c < nsolve; c++) acc -= Lcur[i + n * c] * v[c];
+                v[i] = acc;
+            }
+            sync();
+            cp(vux(dst, s), v, n);
+            for (int j = tid; j < s.nx; j += NT) xprev[j] = v[nu + j];
+            if (!use_Pb && k > 0)
+            {   // stage k-1 needs the xx block of this factor
+                sync();
+                cp(Lcur, wk + s.w_L, n * n);
+            }
+            sync();
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // forward sweep (x_ocp_qp_kkt.c:968-1006 / 1682-1722) + step of the constraint variables
+    // (:1176-1193, EXPAND_SLACKS :524-598, COMPUTE_LAM_T_QP x_core_qp_ipm_aux.c:164-189) + the
+    // ratio test (COMPUTE_ALPHA_QP :375-398).  after_fact: start from -lrow, pi = P x + p with p from lrow;
+    // else: start from the backward quantities stored in the step set, pi = p_backward + P x.
+    // Returns the step length alpha of this step set.
+    // ---------------------------------------------------------------------------------------------
+    __device__ __noinline__ double forward_pass(int rhs, int dst, int after_fact, int mask_out)
+    {
+        const int N = P.N;
+        double *v = sV, *x1 = v + ev(P.nvsmax), *tmp = x1 + ev(P.nxmax), *Linv = tmp + ev(P.nxmax);
+        double *p1 = Linv + ev(P.nmax), *Gam = p1 + ev(P.nxmax), *dt = Gam + ev(P.ncmax), *lam = dt + ev(P.ncmax);
+        double *Zi = lam + ev(P.ncmax), *ds = Zi + ev(2 * P.nsmax);
+        double *Lcur = sM, *Lnext = sAL;
+        double alpha = 1.0;
+        // stage 0 factor
+        {
+            const StageDesc s = SD[0];
+            cp(Lcur, wk + s.w_L, s.n * s.n);
+        }
+        for (int k = 0; k <= N; k++)
+        {
+            const StageDesc s = SD[k];
+            const int n = s.n, nu = s.nu, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1, nu1 = s.nu1, n1 = s.n1;
+            const int *idxb = ipool + s.idx_off, *rev = idxb + nb;
+            const int nsolve = k == 0 ? n : nu;
+            cp(Linv, wk + s.w_Linv, n);
+            {
+                const double *src = after_fact ? wk + s.w_lrow : vux(dst, s);
+                for (int i = tid; i < nsolve; i += NT) v[i] = -src[i];
+                // x part (k>0) was written into v by the previous stage
+            }
+            if (k < N)
+            {
+                const StageDesc s1 = SD[k + 1];
+                cp(sA, qp + s.q_BAt, n * nx1);
+                cp(Lnext, wk + s1.w_L, n1 * n1);
+                if (after_fact)
+                    for (int j = tid; j < nx1; j += NT) p1[j] = (wk + s1.w_lrow)[nu1 + j];
+                else
+                    for (int j = tid; j < nx1; j += NT) p1[j] = vux(dst, s1)[nu1 + j];   // backward value of x_{k+1}
+            }
+            if (ng > 0) cp(sC, qp + s.q_DCt, n * ng);
+            sync();
+            // TRSV_LTN(_MN): back substitution with the transposed factor on the first nsolve unknowns
+            if (tid < 32)
+            {
+                for (int j = nsolve - 1; j >= 0; j--)
+                {
+                    double part = 0.0;
+                    for (int i = j + 1 + tid; i < n; i += 32) part += Lcur[i + n * j] * v[i];
+                    part = wsum(part);
+                    if (tid == 0) v[j] = (v[j] - part) * Linv[j];
+                    __syncwarp();
+                }
+            }
+            sync();
+            cp(vux(dst, s), v, n);
+            if (k < N)
+            {
+                const double *b_ = rb(rhs, s);
+                for (int j = tid; j < nx1; j += NT)
+                {
+                    double acc = b_[j];
+                    for (int i = 0; i < n; i++) acc += sA[i + n * j] * v[i];
+                    x1[j] = acc;
+                }
+                sync();
+                for (int j = tid; j < nx1; j += NT)
+                {
+                    double acc = 0.0;
+                    for (int i = j; i < nx1; i++) acc += Lnext[(nu1 + i) + n1 * (nu1 + j)] * x1[i];
+                    tmp[j] = after_fact ? acc + p1[j] : acc;
+                }
+                sync();
+                double *pi = vpi(dst, s);
+                for (int i = tid; i < nx1; i += NT)
+                {
+                    double acc = 0.0;
+                    for (int j = 0; j <= i; j++) acc += Lnext[(nu1 + i) + n1 * (nu1 + j)] * tmp[j];
+                    pi[i] = after_fact ? acc : acc + p1[i];
+                }
+            }
+            // ---- constraint part of the step at this stage
+            {
+                const double *gl = sol + s.sol.lam, *gt = sol + s.sol.t;
+                for (int i = tid; i < nc; i += NT)
+                {
+                    const double l = gl[i], tt = gt[i];
+                    lam[i] = l;
+                    Gam[i] = (1.0 / tt) * l;
+                }
+                if (ns > 0 && o.t_lam_min == 1)
+                {
+                    const double t_min_inv = o.t_min > 0 ? 1.0 / o.t_min : 1e30;
+                    for (int i = tid; i < nc; i += NT)
+                    {
+                        const double l = gl[i], tt = gt[i];
+                        Gam[i] = (tt < o.t_min ? t_min_inv : 1.0 / tt) * (l < o.lam_min ? o.lam_min : l);
+                    }
+                }
+                for (int i = tid; i < nbg; i += NT)
+                {
+                    double a;
+                    if (i < nb) a = v[idxb[i]];
+                    else
+                    {
+                        a = 0.0;
+                        for (int r = 0; r < n; r++) a += sC[r + n * (i - nb)] * v[r];
+                    }
+                    dt[i] = a;
+                    dt[nbg + i] = -a;
+                }
+                if (ns > 0)
+                {
+                    cp(Zi, wk + s.w_Zsi, 2 * ns);
+                    cp(ds, vux(dst, s) + n, 2 * ns);
+                    sync();
+                    for (int j = tid; j < 2 * ns; j += NT)
+                    {
+                        const int jj = j < ns ? j : j - ns, offc = j < ns ? 0 : nbg;
+                        double d = ds[j];
+                        for (int i = 0; i < nbg; i++)
+                            if (rev[i] == jj) d += Gam[offc + i] * dt[offc + i];
+                        d = -Zi[j] * d;
+                        ds[j] = d;
+                        dt[2 * nbg + j] = d;
+                    }
+                    sync();
+                    for (int i = tid; i < 2 * nbg; i += NT)
+                    {
+                        const int up = i >= nbg, ii = up ? i - nbg : i;
+                        if (rev[ii] >= 0) dt[i] += ds[(up ? ns : 0) + rev[ii]];
+                    }
+                    cp(vux(dst, s) + n, ds, 2 * ns);
+                }
+                sync();
+                const double *grd = rd(rhs, s), *grm = rm(rhs, s), *gm = qp + s.q_dmask;
+                double *odl = vlam(dst, s), *odt = vt(dst, s);
+                for (int i = tid; i < nc; i += NT)
+                {
+                    const double l = lam[i], tt = gt[i], ti = 1.0 / tt, rdi = grd[i];
+                    double dl = -ti * (grm[i] + (l * dt[i]) - (l * rdi));
+                    double dti = dt[i] - rdi;
+                    if (mask_constr && mask_out)
+                    {
+                        const double mk = gm[i];
+                        dl *= mk;
+                        dti *= mk;
+                    }
+                    odl[i] = dl;
+                    odt[i] = dti;
+                    if (dst == 1)
+                    {   // ratio test on the main step (min over constraints, see COMPUTE_ALPHA_QP)
+                        if (l + dl < 0.0) alpha = fmin(alpha, -l / dl);
+                        if (tt + dti < 0.0) alpha = fmin(alpha, -tt / dti);
+                    }
+                }
+            }
+            sync();
+            if (k < N)
+            {
+                for (int j = tid; j < nx1; j += NT) v[nu1 + j] = x1[j];
+                double *tt = Lcur; Lcur = Lnext; Lnext = tt;
+            }
+            sync();
+        }
+        return rmin(alpha);
+    }
+
+    // step length of the main step from global memory (after iterative refinement changed it)
+    __device__ __noinline__ double alpha_pass()
+    {
+        double alpha = 1.0;
+        for (int k = 0; k <= P.N; k++)
+        {
+            const StageDesc s = SD[k];
+            const double *l = sol + s.sol.lam, *t = sol + s.sol.t, *dl = wk + s.step.lam, *dt = wk + s.step.t;
+            for (int i = tid; i < s.nc; i += NT)
+            {
+                if (l[i] + dl[i] < 0.0) alpha = fmin(alpha, -l[i] / dl[i]);
+                if (t[i] + dt[i] < 0.0) alpha = fmin(alpha, -t[i] / dt[i]);
+            }
+        }
+        return rmin(alpha);
+    }
+
+    // COMPUTE_MU_AFF_QP (x_core_qp_ipm_aux.c:636-668)
+    __device__ __noinline__ double mu_aff_pass(double alpha)
+    {
+        double acc = 0.0;
+        for (int k = 0; k <= P.N; k++)
+        {
+            const StageDesc s = SD[k];
+            const double *l = sol + s.sol.lam, *t = sol + s.sol.t, *dl = wk + s.step.lam, *dt = wk + s.step.t;
+            for (int i = tid; i < s.nc; i += NT) acc += fabs((l[i] + alpha * dl[i]) * (t[i] + alpha * dt[i]));
+        }
+        return rsum(acc) * nc_mask_inv;
+    }
+
+    // res_m updates of one IPM iteration (x_core_qp_ipm_aux.c:672-781):
+    // mode 0: bkp <- res_m; res_m <- bkp - tau_min      (affine direction)
+    // mode 1: res_m <- bkp + dt*dlam - sigma_mu         (centring + second-order correction)
+    // mode 2: res_m <- bkp - sigma_mu                   (pure centring)
+    __device__ __noinline__ void res_m_pass(int mode, double sigma_mu)
+    {
+        for (int k = 0; k <= P.N; k++)
+        {
+            const StageDesc s = SD[k];
+            double *m = rm(0, s), *bk = wk + s.w_rmb;
+            const double *dl = wk + s.step.lam, *dt = wk + s.step.t, *gm = qp + s.q_dmask;
+            for (int i = tid; i < s.nc; i += NT)
+            {
+                double r;
+                if (mode == 0)
+                {
+                    const double b = m[i];
+                    bk[i] = b;
+                    r = b - o.tau_min;
+                }
+                else if (mode == 1)
+                    r = bk[i] + dt[i] * dl[i] - sigma_mu;
+                else
+                    r = bk[i] - sigma_mu;
+                if (mask_constr) r *= gm[i];
+                m[i] = r;
+            }
+        }
+        sync();
+    }
+
+    // step <- step + itref
+    __device__ __noinline__ void add_itref()
+    {
+        for (int k = 0; k <= P.N; k++)
+        {
+            const StageDesc s = SD[k];
+            double *a = wk + s.step.ux;
+            const double *b = wk + s.itref.ux;
+            for (int i = tid; i < s.n + 2 * s.ns; i += NT) a[i] += b[i];
+            a = wk + s.step.pi; b = wk + s.itref.pi;
+            for (int i = tid; i < s.nx1; i += NT) a[i] += b[i];
+            a = wk + s.step.lam; b = wk + s.itref.lam;
+            for (int i = tid; i < s.nc; i += NT) a[i] += b[i];
+            a = wk + s.step.t; b = wk + s.itref.t;
+            for (int i = tid; i < s.nc; i += NT) a[i] += b[i];
+        }
+        sync();
+    }
+
+    // UPDATE_VAR_QP (x_core_qp_ipm_aux.c:472-582) + lam masking (x_ocp_qp_ipm.c:2672-2676)
+    __device__ __noinline__ void update_var(double alpha)
+    {
+        if (alpha < 1.0) alpha = alpha * ((1.0 - alpha) * 0.99 + alpha * 0.9999999);
+        for (int k = 0; k <= P.N; k++)
+        {
+            const StageDesc s = SD[k];
+            double *a = sol + s.sol.ux;
+            const double *b = wk + s.step.ux;
+            for (int i = tid; i < s.n + 2 * s.ns; i += NT) a[i] += alpha * b[i];
+            a = sol + s.sol.pi; b = wk + s.step.pi;
+            for (int i = tid; i < s.nx1; i += NT) a[i] += alpha * b[i];
+            double *l = sol + s.sol.lam, *t = sol + s.sol.t;
+            const double *dl = wk + s.step.lam, *dt = wk + s.step.t, *gm = qp + s.q_dmask;
+            for (int i = tid; i < s.nc; i += NT)
+            {
+                double ln = l[i] + alpha * dl[i], tn = t[i] + alpha * dt[i];
+                if (o.t_lam_min == 2)
+                {
+                    ln = ln <= o.lam_min ? o.lam_min : ln;
+                    tn = tn <= o.t_min ? o.t_min : tn;
+                }
+                if (mask_constr) ln *= gm[i];
+                l[i] = ln;
+                t[i] = tn;
+            }
+        }
+        sync();
+    }
+
+    // OCP_QP_INIT_VAR, var_init_scheme 1 (x_ocp_qp_ipm.c:1611-1760,1884-2022)
+    __device__ __noinline__ void init_var()
+    {
+        const double thr0 = 0.1;
+        const int N = P.N;
+        if (o.warm_start >= 2)
+        {
+            const double lmin = o.warm_start >= 3 ? o.lam0_min : thr0, tmin = o.warm_start >= 3 ? o.t0_min : thr0;
+            for (int k = 0; k <= N; k++)
+            {
+                const StageDesc s = SD[k];
+                double *l = sol + s.sol.lam, *t = sol + s.sol.t;
+                for (int i = tid; i < s.nc; i += NT)
+                {
+                    if (l[i] < lmin) l[i] = lmin;
+                    if (t[i] < tmin) t[i] = tmin;
+                }
+            }
+            sync();
+            return;
+        }
+        double *ux = sV, *tt = ux + ev(P.nvsmax), *cg = tt + ev(P.ncmax);
+        for (int k = 0; k <= N; k++)
+        {
+            const StageDesc s = SD[k];
+            const int n = s.n, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc;
+            const int *idxb = ipool + s.idx_off, *rev = idxb + nb;
+            const double *d = qp + s.q_d;
+            double *gux = sol + s.sol.ux, *gpi = sol + s.sol.pi, *gl = sol + s.sol.lam, *gt = sol + s.sol.t;
+            for (int i = tid; i < s.nx1; i += NT) gpi[i] = 0.0;
+            if (o.t0_init == 0 || o.t0_init == 1)
+            {
+                const double l0 = o.t0_init == 0 ? sqrt(o.mu0) : o.mu0, t0 = o.t0_init == 0 ? sqrt(o.mu0) : 1.0;
+                if (o.warm_start == 0)
+                    for (int i = tid; i < n + 2 * ns; i += NT) gux[i] = 0.0;
+                for (int i = tid; i < nc; i += NT) { gl[i] = l0; gt[i] = t0; }
+                continue;
+            }
+            for (int i = tid; i < n + 2 * ns; i += NT) ux[i] = o.warm_start == 0 ? 0.0 : gux[i];
+            sync();
+            for (int j = tid; j < 2 * ns; j += NT)
+            {
+                double tj = ux[n + j] - d[2 * nbg + j];
+                if (tj < thr0)
+                {
+                    tj = thr0;
+                    ux[n + j] = d[2 * nbg + j] + tj;
+                }
+                tt[2 * nbg + j] = tj;
+            }
+            sync();
+            // boxes: serial over constraints if an index repeats, else parallel
+            for (int j = (s.dup_idxb ? 0 : tid); j < nb && (!s.dup_idxb || tid == 0); j += (s.dup_idxb ? 1 : NT))
+            {
+                const int ix = idxb[j];
+                double tl = ux[ix], tu = -ux[ix];
+                if (ns > 0 && rev[j] != -1) { tl += ux[n + rev[j]]; tu += ux[n + ns + rev[j]]; }
+                tl -= d[j];
+                tu -= d[nbg + j];
+                if (tl < thr0)
+                {
+                    if (tu < thr0)
+                    {
+                        ux[ix] = 0.5 * (d[j] - d[nbg + j]);
+                        tl = thr0; tu = thr0;
+                    }
+                    else
+                    {
+                        tl = thr0;
+                        ux[ix] = d[j] + thr0;
+                    }
+                }
+                else if (tu < thr0)
+                {
+                    tu = thr0;
+                    ux[ix] = -d[nbg + j] - thr0;
+                }
+                tt[j] = tl;
+                tt[nbg + j] = tu;
+            }
+            sync();
+            if (ng > 0)
+            {
+                const double *Cm = qp + s.q_DCt;
+                for (int g = tid; g < ng; g += NT)
+                {
+                    double acc = 0.0;
+                    for (int i = 0; i < n; i++) acc += Cm[i + n * g] * ux[i];
+                    cg[g] = acc;
+                }
+                sync();
+                for (int g = tid; g < ng; g += NT)
+                {
+                    double tl = cg[g], tu = -cg[g];
+                    if (ns > 0 && rev[nb + g] != -1) { tl += ux[n + rev[nb + g]]; tu += ux[n + ns + rev[nb + g]]; }
+                    tl -= d[nb + g];
+                    tu -= d[nbg + nb + g];
+                    tt[nb + g] = thr0 > tl ? thr0 : tl;
+                    tt[nbg + nb + g] = thr0 > tu ? thr0 : tu;
+                }
+                sync();
+            }
+            for (int i = tid; i < n + 2 * ns; i += NT) gux[i] = ux[i];
+            for (int i = tid; i < nc; i += NT)
+            {
+                gt[i] = tt[i];
+                gl[i] = o.mu0 / tt[i];
+            }
+            sync();
+        }
+        sync();
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // driver (OCP_QP_IPM_SOLVE x_ocp_qp_ipm.c:2684-3120 + OCP_QP_IPM_DELTA_STEP :2208-2682)
+    // ---------------------------------------------------------------------------------------------
+    __device__ __noinline__ void solve(cuipm_info *info, double *stat)
+    {
+        const int N = P.N;
+        const int SM = CUIPM_STAT_M;
+        double res_max[4] = {0, 0, 0, 0}, mu = 0.0, obj = 0.0, gap = 0.0;
+        int lq_count = 0, status, iter = 0;
+        if (stat)
+            for (int i = tid; i < SM * (o.stat_max + 1); i += NT) stat[i] = 0.0;
+
+        // constraint mask census (x_ocp_qp_ipm.c:2774-2806)
+        int cnt = 0;
+        for (int k = 0; k <= N; k++)
+        {
+            const StageDesc s = SD[k];
+            const double *gm = qp + s.q_dmask;
+            for (int i = tid; i < s.nc; i += NT) cnt += gm[i] != 0.0;
+        }
+        const int nc_mask = (int) (rsum((double) cnt) + 0.5);
+        mask_constr = nc_mask < P.nct;
+        nc_mask_inv = nc_mask > 0 ? 1.0 / nc_mask : 0.0;
+
+        if (P.nct == 0 || nc_mask == 0)
+        {
+            // no (active) constraints: one Riccati pass on the QP data (OCP_QP_FACT_SOLVE_KKT_UNCONSTR, x_ocp_qp_kkt.c:39-137)
+            for (int k = 0; k <= N; k++)
+            {
+                const StageDesc s = SD[k];
+                double *l = sol + s.sol.lam, *t = sol + s.sol.t, *d_ = rd(0, s), *m_ = rm(0, s), *g_ = rg(0, s), *b_ = rb(0, s);
+                for (int i = tid; i < s.nc; i += NT) { l[i] = 0.0; t[i] = 1.0; d_[i] = 0.0; m_[i] = 0.0; }
+                for (int i = tid; i < s.n; i += NT) g_[i] = (qp + s.q_rq)[i];
+                for (int i = tid; i < 2 * s.ns; i += NT) g_[s.n + i] = (qp + s.q_z)[i];
+                for (int i = tid; i < s.nx1; i += NT) b_[i] = (qp + s.q_b)[i];
+            }
+            sync();
+            fact_backward();
+            forward_pass(0, 1, 1, 1);
+            for (int k = 0; k <= N; k++)
+            {
+                const StageDesc s = SD[k];
+                cp(sol + s.sol.ux, wk + s.step.ux, s.n + 2 * s.ns);
+                cp(sol + s.sol.pi, wk + s.step.pi, s.nx1);
+            }
+            sync();
+            res_pass(0, 0, -1, 0, mu, obj, gap, res_max);
+            const double u0 = sol[SD[0].sol.ux];
+            status = (u0 != u0) ? CUIPM_NAN_SOL : CUIPM_SUCCESS;
+        }
+        else
+        {
+            init_var();
+            if (mask_constr)
+            {
+                for (int k = 0; k <= N; k++)
+                {
+                    const StageDesc s = SD[k];
+                    double *l = sol + s.sol.lam;
+                    const double *gm = qp + s.q_dmask;
+                    for (int i = tid; i < s.nc; i += NT) l[i] *= gm[i];
+                }
+                sync();
+            }
+            double alpha = 1.0;
+            res_pass(0, 0, -1, 0, mu, obj, gap, res_max);
+            if (stat && 0 < o.stat_max && tid == 0)
+            {
+                stat[7] = res_max[0]; stat[8] = res_max[1]; stat[9] = res_max[2]; stat[10] = res_max[3];
+                stat[11] = gap; stat[12] = obj;
+            }
+            double res_m_tau = res_m_tau_norm();
+            int kk;
+            for (kk = 0; kk < o.iter_max && alpha > o.alpha_min
+                         && (res_max[0] > o.res_g_max || res_max[1] > o.res_b_max || res_max[2] > o.res_d_max
+                             || res_m_tau > o.res_m_max || gap > o.dual_gap_max);
+                 kk++)
+            {
+                double *st = (stat && kk + 1 < o.stat_max) ? stat + SM * (size_t) (kk + 1) : nullptr;
+                double nrm[4] = {0, 0, 0, 0}, dmy;
+                res_m_pass(0, 0.0);
+                fact_backward();
+                alpha = forward_pass(0, 1, 1, 1);
+                if (o.lq_fact == 1)
+                {
+                    res_pass(1, 1, 0, 1, dmy, dmy, dmy, nrm);
+                    const double g00 = (wk + SD[0].ires.g)[0];
+                    if ((nrm[0] == 0.0 && g00 != g00) || nrm[0] > 1e-5 || nrm[1] > 1e-5 || nrm[2] > 1e-5 || nrm[3] > 1e-5)
+                        lq_count++;
+                }
+                if (st && tid == 0) { st[0] = alpha; st[1] = alpha; }
+                int itref1 = 0;
+                if (o.pred_corr == 1)
+                {
+                    double mu_aff = mu_aff_pass(alpha);
+                    const double tmp = mu_aff / mu;
+                    const double sigma = tmp * tmp * tmp;
+                    double sigma_mu = sigma * mu;
+                    sigma_mu = sigma_mu > o.tau_min ? sigma_mu : o.tau_min;
+                    if (st && tid == 0) { st[2] = mu_aff; st[3] = sigma; }
+                    res_m_pass(1, sigma_mu);
+                    solve_backward(0, 1, 1);
+                    alpha = forward_pass(0, 1, 0, 1);
+                    if (o.cond_pred_corr == 1)
+                    {
+                        const double mu_aff0 = mu_aff;
+                        mu_aff = mu_aff_pass(alpha);
+                        if (mu_aff > 2.0 * mu_aff0)
+                        {
+                            res_m_pass(2, sigma_mu);
+                            solve_backward(0, 1, 1);
+                            alpha = forward_pass(0, 1, 0, 1);
+                        }
+                    }
+                    int iter_ref_step = 0;
+                    if (o.itref_corr_max > 0)
+                    {
+                        for (itref1 = 0; itref1 < o.itref_corr_max; itref1++)
+                        {
+                            res_pass(1, 1, 0, 1, dmy, dmy, dmy, nrm);
+                            if ((nrm[0] < o.res_g_max || nrm[0] < 1e-3 * res_max[0]) && (nrm[1] < o.res_b_max || nrm[1] < 1e-3 * res_max[1])
+                                && (nrm[2] < o.res_d_max || nrm[2] < 1e-3 * res_max[2]) && (nrm[3] < o.res_m_max || nrm[3] < 1e-3 * res_max[3]))
+                                break;
+                            solve_backward(1, 2, 0);
+                            forward_pass(1, 2, 0, 0);
+                            iter_ref_step = 1;
+                            add_itref();
+                        }
+                        if (itref1 == o.itref_corr_max) res_pass(1, 1, 0, 1, dmy, dmy, dmy, nrm);
+                        if (st && tid == 0) { st[16] = nrm[0]; st[17] = nrm[1]; st[18] = nrm[2]; st[19] = nrm[3]; }
+                    }
+                    if (iter_ref_step) alpha = alpha_pass();
+                    if (st && tid == 0) { st[4] = alpha; st[5] = alpha; }
+                }
+                if (st && tid == 0) st[15] = itref1;
+                update_var(alpha);
+                res_pass(0, 0, -1, 0, mu, obj, gap, res_max);
+                if (st && tid == 0)
+                {
+                    st[6] = mu; st[7] = res_max[0]; st[8] = res_max[1]; st[9] = res_max[2]; st[10] = res_max[3];
+                    st[11] = gap; st[12] = obj;
+                }
+                res_m_tau = res_m_tau_norm();
+            }
+            iter = kk;
+            if (kk == o.iter_max) status = CUIPM_MAX_ITER;
+            else if (alpha <= o.alpha_min) status = CUIPM_MIN_STEP;
+            else if (mu != mu) status = CUIPM_NAN_SOL;
+            else status = CUIPM_SUCCESS;
+        }
+        if (tid == 0)
+        {
+            info->status = status;
+            info->iter = iter;
+            for (int i = 0; i < 4; i++) info->res_max[i] = res_max[i];
+            info->mu = mu;
+            info->obj = obj;
+            info->dual_gap = gap;
+            info->lq_count = lq_count;
+            info->reserved = 0;
+        }
+    }
+
+    // || res_m - tau_min * d_mask ||_inf  (x_ocp_qp_ipm.c:3012-3014)
+    __device__ __noinline__ double res_m_tau_norm()
+    {
+        double m = 0.0;
+        int f = 0;
+        for (int k = 0; k <= P.N; k++)
+        {
+            const StageDesc s = SD[k];
+            const double *r = rm(0, s), *gm = qp + s.q_dmask;
+            for (int i = tid; i < s.nc; i += NT)
+            {
+                const double a = fabs(r[i] - o.tau_min * gm[i]);
+                m = fmax(m, a);
+                f |= (a != a);
+            }
+        }
+        return rmax_nan(m, f);
+    }
+};
+
+template <int W>
+__global__ void __launch_bounds__(32 * W) cuipm_solve_kernel(const LaunchArgs a)
+{
+    extern __shared__ __align__(16) double smem[];
+    __shared__ double sred[W > 1 ? W : 1];
+    __shared__ Ker<W> K;
+    if (threadIdx.x == 0)
+    {
+        K.P = a.P;
+        K.SD = a.sd;
+        K.ipool = a.ipool;
+        K.o = a.o;
+        K.sM = smem;
+        K.sA = K.sM + a.P.sm_M;
+        K.sAL = K.sA + a.P.sm_A;
+        K.sC = K.sAL + a.P.sm_AL;
+        K.sV = K.sC + a.P.sm_C;
+        K.sred = sred;
+    }
+    for (int q = blockIdx.x; q < a.nbatch; q += gridDim.x)
+    {
+        if (threadIdx.x == 0)
+        {
+            K.qp = a.qp + (size_t) q * a.P.qp_stride;
+            K.sol = a.sol + (size_t) q * a.P.sol_stride;
+            K.wk = a.work + (size_t) q * a.P.work_stride;
+        }
+        K.sync();
+        K.solve(a.info + q, a.stat ? a.stat + (size_t) q * CUIPM_STAT_M * (a.o.stat_max + 1) : nullptr);
+        K.sync();
+    }
+}
+
+}  // namespace
+
+size_t smem_bytes(const ProbDesc &P) { return sizeof(double) * (size_t) P.sm_total; }
+
+int max_warps() { return 4; }
+
+int launch_solve(const LaunchArgs &a, int warps, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t) stream_;
+    const size_t smem = smem_bytes(a.P);
+    const int grid = a.nbatch;
+    cudaError_t err;
+#define CUIPM_LAUNCH(WW)                                                                                           \
+    do {                                                                                                           \
+        err = cudaFuncSetAttribute(cuipm_solve_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
+        if (err != cudaSuccess) return (int) err;                                                                  \
+        cuipm_solve_kernel<WW><<<grid, 32 * WW, smem, stream>>>(a);                                                \
+    } while (0)
+    if (warps <= 1) CUIPM_LAUNCH(1);
+    else if (warps == 2) CUIPM_LAUNCH(2);
+    else CUIPM_LAUNCH(4);
+#undef CUIPM_LAUNCH
+    return (int) cudaGetLastError();
+}
+
+}  // namespace cuipm
