@@ -978,13 +978,16 @@ struct Ker
     {
         const double thr0 = 0.1;
         const int N = P.N;
+        // the reference's plugin zeroes the primal iterate before every solve, whatever warm_start says
+        // (acados/ocp_qp/ocp_qp_hpipm.c:333-336): warm starts carry over pi, lam and t only
         if (o.warm_start >= 2)
         {
             const double lmin = o.warm_start >= 3 ? o.lam0_min : thr0, tmin = o.warm_start >= 3 ? o.t0_min : thr0;
             for (int k = 0; k <= N; k++)
             {
                 const StageDesc s = SD[k];
-                double *l = sol + s.sol.lam, *t = sol + s.sol.t;
+                double *l = sol + s.sol.lam, *t = sol + s.sol.t, *gux = sol + s.sol.ux;
+                for (int i = tid; i < s.n + 2 * s.ns; i += NT) gux[i] = 0.0;
                 for (int i = tid; i < s.nc; i += NT)
                 {
                     if (l[i] < lmin) l[i] = lmin;
@@ -1006,12 +1009,11 @@ struct Ker
             if (o.t0_init == 0 || o.t0_init == 1)
             {
                 const double l0 = o.t0_init == 0 ? sqrt(o.mu0) : o.mu0, t0 = o.t0_init == 0 ? sqrt(o.mu0) : 1.0;
-                if (o.warm_start == 0)
-                    for (int i = tid; i < n + 2 * ns; i += NT) gux[i] = 0.0;
+                for (int i = tid; i < n + 2 * ns; i += NT) gux[i] = 0.0;
                 for (int i = tid; i < nc; i += NT) { gl[i] = l0; gt[i] = t0; }
                 continue;
             }
-            for (int i = tid; i < n + 2 * ns; i += NT) ux[i] = o.warm_start == 0 ? 0.0 : gux[i];
+            for (int i = tid; i < n + 2 * ns; i += NT) ux[i] = 0.0;
             sync();
             for (int j = tid; j < 2 * ns; j += NT)
             {
@@ -1133,6 +1135,11 @@ struct Ker
             }
             sync();
             res_pass(0, 0, -1, 0, mu, obj, gap, res_max);
+            if (stat && 0 < o.stat_max && tid == 0)
+            {   // column quirk of the reference's unconstrained branch (x_ocp_qp_ipm.c:2822-2829)
+                stat[6] = res_max[0]; stat[7] = res_max[1]; stat[8] = res_max[2]; stat[9] = res_max[3];
+                stat[10] = gap; stat[11] = obj;
+            }
             const double u0 = sol[SD[0].sol.ux];
             status = (u0 != u0) ? CUIPM_NAN_SOL : CUIPM_SUCCESS;
         }

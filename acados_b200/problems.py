@@ -309,14 +309,16 @@ def chain_mass(nbatch: int, n_mass: int = 5, N: int = 40, seed: int = 1234, Ts: 
     g[npos + 1::3] = -9.81 * 0.02                                                # gravity pull (y) on free masses
     b = np.broadcast_to(g * Ts, (nbatch, nx))
 
-    nbx = nf + 1 if soft else 0
+    nbx = nf + 1
+    nsl = nbx if soft else 0
     ypos = [nu + 3 * i + 1 for i in range(nf + 1)]                              # y of free masses and end mass
     nxs = [0] + [nx] * N
     nus = [nu] * N + [0]
     nbs = [nu] + [nu + nbx] * (N - 1) + [nbx]
-    nss = [0] + [nbx] * N
+    nss = [0] + [nsl] * N
     idxb = [list(range(nu))] + [list(range(nu)) + ypos] * (N - 1) + [[i - nu for i in ypos] if nbx else []]
-    rev = [[-1] * nu] + [[-1] * nu + list(range(nbx))] * (N - 1) + [list(range(nbx))]
+    srev = list(range(nbx)) if soft else [-1] * nbx
+    rev = [[-1] * nu] + [[-1] * nu + srev] * (N - 1) + [srev]
     shape = Shape(N, nxs, nus, nbs, [0] * (N + 1), nss, idxb, rev)
     lay = Layout(shape)
     qp = lay.new_qp(nbatch)
@@ -337,7 +339,7 @@ def chain_mass(nbatch: int, n_mass: int = 5, N: int = 40, seed: int = 1234, Ts: 
     R = np.eye(nu) * 0.01 * (1 + perturb * rng.uniform(-1, 1, (nbatch, 1, 1)))
     q = -(Q @ xref) + 0.02 * rng.standard_normal((nbatch, nx))
     r = 0.02 * rng.standard_normal((nbatch, nu))
-    wall = -0.1 - 0.05 * rng.uniform(0, 1, (nbatch, 1))
+    wall = (-0.1 if soft else -0.6) - 0.05 * rng.uniform(0, 1, (nbatch, 1))
     for k in range(N + 1):
         if k == 0:
             _set_cost(lay, qp, k, R=R, r=r)
@@ -353,13 +355,9 @@ def chain_mass(nbatch: int, n_mass: int = 5, N: int = 40, seed: int = 1234, Ts: 
         ub = np.concatenate([np.full(nuk, 1.0), np.full(nbx, 1e9)])
         ubm = np.concatenate([np.ones(nuk), np.zeros(nbx)])
         _set_box(lay, qp, k, lb, ub, ub_mask=ubm)
-        if nbx:
+        if nsl:
             lay.view(qp, "Z", k)[:] = 1e2
-            lay.view(qp, "z", k)[:] = 1.0
-            # slack lower bounds lls = lus = 0; the upper slack of a masked bound is itself masked
-            msk = lay.view(qp, "dmask", k)
-            nb_k = shape.nb[k]
-            msk[:, 2 * nb_k + nbx:2 * nb_k + 2 * nbx] = 0.0
+            lay.view(qp, "z", k)[:] = 1.0     # slack bounds lls = lus = 0 stay active
     return Batch(shape, lay, qp, f"chain_mass nx={nx} nu={nu} N={N}")
 
 
@@ -459,11 +457,11 @@ def named_config(name: str, nbatch: Optional[int] = None, seed: int = 1234) -> B
         return chain_mass(nbatch or 4096, seed=seed)
     if name == "c3":
         sh = random_shape(20, 4, 1, nbx=0)
-        return random_qp(sh, nbatch or 16384, seed=seed, umax=2.0, x0_scale=0.5)
+        return random_qp(sh, nbatch or 16384, seed=seed, umax=0.5, x0_scale=1.0)
     if name == "c4":
-        sh = random_shape(50, 12, 4, nbx=6)
-        return random_qp(sh, nbatch or 8192, seed=seed, umax=1.0, xmax=3.0, x0_scale=0.5)
+        sh = random_shape(50, 12, 4, nbx=6, ns=6)
+        return random_qp(sh, nbatch or 8192, seed=seed, umax=0.5, xmax=1.0, x0_scale=1.0)
     if name == "c5":
-        sh = random_shape(30, 48, 12, nbx=12)
-        return random_qp(sh, nbatch or 1024, seed=seed, umax=1.0, xmax=3.0, x0_scale=0.3)
+        sh = random_shape(30, 48, 12, nbx=12, ns=12)
+        return random_qp(sh, nbatch or 1024, seed=seed, umax=0.5, xmax=1.0, x0_scale=1.0)
     raise ValueError(name)

@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- OCP-QP solves/sec (fp64, batched) of the cuipm CUDA path on chain-mass nx=21 nu=3 N=40.
+
+Contract (see the task brief): ``python bench.py --gpus N --steps K --warmup W`` prints ONE JSON line on rank 0.
+A "step" is one pass of the hot path (the whole interior-point solve, one kernel launch) over one batch of
+synthetic QPs.  Per-GPU work is fixed (``--batch`` QPs per GPU, default 4096 = BASELINE.json configs[1]), so N>1
+is weak scaling; ranks are independent (the batch is the only sharding axis, no data-path collective).
+
+  value        whole-job QP solves/s with the QP records already resident in HBM, timed with CUDA events on the
+               solver's stream, max over ranks.
+  e2e          the same metric through the C-ABI call a plugin makes (cuipm_solve_host): pinned HOST buffers,
+               H2D of the QP records and D2H of the solutions inside the timed region.
+  roofline     HBM roofline of the solve kernel on algorithmic bytes.
+  cpu_baseline the unmodified reference (HPIPM+BLASFEO behind acados' qp_solver vtable, oracle/_ref) on the host
+               cores, bounded sample of the same workload.  ``--impl reference`` times only that arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "OCP-QP solves/sec (fp64, batch) chain-mass N=40"
+UNIT = "QP/s"
+
+
+def workload(batch: int, seed: int):
+    from acados_b200 import problems
+    return problems.chain_mass(batch, n_mass=5, N=40, seed=seed)
+
+
+def algorithmic_bytes_per_qp(b) -> dict:
+    """B_min = 8(|qp_in|+|qp_out|): every QP record is read at least once and its solution written once.
+    B_stream = per-iteration streaming model of SURVEY.md 8(d): qp_in + L written + 3 sweeps reading L and BAt."""
+    lay, sh = b.layout, b.shape
+    qp_in = sum(lay.size[f][k] for f in ("BAt", "RSQ", "DCt", "b", "rq", "d", "dmask", "Z", "z") for k in range(sh.N + 1))
+    qp_out = sum(lay.size[f][k] for f in ("ux", "pi", "lam", "t") for k in range(sh.N + 1))
+    L = sum(sh.nv(k) ** 2 for k in range(sh.N + 1))
+    BA = sum(lay.size["BAt"][k] for k in range(sh.N + 1))
+    return {"B_min": 8 * (qp_in + qp_out), "B_stream_iter": 8 * (qp_in + L + 3 * (L + BA))}
+
+
+def flops_per_qp(b, iters: float) -> float:
+    """F_QP = F_res + I * (F_fact + 2 F_solve + 2 F_res), SURVEY.md 8(d)."""
+    sh = b.shape
+    F_fact = F_solve = F_res = 0.0
+    for k in range(sh.N + 1):
+        nx, nu, n = sh.nx[k], sh.nu[k], sh.nv(k)
+        nx1 = sh.nx_next(k)
+        F_fact += 2 * (n + 1) * nx1 * nx1 / 2 + (n + 1) * n * nx1 + n ** 3 / 3.0 + 2 * sh.ng[k] * n * n
+        F_solve += 4 * n * nx1 + 2 * n * n + 4 * nx1 * nx1
+        F_res += 2 * n * n + 4 * n * nx1
+    return F_res + iters * (F_fact + 2 * F_solve + 2 * F_res)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.lines, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smmax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smmax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smmax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference(batch_obj, opts, nqp: int, threads: int = 0):
+    """Times the unmodified reference on the host cores on the first nqp QPs of the workload."""
+    from acados_b200.problems import Batch
+    from oracle import oracle_binding as ob
+    sub = Batch(batch_obj.shape, batch_obj.layout, np.ascontiguousarray(batch_obj.qp[:nqp]), batch_obj.name)
+    if ob.have_ref():
+        ob.ref_solve(Batch(sub.shape, sub.layout, sub.qp[:min(nqp, 64)].copy()), opts, nthreads=threads)  # warm-up
+        sol, info, tm = ob.ref_solve(sub, opts, nthreads=threads)
+        kind, secs, cores = "reference", tm["wall_s"], tm["threads"]
+    else:   # oracle port (only when oracle/_ref could not be built)
+        t0 = time.perf_counter()
+        sol, info = ob.oracle_solve(sub, opts, nthreads=threads)
+        secs, kind, cores = time.perf_counter() - t0, "port", threads or os.cpu_count()
+    return {"value": nqp / secs, "unit": UNIT, "cores": int(cores), "kind": kind,
+            "sample": f"{nqp} QPs of the workload, one solver object per OpenMP thread, wall clock incl. packing into the "
+                      f"reference's panel-major structs; mean IPM iterations {float(info['iter'].mean()):.2f}"}, sol, info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuipm", choices=["cuipm", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="QPs per GPU")
+    ap.add_argument("--warps", type=int, default=0, help="warps per QP (0 = solver default)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="QPs in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    steps, warmup = args.steps, max(args.warmup, 0)
+
+    from acados_b200.binding import INFO_DTYPE, default_opts
+    opts = default_opts()   # what PARTIAL_CONDENSING_HPIPM runs with out of the box
+    config = {"workload": f"chain-of-masses OCP-QP nx=21 nu=3 N=40 (after x0 elimination), nbu=3 hard + 4 one-sided soft "
+                          f"state bounds (ns=4), batch={args.batch} per GPU, every QP its own matrices",
+              "batch_per_gpu": args.batch, "global_batch": args.batch * max(world, 1), "parallelism": f"batch-sharded x{max(world,1)}",
+              "solver_opts": "acados defaults: BALANCE mode, iter_max=50, tol 1e-6/1e-8/1e-8/1e-8, mu0=1, cold start",
+              "l2": "inputs (1.5 GB per batch) exceed the 126 MB L2; no explicit flush"}
+
+    # ------------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sample = args.cpu_sample or min(args.batch, 1024)
+        b = workload(sample, seed=1234)
+        times = []
+        base = None
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            base, _, info = cpu_reference(b, opts, sample)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        # cpu_reference runs a 64-QP warm-up + the sample; use its own wall clock of the sample
+        val = base["value"]
+        line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+                "ms_per_step": 1e3 * sample / val, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "impl": "reference", "config": config,
+                "cpu_baseline": base, "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the cuipm path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from acados_b200.binding import CuipmSolver
+    b = workload(args.batch, seed=1234 + rank)
+    nb = b.nbatch
+    solver = CuipmSolver(b.shape, nb, device=local_rank)
+    if args.warps:
+        solver.set_tuning("warps", args.warps)
+    stream = torch.cuda.ExternalStream(solver.lib.cuipm_stream(solver.handle), device=torch.device("cuda", local_rank))
+
+    # pinned host buffers (the plugin's view) and device-resident copies (the kernel-only view)
+    h_qp = torch.from_numpy(b.qp).pin_memory()
+    h_sol = torch.zeros((nb, b.layout.sol_stride), dtype=torch.float64).pin_memory()
+    h_info = torch.zeros(nb * INFO_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+    d_qp = h_qp.cuda()
+    d_sol = torch.zeros((nb, b.layout.sol_stride), dtype=torch.float64, device="cuda")
+    d_info = torch.zeros(nb * INFO_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        solver.solve_device(nb, d_qp.data_ptr(), d_sol.data_ptr(), d_info.data_ptr(), opts, sync=False)
+
+    def step_host():
+        import ctypes as C
+        rc = solver.lib.cuipm_solve_host(solver.handle, nb, h_qp.data_ptr(), h_sol.data_ptr(), h_info.data_ptr(), None, C.byref(opts))
+        if rc != 0:
+            raise RuntimeError(solver.lib.cuipm_last_error().decode())
+
+    # ---- kernel-only: inputs resident in HBM
+    for _ in range(warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record()
+    kernel_ms = []
+    for _ in range(steps):
+        step_device()
+    with torch.cuda.stream(stream):
+        ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = ev0.elapsed_time(ev1)
+    # per-launch duration of the solve kernel (events recorded around each launch by the solver itself)
+    solver.solve_device(nb, d_qp.data_ptr(), d_sol.data_ptr(), d_info.data_ptr(), opts, sync=True)
+    kernel_ms = solver.last_kernel_ms
+    info = np.frombuffer(d_info.cpu().numpy().tobytes(), dtype=INFO_DTYPE)
+    iters_mean = float(info["iter"].mean())
+
+    # ---- end to end through the C-ABI host entry
+    for _ in range(max(1, min(warmup, 2))):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    hinfo = np.frombuffer(h_info.numpy().tobytes(), dtype=INFO_DTYPE)
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, kernel_ms = (float(x) for x in t.cpu())
+    total_qps = nb * world * steps
+    value = total_qps / (dev_ms * 1e-3)
+    e2e_value = total_qps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        ab = algorithmic_bytes_per_qp(b)
+        achieved = ab["B_min"] * nb / (kernel_ms * 1e-3) / 1e9
+        stream_gbs = ab["B_stream_iter"] * iters_mean * nb / (kernel_ms * 1e-3) / 1e9
+        tflops = flops_per_qp(b, iters_mean) * nb / (kernel_ms * 1e-3) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": traffic, "kernel": "cuipm_solve_kernel", "kernel_ms": kernel_ms,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
+                    "algorithmic_bytes_per_qp": ab["B_min"], "mean_ipm_iterations": iters_mean,
+                    "stream_model": {"bytes_per_qp": ab["B_stream_iter"] * iters_mean, "achieved_gbs": stream_gbs, "frac": stream_gbs / hbm_peak},
+                    "fp64": {"achieved_tflops": tflops, "nominal_peak_tflops": 40.0, "frac": tflops / 40.0}}
+        cpu = None
+        if not args.no_cpu:
+            try:
+                cpu, _, _ = cpu_reference(b, opts, args.cpu_sample or nb)
+            except Exception as e:  # noqa: BLE001
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(b.qp.nbytes) * world,
+                        "d2h_bytes_per_step": int(h_sol.numel() * 8 + h_info.numel()) * world, "ms_per_step": e2e_ms / steps},
+                "gpu_launches": steps * solver.last_launch_count,
+                "roofline": roofline, "cpu_baseline": cpu,
+                "solver": {"status_hist": np.bincount(hinfo["status"], minlength=5).tolist(), "iter_mean": iters_mean,
+                           "iter_max": int(info["iter"].max()), "lq_count": int(info["lq_count"].sum())}}
+        print(json.dumps(line))
+    solver.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -88,7 +88,7 @@ typedef struct cuipm_opts {
     int itref_pred_max;
     int itref_corr_max;
     int lq_fact;          /* 0: Cholesky only; 1: Cholesky, LQ when inaccurate; 2: always LQ */
-    int warm_start;       /* 0 cold; 1 keep ux guess (acados zeroes it); 2/3 keep lam,t (clipped) */
+    int warm_start;       /* 0/1 cold (the plugin zeroes ux, ocp_qp_hpipm.c:333-336); 2/3 keep pi,lam,t of `sol` (lam,t clipped) */
     int abs_form;         /* must be 0 (delta formulation) */
     int comp_dual_sol_eq; /* must be 1 */
     int comp_res_exit;    /* must be 1 */

@@ -847,6 +847,10 @@ static void init_var(work *w, const cuipm_opts *o)
 {
     const double thr0 = 0.1;
     int N = w->N;
+    /* the plugin zeroes the primal iterate before every solve, whatever warm_start says
+     * (acados/ocp_qp/ocp_qp_hpipm.c:333-336): warm starts carry over pi, lam and t only */
+    for (int k = 0; k <= N; k++)
+        for (int i = 0; i < w->nv[k] + 2 * w->ns[k]; i++) w->sol.ux[k][i] = 0.0;
     if (o->warm_start >= 2)
     {
         double lmin = o->warm_start >= 3 ? o->lam0_min : thr0, tmin = o->warm_start >= 3 ? o->t0_min : thr0;
@@ -858,9 +862,6 @@ static void init_var(work *w, const cuipm_opts *o)
             }
         return;
     }
-    if (o->warm_start == 0)
-        for (int k = 0; k <= N; k++)
-            for (int i = 0; i < w->nv[k] + 2 * w->ns[k]; i++) w->sol.ux[k][i] = 0.0;
     for (int k = 0; k < N; k++)
         for (int i = 0; i < w->nx[k + 1]; i++) w->sol.pi[k][i] = 0.0;
     if (o->t0_init == 0 || o->t0_init == 1)
@@ -982,6 +983,11 @@ static void solve_one(work *w, const cuipm_opts *o, cuipm_info *info, double *st
         }
         res_body(w, 0, &w->sol, 0, 0, &w->res, &mu, &obj, &gap);
         res_inf_norm(w, &w->res, res_max);
+        if (stat && 0 < o->stat_max)
+        {   /* column quirk of the reference's unconstrained branch (x_ocp_qp_ipm.c:2822-2829) */
+            stat[6] = res_max[0]; stat[7] = res_max[1]; stat[8] = res_max[2]; stat[9] = res_max[3];
+            stat[10] = gap; stat[11] = obj;
+        }
         info->status = isnan(w->sol.ux[0][0]) ? CUIPM_NAN_SOL : CUIPM_SUCCESS;
         info->iter = 0;
         goto fill;

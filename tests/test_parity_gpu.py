@@ -1,0 +1,176 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI, against
+ (a) the plain-C oracle on the same seeded records, (b) the committed golden vectors produced by the reference,
+ (c) the reference itself when oracle/_ref travelled, and (d) size-independent properties at BASELINE.json's sizes.
+Tolerance (north_star): |du|_inf <= 1e-10 on identical inputs, IPM iteration counts equal."""
+import os
+
+import numpy as np
+import pytest
+
+from acados_b200 import problems as P
+from acados_b200.binding import CuipmSolver, default_opts
+from test_oracle_vs_reference import CASES, GOLD, TOL_U
+
+pytestmark = pytest.mark.gpu
+
+
+def _solve(b, o, warps=None, **kw):
+    s = CuipmSolver(b.shape, b.nbatch)
+    if warps:
+        s.set_tuning("warps", warps)
+    out = s.solve(b.qp, o, **kw)
+    s.close()
+    return out
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("warps", [1, 2, 4])
+def test_cuda_matches_oracle(built, name, warps):
+    from oracle import oracle_binding as ob
+    b = CASES[name]()
+    o = default_opts()
+    sol, info, stat = _solve(b, o, warps, want_stat=True)
+    osol, oinfo, ostat = ob.oracle_solve(b, o, want_stat=True)
+    assert np.array_equal(info["iter"], oinfo["iter"]), (info["iter"], oinfo["iter"])
+    assert np.array_equal(info["status"], oinfo["status"])
+    assert np.array_equal(info["lq_count"] > 0, oinfo["lq_count"] > 0)
+    du = np.max(np.abs(b.layout.u_traj(sol) - b.layout.u_traj(osol)))
+    assert du <= TOL_U, du
+    assert np.max(np.abs(sol - osol)) <= 1e-6 * max(1.0, np.max(np.abs(osol)))
+    for q in range(b.nbatch):
+        it = info["iter"][q]
+        assert np.allclose(stat[q, :it + 1, :13], ostat[q, :it + 1, :13], rtol=1e-4, atol=1e-7)
+    assert np.allclose(info["obj"], oinfo["obj"], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", sorted(f[:-4] for f in os.listdir(GOLD) if f.endswith(".npz")))
+def test_cuda_matches_golden_reference_vectors(built, name):
+    g = np.load(os.path.join(GOLD, name + ".npz"), allow_pickle=False)
+    b = CASES[str(g["case"])]()
+    assert np.array_equal(np.asarray(b.qp[:, :64]), g["qp_head"])
+    sol, info = _solve(b, default_opts())
+    assert np.array_equal(info["iter"], g["iter"]) and np.array_equal(info["status"], g["status"])
+    assert np.max(np.abs(b.layout.u_traj(sol) - g["u"])) <= TOL_U
+
+
+def test_cuda_matches_reference_when_present(built):
+    from oracle import oracle_binding as ob
+    if not ob.have_ref():
+        pytest.skip("oracle/_ref did not travel")
+    b = P.chain_mass(64, seed=77)
+    o = default_opts()
+    sol, info = _solve(b, o)
+    rsol, rinfo, _ = ob.ref_solve(b, o)
+    ok = rinfo["lq_count"] == 0
+    assert ok.mean() > 0.9
+    assert np.array_equal(info["iter"][ok], rinfo["iter"][ok])
+    assert np.max(np.abs(b.layout.u_traj(sol) - b.layout.u_traj(rsol))[ok]) <= TOL_U
+
+
+@pytest.mark.parametrize("ws", [2, 3])
+def test_warm_start_parity(built, ws):
+    from oracle import oracle_binding as ob
+    b = P.chain_mass(8, N=12, seed=21)
+    sol0, _ = ob.oracle_solve(b, default_opts())
+    o = default_opts(warm_start=ws)
+    sol, info = _solve(b, o, sol0=sol0)
+    osol, oinfo = ob.oracle_solve(b, o, sol0=sol0)
+    assert np.array_equal(info["iter"], oinfo["iter"]) and np.array_equal(info["status"], oinfo["status"])
+    assert np.max(np.abs(b.layout.u_traj(sol) - b.layout.u_traj(osol))) <= (1e-9 if ws == 2 else 1e-7)
+
+
+def test_tight_tolerance_parity(built):
+    """Both solvers driven to 1e-12 residuals: solutions agree far below the 1e-10 bar (iteration count may flip by one)."""
+    from oracle import oracle_binding as ob
+    b = P.chain_mass(16, seed=9)
+    o = default_opts(res_g_max=1e-12, res_b_max=1e-12, res_d_max=1e-12, res_m_max=1e-12)
+    sol, info = _solve(b, o)
+    osol, oinfo = ob.oracle_solve(b, o)
+    assert np.max(np.abs(info["iter"] - oinfo["iter"])) <= 1
+    same = info["iter"] == oinfo["iter"]
+    assert np.max(np.abs(b.layout.u_traj(sol) - b.layout.u_traj(osol))[same]) <= 1e-11
+
+
+def test_full_size_properties_c2(built):
+    """BASELINE config 2 at full size (batch 4096): every instance converges, independently recomputed KKT
+    residuals are within the solver tolerances, results do not depend on the position in the batch, and a second
+    run is bit-identical."""
+    from oracle import oracle_binding as ob
+    b = P.chain_mass(4096, seed=1234)
+    o = default_opts()
+    s = CuipmSolver(b.shape, b.nbatch)
+    sol, info = s.solve(b.qp, o)
+    assert (info["status"] == 0).all()
+    assert info["iter"].max() <= 30 and info["iter"].min() >= 3
+    r = ob.oracle_residuals(b, sol)
+    assert (r["res_max"][:, 0] <= o.res_g_max).all() and (r["res_max"][:, 1] <= o.res_b_max).all()
+    assert (r["res_max"][:, 2] <= o.res_d_max).all() and (r["res_max"][:, 3] <= o.res_m_max + 1e-9).all()
+    assert np.allclose(r["obj"], info["obj"], rtol=1e-10, atol=1e-10)
+    # spot-check a slice against the oracle
+    idx = np.arange(0, 4096, 128)
+    sub = P.Batch(b.shape, b.layout, np.ascontiguousarray(b.qp[idx]))
+    osol, oinfo = ob.oracle_solve(sub, o)
+    assert np.array_equal(info["iter"][idx], oinfo["iter"])
+    assert np.max(np.abs(b.layout.u_traj(sol[idx]) - b.layout.u_traj(osol))) <= TOL_U
+    # batch-position independence + determinism
+    perm = np.random.default_rng(0).permutation(4096)
+    sol_p, info_p = s.solve(np.ascontiguousarray(b.qp[perm]), o)
+    assert np.array_equal(sol_p, sol[perm]) and np.array_equal(info_p["iter"], info["iter"][perm])
+    sol2, _ = s.solve(b.qp, o)
+    assert np.array_equal(sol2, sol)
+    s.close()
+
+
+@pytest.mark.parametrize("name,nb", [("c3", 16384), ("c4", 2048), ("c5", 256)])
+def test_other_configs_at_size(built, name, nb):
+    from oracle import oracle_binding as ob
+    b = P.named_config(name, nb)
+    o = default_opts()
+    sol, info = _solve(b, o)
+    assert (info["status"] == 0).mean() > 0.98
+    idx = np.arange(0, nb, max(1, nb // 16))
+    sub = P.Batch(b.shape, b.layout, np.ascontiguousarray(b.qp[idx]))
+    osol, oinfo = ob.oracle_solve(sub, o)
+    assert np.array_equal(info["iter"][idx], oinfo["iter"])
+    assert np.max(np.abs(b.layout.u_traj(sol[idx]) - b.layout.u_traj(osol))) <= TOL_U
+
+
+def test_edge_cases(built):
+    from oracle import oracle_binding as ob
+    o = default_opts()
+    # empty batch, batch of one, horizon of one
+    s = CuipmSolver(P.mass_spring(1).shape, 4)
+    sol, info = s.solve(np.zeros((0, s.layout.qp_stride)), o)
+    assert sol.shape[0] == 0
+    with pytest.raises(RuntimeError):
+        s.solve(P.mass_spring(5).qp, o)      # larger than max_batch
+    s.close()
+    b = P.random_qp(P.random_shape(1, 3, 2, nbx=2), 3, seed=3, umax=0.5, xmax=3.0)
+    sol, info = _solve(b, o)
+    osol, oinfo = ob.oracle_solve(b, o)
+    assert np.array_equal(info["iter"], oinfo["iter"]) and np.max(np.abs(sol - osol)) < 1e-9
+    # iteration limit and unsupported options
+    b = P.chain_mass(4, N=8, seed=2)
+    sol, info = _solve(b, default_opts(iter_max=2))
+    assert (info["status"] == 1).all() and (info["iter"] == 2).all()
+    with pytest.raises(RuntimeError, match="not supported"):
+        _solve(b, default_opts("SPEED"))
+
+
+def test_riccati_getters(built):
+    """P, p, K, k, Lr of the last factorisation (reference getters ocp_qp_hpipm.c:417-478) on an unconstrained LQR:
+    u_0 = K_0 x_0 + k_0 must reproduce the solution and P must be symmetric positive definite."""
+    b = P.random_qp(P.random_shape(6, 4, 2, nbu=0, x0_eliminated=False), 2, seed=4)
+    s = CuipmSolver(b.shape, b.nbatch)
+    sol, info = s.solve(b.qp, default_opts())
+    for q in range(b.nbatch):
+        for k in range(0, 6):
+            nx, nu = b.shape.nx[k], b.shape.nu[k]
+            K = s.get_ric(q, "K", k, (nu, nx)); kk = s.get_ric(q, "k", k, (nu, 1)).ravel()
+            Pm = s.get_ric(q, "P", k, (nx, nx))
+            ux = b.layout.view(sol, "ux", k)[q]
+            assert np.allclose(K @ ux[nu:nu + nx] + kk, ux[:nu], atol=1e-9)
+            assert np.allclose(Pm, Pm.T) and (np.linalg.eigvalsh(Pm) > 0).all()
+            Lr = s.get_ric(q, "Lr", k, (nu, nu))
+            assert np.allclose(np.triu(Lr, 1), 0) and (np.diag(Lr) > 0).all()
+    s.close()
