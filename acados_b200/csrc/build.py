@@ -17,6 +17,8 @@ HEADERS = ["cuipm_device.h", "cuipm_internal.h", os.path.join(ROOT, "include", "
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "-I" + os.path.join(ROOT, "include"), "-I" + HERE]
+if os.environ.get("CUIPM_PROFILE"):
+    FLAGS.append("-DCUIPM_PROFILE")   # per-pass cycle counters into the last row of the stat table (development)
 
 
 def _newer(target: str, deps) -> bool:

@@ -37,6 +37,14 @@ struct Ker
     cuipm_opts o;
     int mask_constr;
     double nc_mask_inv;
+#ifdef CUIPM_PROFILE
+    long long prof[16];   // cycles per pass kind (thread 0): 0 res, 1 res_lin, 2 fact_backward, 3 forward, 4 solve_backward, 5 vector passes
+#define PROF_T0() long long t0_ = clock64()
+#define PROF_ADD(slot) do { if (tid == 0) prof[slot] += clock64() - t0_; t0_ = clock64(); } while (0)
+#else
+#define PROF_T0() do {} while (0)
+#define PROF_ADD(slot) do {} while (0)
+#endif
 
     // ---- CTA primitives -------------------------------------------------------------------------
     __device__ __forceinline__ void sync()
@@ -1099,6 +1107,10 @@ struct Ker
         int lq_count = 0, status, iter = 0;
         if (stat)
             for (int i = tid; i < SM * (o.stat_max + 1); i += NT) stat[i] = 0.0;
+#ifdef CUIPM_PROFILE
+        if (tid == 0)
+            for (int i = 0; i < 16; i++) prof[i] = 0;
+#endif
 
         // constraint mask census (x_ocp_qp_ipm.c:2774-2806)
         int cnt = 0;
@@ -1173,12 +1185,17 @@ struct Ker
             {
                 double *st = (stat && kk + 1 < o.stat_max) ? stat + SM * (size_t) (kk + 1) : nullptr;
                 double nrm[4] = {0, 0, 0, 0}, dmy;
+                PROF_T0();
                 res_m_pass(0, 0.0);
+                PROF_ADD(5);
                 fact_backward();
+                PROF_ADD(2);
                 alpha = forward_pass(0, 1, 1, 1);
+                PROF_ADD(3);
                 if (o.lq_fact == 1)
                 {
                     res_pass(1, 1, 0, 1, dmy, dmy, dmy, nrm);
+                    PROF_ADD(1);
                     const double g00 = (wk + SD[0].ires.g)[0];
                     if ((nrm[0] == 0.0 && g00 != g00) || nrm[0] > 1e-5 || nrm[1] > 1e-5 || nrm[2] > 1e-5 || nrm[3] > 1e-5)
                         lq_count++;
@@ -1194,8 +1211,11 @@ struct Ker
                     sigma_mu = sigma_mu > o.tau_min ? sigma_mu : o.tau_min;
                     if (st && tid == 0) { st[2] = mu_aff; st[3] = sigma; }
                     res_m_pass(1, sigma_mu);
+                    PROF_ADD(5);
                     solve_backward(0, 1, 1);
+                    PROF_ADD(4);
                     alpha = forward_pass(0, 1, 0, 1);
+                    PROF_ADD(3);
                     if (o.cond_pred_corr == 1)
                     {
                         const double mu_aff0 = mu_aff;
@@ -1212,7 +1232,9 @@ struct Ker
                     {
                         for (itref1 = 0; itref1 < o.itref_corr_max; itref1++)
                         {
+                            PROF_ADD(5);
                             res_pass(1, 1, 0, 1, dmy, dmy, dmy, nrm);
+                            PROF_ADD(1);
                             if ((nrm[0] < o.res_g_max || nrm[0] < 1e-3 * res_max[0]) && (nrm[1] < o.res_b_max || nrm[1] < 1e-3 * res_max[1])
                                 && (nrm[2] < o.res_d_max || nrm[2] < 1e-3 * res_max[2]) && (nrm[3] < o.res_m_max || nrm[3] < 1e-3 * res_max[3]))
                                 break;
@@ -1228,8 +1250,11 @@ struct Ker
                     if (st && tid == 0) { st[4] = alpha; st[5] = alpha; }
                 }
                 if (st && tid == 0) st[15] = itref1;
+                PROF_ADD(5);
                 update_var(alpha);
+                PROF_ADD(5);
                 res_pass(0, 0, -1, 0, mu, obj, gap, res_max);
+                PROF_ADD(0);
                 if (st && tid == 0)
                 {
                     st[6] = mu; st[7] = res_max[0]; st[8] = res_max[1]; st[9] = res_max[2]; st[10] = res_max[3];
@@ -1243,6 +1268,10 @@ struct Ker
             else if (mu != mu) status = CUIPM_NAN_SOL;
             else status = CUIPM_SUCCESS;
         }
+#ifdef CUIPM_PROFILE
+        if (stat && tid == 0)
+            for (int i = 0; i < 16; i++) stat[SM * (size_t) o.stat_max + i] = (double) prof[i];
+#endif
         if (tid == 0)
         {
             info->status = status;
