@@ -89,12 +89,18 @@ static int build_desc(cuipm_solver *s, const cuipm_shape *sh)
         const size_t nvs = (size_t) d.n + 2 * d.ns;
         auto take = [&](size_t n) { unsigned o = (unsigned) w; w += ev2u(n); return o; };
         // factor first (read by two sweeps per solve), then the vectors
+        d.q_stage = (unsigned) l->qp_stage[k];
+        d.q_stage_bytes = (unsigned) ((l->qp_stage[k + 1] - l->qp_stage[k]) * sizeof(double));
+        d.w_fac = (unsigned) w;
         d.w_L = take((size_t) d.n * d.n); d.w_Linv = take(d.n); d.w_lrow = take(d.n); d.w_Pb = take(d.nx1); d.w_Zsi = take(2 * d.ns);
+        d.w_fac_bytes = (unsigned) ((w - d.w_fac) * sizeof(double));
+        d.w_vec = (unsigned) w;
         d.step = VOff{take(nvs), take(d.nx1), take(d.nc), take(d.nc)};
         d.res = ROff{take(nvs), take(d.nx1), take(d.nc), take(d.nc)};
         d.w_rmb = take(d.nc);
         d.ires = ROff{take(nvs), take(d.nx1), take(d.nc), take(d.nc)};
         d.itref = VOff{take(nvs), take(d.nx1), take(d.nc), take(d.nc)};
+        d.w_vec_bytes = (unsigned) ((w - d.w_vec) * sizeof(double));
         P.nmax = std::max(P.nmax, d.n); P.nxmax = std::max(P.nxmax, std::max(d.nx, d.nx1)); P.ngmax = std::max(P.ngmax, d.ng);
         P.nsmax = std::max(P.nsmax, d.ns); P.nbgmax = std::max(P.nbgmax, d.nbg); P.ncmax = std::max(P.ncmax, d.nc);
         P.nvsmax = std::max(P.nvsmax, (int) nvs);
@@ -103,11 +109,13 @@ static int build_desc(cuipm_solver *s, const cuipm_shape *sh)
     if (w >= (size_t) 1 << 32 || l->qp_stride >= (size_t) 1 << 32) { set_error("QP record too large for 32-bit offsets"); return CUIPM_ERR_TOO_LARGE; }
     P.qp_stride = l->qp_stride; P.sol_stride = l->sol_stride; P.work_stride = w;
     auto e = [](int n) { return (n + 1) & ~1; };
-    P.sm_M = e(P.nmax * P.nmax);
-    P.sm_A = e(P.nmax * P.nxmax);
-    P.sm_AL = e(std::max((P.nmax + 1) * P.nxmax, P.nmax * P.nmax));
-    P.sm_C = e(P.nmax * P.ngmax);
-    P.sm_V = 3 * e(P.nvsmax) + 6 * e(P.nxmax) + 8 * e(P.ncmax) + 6 * e(P.nbgmax) + 6 * e(P.nmax + 1) + 8 * e(2 * P.nsmax) + 16;
+    // leading dimensions used on chip: nmax|1 (odd, conflict-free row/column access) or even(nmax+1) (factorisation:
+    // rows incl. the gradient row, 16-byte aligned column starts); both <= nmax+2
+    P.sm_M = e((P.nmax + 2) * P.nmax + 8);
+    P.sm_A = e((P.nmax + 2) * P.nxmax + 8);
+    P.sm_AL = e(std::max((P.nmax + 2) * (P.nxmax + P.ngmax), (P.nmax + 2) * P.nmax) + 8);
+    P.sm_C = P.ngmax > 0 ? 2 * e((P.nmax + 2) * P.ngmax) + 8 : 0;
+    P.sm_V = 5 * e(P.nvsmax) + 8 * e(P.nxmax) + 8 * e(P.ncmax) + 6 * e(P.nbgmax) + 8 * e(P.nmax + 1) + 8 * e(2 * P.nsmax) + 32;
     P.sm_total = P.sm_M + P.sm_A + P.sm_AL + P.sm_C + P.sm_V;
     if (smem_bytes(P) > 227 * 1024) { set_error("stage dimensions need more than 227 KB of shared memory"); return CUIPM_ERR_TOO_LARGE; }
     CK(cudaMalloc(&s->d_sd, sizeof(StageDesc) * (N + 1)));

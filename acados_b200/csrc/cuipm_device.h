@@ -24,6 +24,9 @@ struct StageDesc
     VOff sol, step, itref;
     ROff res, ires;
     unsigned w_rmb, w_L, w_Linv, w_lrow, w_Pb, w_Zsi;
+    unsigned q_stage, q_stage_bytes;      // this stage's sub-record inside the QP record (16-byte multiple)
+    unsigned w_fac, w_fac_bytes;          // factor part of the work record (L, Linv, lrow, Pb, Zs_inv)
+    unsigned w_vec, w_vec_bytes;          // vector part of the work record
 };
 
 struct ProbDesc

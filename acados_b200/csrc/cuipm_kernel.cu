@@ -161,6 +161,68 @@ struct Ker
         }
     }
 
+    // ---- asynchronous staging -------------------------------------------------------------------
+    __device__ __forceinline__ void cpa8(double *sdst, const double *gsrc)
+    {
+        const unsigned sa = (unsigned) __cvta_generic_to_shared(sdst);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc));
+    }
+    __device__ __forceinline__ void cpa_wait()
+    {
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    }
+    // column-major rows x cols block (ld = rows in global) -> shared with leading dimension ldd
+    __device__ __forceinline__ void cpa_mat(double *dst, int ldd, const double *src, int rows, int cols)
+    {
+        if (rows <= 0) return;
+        int e = tid, j = e / rows, i = e - j * rows;
+        const int tot = rows * cols;
+        for (; e < tot; e += NT)
+        {
+            cpa8(dst + i + ldd * j, src + e);
+            i += NT;
+            while (i >= rows) { i -= rows; j++; }
+        }
+    }
+    // symmetric matrix of which only the lower triangle is valid in global memory -> full matrix in shared
+    __device__ __forceinline__ void cpa_sym(double *dst, int ldd, const double *src, int n)
+    {
+        if (n <= 0) return;
+        int e = tid, j = e / n, i = e - j * n;
+        const int tot = n * n;
+        for (; e < tot; e += NT)
+        {
+            cpa8(dst + i + ldd * j, i >= j ? src + e : src + j + n * i);
+            i += NT;
+            while (i >= n) { i -= n; j++; }
+        }
+    }
+    __device__ __forceinline__ void cpa_vec(double *dst, const double *src, int n)
+    {
+        for (int i = tid; i < n; i += NT) cpa8(dst + i, src + i);
+    }
+    // L2 prefetch of a 16-byte-multiple chunk (TMA bulk prefetch), issued by one thread
+    __device__ __forceinline__ void prefetch_l2(const double *p, unsigned bytes)
+    {
+        if (tid == 0 && bytes)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+    }
+    // sum_c a[c*sa] * b[c*sb], 4 independent chains
+    __device__ __forceinline__ double dot(const double *a, int sa, const double *b, int sb, int len)
+    {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int c = 0;
+        for (; c + 3 < len; c += 4)
+        {
+            s0 += a[c * sa] * b[c * sb];
+            s1 += a[(c + 1) * sa] * b[(c + 1) * sb];
+            s2 += a[(c + 2) * sa] * b[(c + 2) * sb];
+            s3 += a[(c + 3) * sa] * b[(c + 3) * sb];
+        }
+        for (; c < len; c++) s0 += a[c * sa] * b[c * sb];
+        return (s0 + s1) + (s2 + s3);
+    }
+
     // ---------------------------------------------------------------------------------------------
     // residuals (restates OCP_QP_RES_COMPUTE / _LIN, external/hpipm/ocp_qp/x_ocp_qp_res.c:345-683)
     // lin==0: KKT residuals of the QP at point set `pset` -> residual set `out`; returns mu, obj, gap.
@@ -176,22 +238,29 @@ struct Ker
         double *ux = sV, *x1 = ux + ev(P.nvsmax), *pi = x1 + ev(P.nxmax), *pim = pi + ev(P.nxmax);
         double *lam = pim + ev(P.nxmax), *lamr = lam + ev(P.ncmax), *t = lamr + ev(P.ncmax), *msk = t + ev(P.ncmax);
         double *tmp0 = msk + ev(P.ncmax), *tmp1 = tmp0 + ev(P.nbgmax), *g_ = tmp1 + ev(P.nbgmax);
+        double *gv_ = g_ + ev(P.nvsmax), *bv_ = gv_ + ev(P.nvsmax);
         for (int k = 0; k <= N; k++)
         {
-            const StageDesc s = SD[k];
+            const StageDesc &s = SD[k];
             const int n = s.n, nu = s.nu, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1;
+            const int ld = n | 1;
             const int *idxb = ipool + s.idx_off, *rev = idxb + nb;
             const double *qk = qp;
-            // ---- stage data to shared memory
-            cp(ux, vux(pset, s), n + 2 * ns);
+            // ---- stage data to shared memory (asynchronous copies, all in flight together)
+            cpa_sym(sM, ld, qk + s.q_RSQ, n);
+            cpa_vec(ux, vux(pset, s), n + 2 * ns);
+            cpa_vec(gv_, rhs < 0 ? qk + s.q_rq : rg(rhs, s), n);
             if (k < N)
             {
-                const StageDesc s1 = SD[k + 1];
-                cp(x1, vux(pset, s1) + s1.nu, nx1);
-                cp(pi, vpi(pset, s), nx1);
-                cp(sA, qk + s.q_BAt, n * nx1);
+                const StageDesc &s1 = SD[k + 1];
+                cpa_mat(sA, ld, qk + s.q_BAt, n, nx1);
+                cpa_vec(x1, vux(pset, s1) + s1.nu, nx1);
+                cpa_vec(pi, vpi(pset, s), nx1);
+                cpa_vec(bv_, rhs < 0 ? qk + s.q_b : rb(rhs, s), nx1);
+                prefetch_l2(qk + s1.q_stage, s1.q_stage_bytes);
             }
-            if (k > 0) cp(pim, vpi(pset, SD[k - 1]), s.nx);
+            if (k > 0) cpa_vec(pim, vpi(pset, SD[k - 1]), s.nx);
+            if (ng > 0) cpa_mat(sC, ld, qk + s.q_DCt, n, ng);
             {
                 const double *gl = vlam(pset, s), *gt = vt(pset, s), *gm = qk + s.q_dmask;
                 for (int i = tid; i < nc; i += NT)
@@ -203,24 +272,19 @@ struct Ker
                     msk[i] = mk;
                 }
             }
-            cp(sM, qk + s.q_RSQ, n * n);
-            if (ng > 0) cp(sC, qk + s.q_DCt, n * ng);
+            cpa_wait();
             sync();
             for (int i = tid; i < nbg; i += NT) tmp0[i] = lam[nbg + i] - lam[i];
             sync();
-            // ---- rows of res_g, res_b and C'ux
-            const double *gvec = rhs < 0 ? qk + s.q_rq : rg(rhs, s);
-            const double *bvec = rhs < 0 ? qk + s.q_b : rb(rhs, s);
+            // ---- rows of res_g (lane = row), res_b and C'ux (lane = column)
             double *ob = rb(out, s);
             for (int oo = tid; oo < n + nx1 + ng; oo += NT)
             {
                 if (oo < n)
                 {
                     const int i = oo;
-                    double acc = 0.0;
-                    for (int j = 0; j <= i; j++) acc += sM[i + n * j] * ux[j];
-                    for (int j = i + 1; j < n; j++) acc += sM[j + n * i] * ux[j];
-                    const double gv = gvec[i];
+                    const double acc = dot(sM + i, ld, ux, 1, n);
+                    const double gv = gv_[i];
                     double r;
                     if (!lin)
                     {
@@ -232,16 +296,15 @@ struct Ker
                     else
                         r = acc + gv;
                     if (k > 0 && i >= nu) r -= pim[i - nu];
-                    for (int j = 0; j < nx1; j++) r += sA[i + n * j] * pi[j];
-                    for (int g = 0; g < ng; g++) r += sC[i + n * g] * tmp0[nb + g];
+                    r += dot(sA + i, ld, pi, 1, nx1);
+                    for (int g = 0; g < ng; g++) r += sC[i + ld * g] * tmp0[nb + g];
                     g_[i] = r;
                 }
                 else if (oo < n + nx1)
                 {
                     const int j = oo - n;
-                    double acc = 0.0;
-                    for (int i = 0; i < n; i++) acc += sA[i + n * j] * ux[i];
-                    const double bv = bvec[j];
+                    const double acc = dot(sA + ld * j, 1, ux, 1, n);
+                    const double bv = bv_[j];
                     const double r = bv - x1[j] + acc;
                     ob[j] = r;
                     const double a = fabs(r);
@@ -252,9 +315,7 @@ struct Ker
                 else
                 {
                     const int g = oo - n - nx1;
-                    double acc = 0.0;
-                    for (int i = 0; i < n; i++) acc += sC[i + n * g] * ux[i];
-                    tmp1[nb + g] = acc;
+                    tmp1[nb + g] = dot(sC + ld * g, 1, ux, 1, n);
                 }
             }
             sync();
@@ -412,22 +473,43 @@ struct Ker
     // ---------------------------------------------------------------------------------------------
     // backward Riccati sweep with factorisation (OCP_QP_FACT_SOLVE_KKT_STEP, x_ocp_qp_kkt.c:880-966)
     // rhs = residual set 0.  Writes L, Linv, lrow, Pb, Zs_inv (and the slack part of the step rhs).
+    //
+    // Thread r owns row r of the (n+1) x n stage block (row n carries the gradient).  Per stage:
+    //   [A; b'] -> sAL, then in place  AL = [A; b'] * Lxx_{k+1}         (TRMM_RLNN)
+    //   column tiles of 4:  acc = H + diag + AL AL' - (already factored columns)   (SYRK + left-looking POTRF)
+    //   the 4x4 diagonal block is factorised redundantly by every thread, the panel scaled, columns stored.
+    // sM holds L_{k+1} (rows 0..n1, row n1 = its gradient row) when the stage starts and L_k when it ends.
     // ---------------------------------------------------------------------------------------------
     __device__ __noinline__ void fact_backward()
     {
         const int N = P.N;
         double *Gam = sV, *gam = Gam + ev(P.ncmax), *tmp0 = gam + ev(P.ncmax), *tmp1 = tmp0 + ev(P.nbgmax);
-        double *row = tmp1 + ev(P.nbgmax), *Linv = row + ev(P.nmax), *lrow1 = Linv + ev(P.nmax);
-        double *bvec = lrow1 + ev(P.nmax), *Zi = bvec + ev(P.nxmax), *ds = Zi + ev(2 * P.nsmax);
-        double *tcol = ds + ev(2 * P.nsmax);
+        double *dadd = tmp1 + ev(P.nbgmax), *rowv = dadd + ev(P.nmax), *Linv = rowv + ev(P.nmax);
+        double *Zi = Linv + ev(P.nmax), *ds = Zi + ev(2 * P.nsmax), *D = ds + ev(2 * P.nsmax);   // D: 4 x 4 diagonal block
+        double *sCb = sC + ev((P.nmax + 2) * P.ngmax);
+        int ldm_prev = 0;
         for (int k = N; k >= 0; k--)
         {
-            const StageDesc s = SD[k];
+            const StageDesc &s = SD[k];
             const int n = s.n, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1, nu1 = s.nu1, n1 = s.n1;
             const int *idxb = ipool + s.idx_off;
-            const int ldal = n + 1;
-            // ---- Gamma, gamma (COMPUTE_GAMMA_GAMMA_QP, x_core_qp_ipm_aux.c:38-86)
+            const int ldal = ev(n + 1), ldm = ev(n + 1);
+            const int kc = k < N ? nx1 : 0;
+            // ---- stage inputs: [A; b'] into sAL (asynchronous), constraint quantities
+            if (k < N)
             {
+                cpa_mat(sAL, ldal, qp + s.q_BAt, n, nx1);
+                const double *b_ = rb(0, s);
+                for (int j = tid; j < nx1; j += NT) cpa8(sAL + n + ldal * j, b_ + j);
+            }
+            if (k > 0)
+            {
+                const StageDesc &sp = SD[k - 1];
+                prefetch_l2(qp + sp.q_stage, sp.q_stage_bytes);
+                prefetch_l2(wk + sp.w_vec, sp.w_vec_bytes);
+            }
+            {
+                // Gamma, gamma (COMPUTE_GAMMA_GAMMA_QP, x_core_qp_ipm_aux.c:38-86)
                 const double *gl = sol + s.sol.lam, *gt = sol + s.sol.t, *grd = rd(0, s), *grm = rm(0, s);
                 const double t_min_inv = o.t_min > 0 ? 1.0 / o.t_min : 1e30;
                 for (int i = tid; i < nc; i += NT)
@@ -439,140 +521,241 @@ struct Ker
                         Gam[i] = ti * l;
                     gam[i] = ti * (grm[i] - l * grd[i]);
                 }
-            }
-            if (k < N)
-            {
-                // sM still holds L_{k+1}, lrow1 its last row
-                cp(sA, qp + s.q_BAt, n * nx1);
-                cp(bvec, rb(0, s), nx1);
-                sync();
-                // AL = [A; b'] * Lxx  (TRMM_RLNN)
-                for (int e = tid; e < ldal * nx1; e += NT)
+                const double *g_ = rg(0, s);
+                for (int i = tid; i < n; i += NT)
                 {
-                    const int j = e / ldal, i = e - j * ldal;
-                    double acc = 0.0;
-                    const double *Lc = sM + nu1 + n1 * (nu1 + j);
-                    if (i < n)
-                        for (int c = j; c < nx1; c++) acc += sA[i + n * c] * Lc[c];
-                    else
-                        for (int c = j; c < nx1; c++) acc += bvec[c] * Lc[c];
-                    sAL[e] = acc;
+                    dadd[i] = o.reg_prim;
+                    rowv[i] = g_[i];
                 }
-                sync();
-                // Pb = Lxx * (Lxx' b)
-                {
-                    double *Pb = wk + s.w_Pb;
-                    for (int i = tid; i < nx1; i += NT)
-                    {
-                        double acc = 0.0;
-                        for (int j = 0; j <= i; j++) acc += sM[(nu1 + i) + n1 * (nu1 + j)] * sAL[n + ldal * j];
-                        Pb[i] = acc;
-                    }
-                }
-                sync();
-                for (int j = tid; j < nx1; j += NT) sAL[n + ldal * j] += lrow1[nu1 + j];
-                sync();
             }
-            else
-                sync();
-            // ---- M = tril(H) + reg I, row = res_g
-            {
-                const double *H = qp + s.q_RSQ;
-                for (int e = tid; e < n * n; e += NT)
-                {
-                    const int j = e / n, i = e - j * n;
-                    sM[e] = i > j ? H[e] : (i == j ? H[e] + o.reg_prim : 0.0);
-                }
-                cp(row, rg(0, s), n);
-                if (ng > 0) cp(sC, qp + s.q_DCt, n * ng);
-            }
+            sync();
             if (ns > 0)
             {
-                sync();
                 cond_slacks(s, 1, Gam, gam, rg(0, s) + n, Zi, ds, tmp0, tmp1);
                 sync();
-                cp(wk + s.w_Zsi, Zi, 2 * ns);
-                cp(wk + s.step.ux + n, ds, 2 * ns);
+                for (int j = tid; j < 2 * ns; j += NT)
+                {
+                    (wk + s.w_Zsi)[j] = Zi[j];
+                    (wk + s.step.ux + n)[j] = ds[j];
+                }
             }
             else
             {
-                sync();
                 for (int i = tid; i < nbg; i += NT)
                 {
                     tmp0[i] = Gam[i] + Gam[nbg + i];
                     tmp1[i] = gam[i] - gam[nbg + i];
                 }
+                sync();
             }
-            sync();
             if (!s.dup_idxb)
                 for (int i = tid; i < nb; i += NT)
                 {
                     const int ix = idxb[i];
-                    sM[ix + n * ix] += tmp0[i];
-                    row[ix] += tmp1[i];
+                    dadd[ix] += tmp0[i];
+                    rowv[ix] += tmp1[i];
                 }
             else if (tid == 0)
                 for (int i = 0; i < nb; i++)
                 {
                     const int ix = idxb[i];
-                    sM[ix + n * ix] += tmp0[i];
-                    row[ix] += tmp1[i];
+                    dadd[ix] += tmp0[i];
+                    rowv[ix] += tmp1[i];
                 }
+            cpa_wait();
             sync();
-            // ---- M += AL AL' + C diag(tmp0) C' (lower), row += ALrow AL' + tmp1' C'   (SYRK part of SYRK_POTRF_LN_MN)
+            if (k < N)
             {
-                const int kc = k < N ? nx1 : 0;
-                for_lower_plus_row(n, [&](int i, int j) {
-                    double acc = 0.0;
-                    for (int c = 0; c < kc; c++) acc += sAL[i + ldal * c] * sAL[j + ldal * c];
-                    if (i < n)
+                // ---- in place: AL = [A; b'] * Lxx   (row r, column tiles of 4; columns only read at c >= tile start)
+                const double *Lx = sM + nu1 + ldm_prev * nu1;       // Lxx(c, j) = Lx[c + ldm_prev*j], zero above the diagonal
+                for (int r = tid; r <= n; r += NT)
+                {
+                    double *arow = sAL + r;
+                    for (int jt = 0; jt < nx1; jt += 4)
                     {
-                        for (int g = 0; g < ng; g++) acc += sC[i + n * g] * tmp0[nb + g] * sC[j + n * g];
-                        sM[i + n * j] += acc;
+                        const int j1 = min(jt + 1, nx1 - 1), j2 = min(jt + 2, nx1 - 1), j3 = min(jt + 3, nx1 - 1);
+                        double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+                        for (int c = jt; c < nx1; c++)
+                        {
+                            const double a = arow[ldal * c];
+                            const double *Lc = Lx + c;
+                            c0 += a * Lc[ldm_prev * jt];
+                            c1 += a * Lc[ldm_prev * j1];
+                            c2 += a * Lc[ldm_prev * j2];
+                            c3 += a * Lc[ldm_prev * j3];
+                        }
+                        arow[ldal * jt] = c0;
+                        if (jt + 1 < nx1) arow[ldal * (jt + 1)] = c1;
+                        if (jt + 2 < nx1) arow[ldal * (jt + 2)] = c2;
+                        if (jt + 3 < nx1) arow[ldal * (jt + 3)] = c3;
+                    }
+                }
+                sync();
+                // Pb = Lxx * (Lxx' b),  then the gradient row gets l_{k+1}
+                {
+                    double *Pb = wk + s.w_Pb;
+                    for (int i = tid; i < nx1; i += NT) Pb[i] = dot(Lx + i, ldm_prev, sAL + n, ldal, i + 1);
+                }
+                sync();
+                for (int j = tid; j < nx1; j += NT) sAL[n + ldal * j] += sM[n1 + ldm_prev * (nu1 + j)];
+            }
+            if (ng > 0)
+            {
+                // general constraints enter the rank update as extra columns: own-row operand C diag(tmp0) (row n: tmp1),
+                // broadcast operand C
+                const double *Cg = qp + s.q_DCt;
+                for (int e = tid; e < (n + 1) * ng; e += NT)
+                {
+                    const int g = e / (n + 1), i = e - g * (n + 1);
+                    sAL[i + ldal * (kc + g)] = i < n ? Cg[i + n * g] * tmp0[nb + g] : tmp1[nb + g];
+                    if (i < n) sCb[i + ldal * g] = Cg[i + n * g];
+                }
+            }
+            sync();
+            // ---- column tiles: SYRK + left-looking Cholesky, rows r >= jt (row n = gradient row)
+            const double *Hg = qp + s.q_RSQ;
+            for (int jt = 0; jt < n; jt += 4)
+            {
+                const int w4 = min(4, n - jt);
+                for (int r = jt + tid; r <= n; r += NT)
+                {
+                    // init: H (lower, from global; issued first so the loads overlap the products below)
+                    double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0;
+                    if (r < n)
+                    {
+                        h0 = __ldg(Hg + r + n * jt);
+                        if (w4 > 1 && r >= jt + 1) h1 = __ldg(Hg + r + n * (jt + 1));
+                        if (w4 > 2 && r >= jt + 2) h2 = __ldg(Hg + r + n * (jt + 2));
+                        if (w4 > 3 && r >= jt + 3) h3 = __ldg(Hg + r + n * (jt + 3));
+                        if (r - jt < 4)
+                        {
+                            const double dd = dadd[r];
+                            if (r == jt) h0 += dd;
+                            else if (r == jt + 1) h1 += dd;
+                            else if (r == jt + 2) h2 += dd;
+                            else h3 += dd;
+                        }
                     }
                     else
                     {
-                        for (int g = 0; g < ng; g++) acc += tmp1[nb + g] * sC[j + n * g];
-                        row[j] += acc;
+                        h0 = rowv[jt];
+                        if (w4 > 1) h1 = rowv[jt + 1];
+                        if (w4 > 2) h2 = rowv[jt + 2];
+                        if (w4 > 3) h3 = rowv[jt + 3];
                     }
-                });
+                    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+                    {
+                        const double *own = sAL + r, *bc = sAL + jt;
+                        for (int c = 0; c < kc; c++)
+                        {
+                            const double a = own[ldal * c];
+                            const double2 b01 = *reinterpret_cast<const double2 *>(bc + ldal * c);
+                            const double2 b23 = *reinterpret_cast<const double2 *>(bc + ldal * c + 2);
+                            c0 += a * b01.x; c1 += a * b01.y; c2 += a * b23.x; c3 += a * b23.y;
+                        }
+                        const double *bcg = sCb + jt;
+                        for (int g = 0; g < ng; g++)
+                        {
+                            const double a = own[ldal * (kc + g)];
+                            c0 += a * bcg[ldal * g]; c1 += a * bcg[ldal * g + 1]; c2 += a * bcg[ldal * g + 2]; c3 += a * bcg[ldal * g + 3];
+                        }
+                    }
+                    {
+                        const double *own = sM + r, *bc = sM + jt;
+                        double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+                        for (int c = 0; c < jt; c++)
+                        {
+                            const double a = own[ldm * c];
+                            const double2 b01 = *reinterpret_cast<const double2 *>(bc + ldm * c);
+                            const double2 b23 = *reinterpret_cast<const double2 *>(bc + ldm * c + 2);
+                            e0 += a * b01.x; e1 += a * b01.y; e2 += a * b23.x; e3 += a * b23.y;
+                        }
+                        c0 -= e0; c1 -= e1; c2 -= e2; c3 -= e3;
+                    }
+                    c0 += h0; c1 += h1; c2 += h2; c3 += h3;
+                    // park the raw panel row (rows of the diagonal block are read back by everybody)
+                    double *mr = sM + r + ldm * jt;
+                    mr[0] = c0;
+                    if (w4 > 1) mr[ldm] = c1;
+                    if (w4 > 2) mr[2 * ldm] = c2;
+                    if (w4 > 3) mr[3 * ldm] = c3;
+                }
+                sync();
+                // ---- 4x4 diagonal block (pivot rule blasfeo_ref/x_lapack_ref.c:84-91), redundantly per thread
+                {
+                    const double *dg = sM + jt + ldm * jt;
+                    double d00 = dg[0], d10 = 0, d20 = 0, d30 = 0, d11 = 0, d21 = 0, d31 = 0, d22 = 0, d32 = 0, d33 = 0;
+                    if (w4 > 1) { d10 = dg[1]; d11 = dg[1 + ldm]; }
+                    if (w4 > 2) { d20 = dg[2]; d21 = dg[2 + ldm]; d22 = dg[2 + 2 * ldm]; }
+                    if (w4 > 3) { d30 = dg[3]; d31 = dg[3 + ldm]; d32 = dg[3 + 2 * ldm]; d33 = dg[3 + 3 * ldm]; }
+                    const double i0 = d00 > 0.0 ? rsqrt(d00) : 0.0;
+                    const double l10 = d10 * i0, l20 = d20 * i0, l30 = d30 * i0;
+                    d11 -= l10 * l10;
+                    const double i1 = d11 > 0.0 ? rsqrt(d11) : 0.0;
+                    const double l21 = (d21 - l20 * l10) * i1, l31 = (d31 - l30 * l10) * i1;
+                    d22 -= l20 * l20 + l21 * l21;
+                    const double i2 = d22 > 0.0 ? rsqrt(d22) : 0.0;
+                    const double l32 = (d32 - l30 * l20 - l31 * l21) * i2;
+                    d33 -= l30 * l30 + l31 * l31 + l32 * l32;
+                    const double i3 = d33 > 0.0 ? rsqrt(d33) : 0.0;
+                    sync();   // everybody has read the raw block before it is overwritten
+                    for (int r = jt + tid; r <= n; r += NT)
+                    {
+                        double *mr = sM + r + ldm * jt;
+                        const int rr = r - jt;     // position inside the panel: rows 0..3 form the diagonal block
+                        double x0 = mr[0] * i0;
+                        if (rr == 0) x0 = d00 * i0;
+                        mr[0] = x0;
+                        if (w4 > 1)
+                        {
+                            double x1 = rr == 0 ? 0.0 : (rr == 1 ? d11 * i1 : (mr[ldm] - x0 * l10) * i1);
+                            mr[ldm] = x1;
+                            if (w4 > 2)
+                            {
+                                double x2 = rr <= 1 ? 0.0 : (rr == 2 ? d22 * i2 : (mr[2 * ldm] - x0 * l20 - x1 * l21) * i2);
+                                mr[2 * ldm] = x2;
+                                if (w4 > 3)
+                                {
+                                    double x3 = rr <= 2 ? 0.0 : (rr == 3 ? d33 * i3 : (mr[3 * ldm] - x0 * l30 - x1 * l31 - x2 * l32) * i3);
+                                    mr[3 * ldm] = x3;
+                                }
+                            }
+                        }
+                    }
+                    if (tid == 0)
+                    {
+                        Linv[jt] = i0;
+                        if (w4 > 1) Linv[jt + 1] = i1;
+                        if (w4 > 2) Linv[jt + 2] = i2;
+                        if (w4 > 3) Linv[jt + 3] = i3;
+                    }
+                }
+                sync();
+            }
+            // rows above the diagonal inside a tile were written as zeros; rows r < jt of later tiles were never
+            // touched: clear the strict upper triangle so that Lxx can be used as a full matrix by the next stage
+            for (int e = tid; e < n * n; e += NT)
+            {
+                const int j = e / n, i = e - j * n;
+                if (i < j) sM[i + ldm * j] = 0.0;
             }
             sync();
-            // ---- Cholesky with the extra row carried along (POTRF part; pivot rule blasfeo_ref/x_lapack_ref.c:84-91)
-            for (int j = 0; j < n; j++)
+            // ---- keep the factor (global: column-major n x n, ld n)
             {
-                for (int i = j + tid; i <= n; i += NT)
+                double *Lg = wk + s.w_L;
+                for (int e = tid; e < n * n; e += NT)
                 {
-                    double acc;
-                    if (i < n)
-                    {
-                        acc = sM[i + n * j];
-                        for (int c = 0; c < j; c++) acc -= sM[i + n * c] * sM[j + n * c];
-                    }
-                    else
-                    {
-                        acc = row[j];
-                        for (int c = 0; c < j; c++) acc -= row[c] * sM[j + n * c];
-                    }
-                    tcol[i] = acc;
+                    const int j = e / n, i = e - j * n;
+                    Lg[e] = sM[i + ldm * j];
                 }
-                sync();
-                const double piv = tcol[j];
-                const double inv = piv > 0.0 ? 1.0 / sqrt(piv) : 0.0;
-                for (int i = j + tid; i <= n; i += NT)
+                double *lr = wk + s.w_lrow, *li = wk + s.w_Linv;
+                for (int j = tid; j < n; j += NT)
                 {
-                    const double v = tcol[i] * inv;
-                    if (i < n) sM[i + n * j] = v;
-                    else row[j] = v;
+                    lr[j] = sM[n + ldm * j];
+                    li[j] = Linv[j];
                 }
-                if (tid == 0) Linv[j] = inv;
-                sync();
             }
-            // ---- keep the factor
-            cp(wk + s.w_L, sM, n * n);
-            cp(wk + s.w_Linv, Linv, n);
-            cp(wk + s.w_lrow, row, n);
-            for (int i = tid; i < n; i += NT) lrow1[i] = row[i];
+            ldm_prev = ldm;
             sync();
         }
     }
@@ -587,54 +770,61 @@ struct Ker
         double *v = sV, *gam = v + ev(P.nvsmax), *Gam = gam + ev(P.ncmax), *tmp0 = Gam + ev(P.ncmax);
         double *tmp1 = tmp0 + ev(P.nbgmax), *Zi = tmp1 + ev(P.nbgmax), *ds = Zi + ev(2 * P.nsmax);
         double *xprev = ds + ev(2 * P.nsmax), *tmpx = xprev + ev(P.nxmax), *tmpl = tmpx + ev(P.nxmax);
-        double *Linv = tmpl + ev(P.nxmax);
+        double *Linv = tmpl + ev(P.nxmax), *pbv = Linv + ev(P.nmax);
         double *Lcur = sM, *Lnext = sAL;   // two factor buffers (Lnext only needed when !use_Pb)
+        int ld_next = 1;
         for (int k = N; k >= 0; k--)
         {
-            const StageDesc s = SD[k];
-            const int n = s.n, nu = s.nu, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1, nu1 = s.nu1, n1 = s.n1;
+            const StageDesc &s = SD[k];
+            const int n = s.n, nu = s.nu, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1, nu1 = s.nu1;
             const int *idxb = ipool + s.idx_off;
             const int nsolve = k == 0 ? n : nu;
+            const int ld = n | 1;
             if (!use_Pb && k < N)
             {   // previous stage's factor becomes "next"
                 double *tt = Lcur; Lcur = Lnext; Lnext = tt;
             }
-            cp(v, rg(rhs, s), n);
+            cpa_vec(v, rg(rhs, s), n);
+            cpa_mat(Lcur, ld, wk + s.w_L, n, nsolve);
+            cpa_vec(Linv, wk + s.w_Linv, n);
+            if (k < N)
+            {
+                cpa_mat(sA, ld, qp + s.q_BAt, n, nx1);
+                if (use_Pb) cpa_vec(pbv, wk + s.w_Pb, nx1);
+            }
+            if (ng > 0) cpa_mat(sC, ld, qp + s.q_DCt, n, ng);
+            if (ns > 0) cpa_vec(Zi, wk + s.w_Zsi, 2 * ns);
+            if (k > 0)
+            {
+                const StageDesc &sp = SD[k - 1];
+                prefetch_l2(qp + sp.q_stage, sp.q_stage_bytes);
+                prefetch_l2(wk + sp.w_fac, sp.w_fac_bytes);
+            }
             {
                 const double *gl = sol + s.sol.lam, *gt = sol + s.sol.t, *grd = rd(rhs, s), *grm = rm(rhs, s);
+                const double t_min_inv = o.t_min > 0 ? 1.0 / o.t_min : 1e30;
                 for (int i = tid; i < nc; i += NT)
                 {
-                    const double l = gl[i], ti = 1.0 / gt[i];
-                    Gam[i] = ti * l;      // t_lam_min==1 clipping only enters through the factorisation (COMPUTE_GAMMA_QP)
+                    const double l = gl[i], tt = gt[i], ti = 1.0 / tt;
+                    // the slack elimination needs the Gamma of the factorisation (clipped when t_lam_min==1)
+                    Gam[i] = (ns > 0 && o.t_lam_min == 1) ? (tt < o.t_min ? t_min_inv : ti) * (l < o.lam_min ? o.lam_min : l) : ti * l;
                     gam[i] = ti * (grm[i] - l * grd[i]);
                 }
             }
-            cp(Lcur, wk + s.w_L, n * nsolve);
-            cp(Linv, wk + s.w_Linv, n);
-            if (k < N) cp(sA, qp + s.q_BAt, n * nx1);
-            if (ng > 0) cp(sC, qp + s.q_DCt, n * ng);
-            if (ns > 0) cp(Zi, wk + s.w_Zsi, 2 * ns);
+            cpa_wait();
             sync();
             if (ns > 0)
             {
-                if (o.t_lam_min == 1)
-                {   // Gamma used by the slack elimination must be the (clipped) one of the factorisation
-                    const double *gl = sol + s.sol.lam, *gt = sol + s.sol.t;
-                    const double t_min_inv = o.t_min > 0 ? 1.0 / o.t_min : 1e30;
-                    for (int i = tid; i < nc; i += NT)
-                    {
-                        const double l = gl[i], tt = gt[i];
-                        Gam[i] = (tt < o.t_min ? t_min_inv : 1.0 / tt) * (l < o.lam_min ? o.lam_min : l);
-                    }
-                    sync();
-                }
                 cond_slacks(s, 0, Gam, gam, rg(rhs, s) + n, Zi, ds, tmp0, tmp1);
                 sync();
-                cp(vux(dst, s) + n, ds, 2 * ns);
+                double *o_ = vux(dst, s) + n;
+                for (int j = tid; j < 2 * ns; j += NT) o_[j] = ds[j];
             }
             else
+            {
                 for (int i = tid; i < nbg; i += NT) tmp1[i] = gam[i] - gam[nbg + i];
-            sync();
+                sync();
+            }
             if (!s.dup_idxb)
                 for (int i = tid; i < nb; i += NT) v[idxb[i]] += tmp1[i];
             else if (tid == 0)
@@ -642,31 +832,22 @@ struct Ker
             if (k < N)
             {
                 if (use_Pb)
-                    for (int j = tid; j < nx1; j += NT) tmpx[j] = xprev[j] + (wk + s.w_Pb)[j];
+                    for (int j = tid; j < nx1; j += NT) tmpx[j] = xprev[j] + pbv[j];
                 else
                 {
                     const double *b_ = rb(rhs, s);
-                    for (int j = tid; j < nx1; j += NT)
-                    {
-                        double acc = 0.0;
-                        for (int i = j; i < nx1; i++) acc += Lnext[(nu1 + i) + n1 * (nu1 + j)] * b_[i];
-                        tmpl[j] = acc;
-                    }
+                    const double *Lx = Lnext + nu1 + ld_next * nu1;
+                    for (int j = tid; j < nx1; j += NT) tmpl[j] = dot(Lx + j + ld_next * j, 1, b_ + j, 1, nx1 - j);
                     sync();
-                    for (int i = tid; i < nx1; i += NT)
-                    {
-                        double acc = 0.0;
-                        for (int j = 0; j <= i; j++) acc += Lnext[(nu1 + i) + n1 * (nu1 + j)] * tmpl[j];
-                        tmpx[i] = acc + xprev[i];
-                    }
+                    for (int i = tid; i < nx1; i += NT) tmpx[i] = dot(Lx + i, ld_next, tmpl, 1, i + 1) + xprev[i];
                 }
             }
             sync();
             for (int i = tid; i < n; i += NT)
             {
                 double acc = v[i];
-                for (int g = 0; g < ng; g++) acc += sC[i + n * g] * tmp1[nb + g];
-                for (int j = 0; j < nx1; j++) acc += sA[i + n * j] * tmpx[j];
+                for (int g = 0; g < ng; g++) acc += sC[i + ld * g] * tmp1[nb + g];
+                acc += dot(sA + i, ld, tmpx, 1, nx1);
                 v[i] = acc;
             }
             sync();
@@ -676,27 +857,27 @@ struct Ker
                 for (int j = 0; j < nsolve; j++)
                 {
                     double part = 0.0;
-                    for (int c = tid; c < j; c += 32) part += Lcur[j + n * c] * v[c];
+                    for (int c = tid; c < j; c += 32) part += Lcur[j + ld * c] * v[c];
                     part = wsum(part);
                     if (tid == 0) v[j] = (v[j] - part) * Linv[j];
                     __syncwarp();
                 }
             }
             sync();
-            for (int i = nsolve + tid; i < n; i += NT)
-            {
-                double acc = v[i];
-                for (int c = 0; c < nsolve; c++) acc -= Lcur[i + n * c] * v[c];
-                v[i] = acc;
-            }
+            for (int i = nsolve + tid; i < n; i += NT) v[i] -= dot(Lcur + i, ld, v, 1, nsolve);
             sync();
-            cp(vux(dst, s), v, n);
-            for (int j = tid; j < s.nx; j += NT) xprev[j] = v[nu + j];
+            {
+                double *o_ = vux(dst, s);
+                for (int i = tid; i < n; i += NT) o_[i] = v[i];
+                for (int j = tid; j < s.nx; j += NT) xprev[j] = v[nu + j];
+            }
             if (!use_Pb && k > 0)
             {   // stage k-1 needs the xx block of this factor
                 sync();
-                cp(Lcur, wk + s.w_L, n * n);
+                cpa_mat(Lcur, ld, wk + s.w_L, n, n);
+                cpa_wait();
             }
+            ld_next = ld;
             sync();
         }
     }
@@ -713,21 +894,22 @@ struct Ker
         const int N = P.N;
         double *v = sV, *x1 = v + ev(P.nvsmax), *tmp = x1 + ev(P.nxmax), *Linv = tmp + ev(P.nxmax);
         double *p1 = Linv + ev(P.nmax), *Gam = p1 + ev(P.nxmax), *dt = Gam + ev(P.ncmax), *lam = dt + ev(P.ncmax);
-        double *Zi = lam + ev(P.ncmax), *ds = Zi + ev(2 * P.nsmax);
+        double *Zi = lam + ev(P.ncmax), *ds = Zi + ev(2 * P.nsmax), *bv_ = ds + ev(2 * P.nsmax);
         double *Lcur = sM, *Lnext = sAL;
         double alpha = 1.0;
         // stage 0 factor
         {
-            const StageDesc s = SD[0];
-            cp(Lcur, wk + s.w_L, s.n * s.n);
+            const StageDesc &s = SD[0];
+            cpa_mat(Lcur, s.n | 1, wk + s.w_L, s.n, s.n);
         }
         for (int k = 0; k <= N; k++)
         {
-            const StageDesc s = SD[k];
-            const int n = s.n, nu = s.nu, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1, nu1 = s.nu1, n1 = s.n1;
+            const StageDesc &s = SD[k];
+            const int n = s.n, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1, nu1 = s.nu1, n1 = s.n1;
             const int *idxb = ipool + s.idx_off, *rev = idxb + nb;
-            const int nsolve = k == 0 ? n : nu;
-            cp(Linv, wk + s.w_Linv, n);
+            const int nsolve = k == 0 ? n : s.nu;
+            const int ld = n | 1, ld1 = n1 | 1;
+            cpa_vec(Linv, wk + s.w_Linv, n);
             {
                 const double *src = after_fact ? wk + s.w_lrow : vux(dst, s);
                 for (int i = tid; i < nsolve; i += NT) v[i] = -src[i];
@@ -735,15 +917,25 @@ struct Ker
             }
             if (k < N)
             {
-                const StageDesc s1 = SD[k + 1];
-                cp(sA, qp + s.q_BAt, n * nx1);
-                cp(Lnext, wk + s1.w_L, n1 * n1);
-                if (after_fact)
-                    for (int j = tid; j < nx1; j += NT) p1[j] = (wk + s1.w_lrow)[nu1 + j];
-                else
-                    for (int j = tid; j < nx1; j += NT) p1[j] = vux(dst, s1)[nu1 + j];   // backward value of x_{k+1}
+                const StageDesc &s1 = SD[k + 1];
+                cpa_mat(sA, ld, qp + s.q_BAt, n, nx1);
+                cpa_mat(Lnext, ld1, wk + s1.w_L, n1, n1);
+                cpa_vec(p1, after_fact ? wk + s1.w_lrow + nu1 : vux(dst, s1) + nu1, nx1);   // p part / backward value of x_{k+1}
+                cpa_vec(bv_, rb(rhs, s), nx1);
+                if (k + 1 < N)
+                {
+                    const StageDesc &s2 = SD[k + 2];
+                    prefetch_l2(wk + s2.w_fac, s2.w_fac_bytes);
+                }
+                prefetch_l2(qp + s1.q_stage, s1.q_stage_bytes);
             }
-            if (ng > 0) cp(sC, qp + s.q_DCt, n * ng);
+            if (ng > 0) cpa_mat(sC, ld, qp + s.q_DCt, n, ng);
+            if (ns > 0)
+            {
+                cpa_vec(Zi, wk + s.w_Zsi, 2 * ns);
+                cpa_vec(ds, vux(dst, s) + n, 2 * ns);
+            }
+            cpa_wait();
             sync();
             // TRSV_LTN(_MN): back substitution with the transposed factor on the first nsolve unknowns
             if (tid < 32)
@@ -751,73 +943,54 @@ struct Ker
                 for (int j = nsolve - 1; j >= 0; j--)
                 {
                     double part = 0.0;
-                    for (int i = j + 1 + tid; i < n; i += 32) part += Lcur[i + n * j] * v[i];
+                    for (int i = j + 1 + tid; i < n; i += 32) part += Lcur[i + ld * j] * v[i];
                     part = wsum(part);
                     if (tid == 0) v[j] = (v[j] - part) * Linv[j];
                     __syncwarp();
                 }
             }
             sync();
-            cp(vux(dst, s), v, n);
+            {
+                double *o_ = vux(dst, s);
+                for (int i = tid; i < n; i += NT) o_[i] = v[i];
+            }
             if (k < N)
             {
-                const double *b_ = rb(rhs, s);
-                for (int j = tid; j < nx1; j += NT)
-                {
-                    double acc = b_[j];
-                    for (int i = 0; i < n; i++) acc += sA[i + n * j] * v[i];
-                    x1[j] = acc;
-                }
+                const double *Lx = Lnext + nu1 + ld1 * nu1;
+                for (int j = tid; j < nx1; j += NT) x1[j] = bv_[j] + dot(sA + ld * j, 1, v, 1, n);
                 sync();
                 for (int j = tid; j < nx1; j += NT)
                 {
-                    double acc = 0.0;
-                    for (int i = j; i < nx1; i++) acc += Lnext[(nu1 + i) + n1 * (nu1 + j)] * x1[i];
+                    const double acc = dot(Lx + j + ld1 * j, 1, x1 + j, 1, nx1 - j);
                     tmp[j] = after_fact ? acc + p1[j] : acc;
                 }
                 sync();
                 double *pi = vpi(dst, s);
                 for (int i = tid; i < nx1; i += NT)
                 {
-                    double acc = 0.0;
-                    for (int j = 0; j <= i; j++) acc += Lnext[(nu1 + i) + n1 * (nu1 + j)] * tmp[j];
+                    const double acc = dot(Lx + i, ld1, tmp, 1, i + 1);
                     pi[i] = after_fact ? acc : acc + p1[i];
                 }
             }
             // ---- constraint part of the step at this stage
             {
                 const double *gl = sol + s.sol.lam, *gt = sol + s.sol.t;
+                const double t_min_inv = o.t_min > 0 ? 1.0 / o.t_min : 1e30;
                 for (int i = tid; i < nc; i += NT)
                 {
                     const double l = gl[i], tt = gt[i];
                     lam[i] = l;
-                    Gam[i] = (1.0 / tt) * l;
-                }
-                if (ns > 0 && o.t_lam_min == 1)
-                {
-                    const double t_min_inv = o.t_min > 0 ? 1.0 / o.t_min : 1e30;
-                    for (int i = tid; i < nc; i += NT)
-                    {
-                        const double l = gl[i], tt = gt[i];
-                        Gam[i] = (tt < o.t_min ? t_min_inv : 1.0 / tt) * (l < o.lam_min ? o.lam_min : l);
-                    }
+                    Gam[i] = (ns > 0 && o.t_lam_min == 1) ? (tt < o.t_min ? t_min_inv : 1.0 / tt) * (l < o.lam_min ? o.lam_min : l)
+                                                          : (1.0 / tt) * l;
                 }
                 for (int i = tid; i < nbg; i += NT)
                 {
-                    double a;
-                    if (i < nb) a = v[idxb[i]];
-                    else
-                    {
-                        a = 0.0;
-                        for (int r = 0; r < n; r++) a += sC[r + n * (i - nb)] * v[r];
-                    }
+                    const double a = i < nb ? v[idxb[i]] : dot(sC + ld * (i - nb), 1, v, 1, n);
                     dt[i] = a;
                     dt[nbg + i] = -a;
                 }
                 if (ns > 0)
                 {
-                    cp(Zi, wk + s.w_Zsi, 2 * ns);
-                    cp(ds, vux(dst, s) + n, 2 * ns);
                     sync();
                     for (int j = tid; j < 2 * ns; j += NT)
                     {
@@ -835,7 +1008,8 @@ struct Ker
                         const int up = i >= nbg, ii = up ? i - nbg : i;
                         if (rev[ii] >= 0) dt[i] += ds[(up ? ns : 0) + rev[ii]];
                     }
-                    cp(vux(dst, s) + n, ds, 2 * ns);
+                    double *o_ = vux(dst, s) + n;
+                    for (int j = tid; j < 2 * ns; j += NT) o_[j] = ds[j];
                 }
                 sync();
                 const double *grd = rd(rhs, s), *grm = rm(rhs, s), *gm = qp + s.q_dmask;
