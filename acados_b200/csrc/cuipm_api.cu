@@ -111,11 +111,19 @@ static int build_desc(cuipm_solver *s, const cuipm_shape *sh)
     auto e = [](int n) { return (n + 1) & ~1; };
     // leading dimensions used on chip: nmax|1 (odd, conflict-free row/column access) or even(nmax+1) (factorisation:
     // rows incl. the gradient row, 16-byte aligned column starts); both <= nmax+2
-    P.sm_M = e((P.nmax + 2) * P.nmax + 8);
-    P.sm_A = e((P.nmax + 2) * P.nxmax + 8);
-    P.sm_AL = e(std::max((P.nmax + 2) * (P.nxmax + P.ngmax), (P.nmax + 2) * P.nmax) + 8);
+    P.sm_M = e((P.nmax + 2) * P.nmax + 8);                       // factor of the stage being eliminated (rows incl. gradient row)
+    P.sm_A = 0;                                                  // (matrices of the substitution / residual sweeps are streamed from global memory)
+    P.sm_AL = e((P.nmax + 2) * (P.nxmax + P.ngmax) + 8);         // [A; b'] -> A L_xx in place (+ general-constraint columns)
     P.sm_C = P.ngmax > 0 ? 2 * e((P.nmax + 2) * P.ngmax) + 8 : 0;
-    P.sm_V = 5 * e(P.nvsmax) + 8 * e(P.nxmax) + 8 * e(P.ncmax) + 6 * e(P.nbgmax) + 8 * e(P.nmax + 1) + 8 * e(2 * P.nsmax) + 32;
+    {
+        const int nvs = e(P.nvsmax), nx = e(P.nxmax), nc = e(P.ncmax), nbg = e(P.nbgmax), n = e(P.nmax + 1), ns2 = e(2 * P.nsmax);
+        const int v_res = 2 * nvs + 3 * nx + 4 * nc + 2 * nbg;
+        const int v_fwd = 2 * nvs + 5 * nx + 4 * nc + 2 * ns2 + nbg;
+        const int v_fact = 2 * nc + 2 * nbg + 3 * n + 2 * ns2 + 16;
+        const int v_slv = nvs + 2 * nc + 2 * nbg + 2 * ns2 + 3 * nx;
+        const int v_init = nvs + nc + e(P.ngmax);
+        P.sm_V = std::max(std::max(std::max(v_res, v_fwd), std::max(v_fact, v_slv)), v_init) + 8;
+    }
     P.sm_total = P.sm_M + P.sm_A + P.sm_AL + P.sm_C + P.sm_V;
     if (smem_bytes(P) > 227 * 1024) { set_error("stage dimensions need more than 227 KB of shared memory"); return CUIPM_ERR_TOO_LARGE; }
     CK(cudaMalloc(&s->d_sd, sizeof(StageDesc) * (N + 1)));

@@ -22,29 +22,46 @@ namespace {
 
 __device__ __forceinline__ int ev(int n) { return (n + 1) & ~1; }
 
-template <int W>
-struct Ker
-{
-    static constexpr int NT = 32 * W;
 
+// Per-CTA solver context.  It lives in static shared memory and is reached by name (never through a pointer), and the
+// dynamic shared memory is reached through the extern array below, so that every on-chip access compiles to LDS/STS
+// with 32-bit addressing instead of generic loads.
+struct Ctx
+{
     ProbDesc P;
-    const StageDesc *__restrict__ SD;
-    const int *__restrict__ ipool;
-    const double *__restrict__ qp;   // this QP's record (read-only for the whole kernel)
-    double *sol;                     // this QP's solution record
-    double *wk;                      // this QP's work record
-    double *sM, *sA, *sAL, *sC, *sV, *sred;
+    const StageDesc *SD;
+    const int *ipool;
+    const double *qp;   // this QP's record (read-only for the whole kernel)
+    double *sol;        // this QP's solution record
+    double *wk;         // this QP's work record
     cuipm_opts o;
     int mask_constr;
     double nc_mask_inv;
 #ifdef CUIPM_PROFILE
     long long prof[16];   // cycles per pass kind (thread 0): 0 res, 1 res_lin, 2 fact_backward, 3 forward, 4 solve_backward, 5 vector passes
+#endif
+};
+__shared__ Ctx g_cx;
+__shared__ double g_red[8];
+extern __shared__ __align__(16) double g_smem[];
+#define CX g_cx
+#define SM_ (g_smem)
+#define SA_ (g_smem + CX.P.sm_M)
+#define SAL_ (g_smem + CX.P.sm_M + CX.P.sm_A)
+#define SC_ (g_smem + CX.P.sm_M + CX.P.sm_A + CX.P.sm_AL)
+#define SV_ (g_smem + CX.P.sm_M + CX.P.sm_A + CX.P.sm_AL + CX.P.sm_C)
+#ifdef CUIPM_PROFILE
 #define PROF_T0() long long t0_ = clock64()
-#define PROF_ADD(slot) do { if (tid == 0) prof[slot] += clock64() - t0_; t0_ = clock64(); } while (0)
+#define PROF_ADD(slot) do { if (tid == 0) CX.prof[slot] += clock64() - t0_; t0_ = clock64(); } while (0)
 #else
 #define PROF_T0() do {} while (0)
 #define PROF_ADD(slot) do {} while (0)
 #endif
+
+template <int W>
+struct Ker
+{
+    static constexpr int NT = 32 * W;
 
     // ---- CTA primitives -------------------------------------------------------------------------
     __device__ __forceinline__ void sync()
@@ -63,11 +80,11 @@ struct Ker
         v = wsum(v);
         if (W > 1)
         {
-            if ((tid & 31) == 0) sred[tid >> 5] = v;
+            if ((tid & 31) == 0) g_red[tid >> 5] = v;
             __syncthreads();
             v = 0.0;
 #pragma unroll
-            for (int w = 0; w < W; w++) v += sred[w];
+            for (int w = 0; w < W; w++) v += g_red[w];
             __syncthreads();
         }
         return v;
@@ -78,11 +95,11 @@ struct Ker
         for (int m = 16; m > 0; m >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, m));
         if (W > 1)
         {
-            if ((tid & 31) == 0) sred[tid >> 5] = v;
+            if ((tid & 31) == 0) g_red[tid >> 5] = v;
             __syncthreads();
-            v = sred[0];
+            v = g_red[0];
 #pragma unroll
-            for (int w = 1; w < W; w++) v = fmin(v, sred[w]);
+            for (int w = 1; w < W; w++) v = fmin(v, g_red[w]);
             __syncthreads();
         }
         return v;
@@ -98,14 +115,14 @@ struct Ker
         }
         if (W > 1)
         {
-            if ((tid & 31) == 0) sred[tid >> 5] = isnan_ ? NAN : v;
+            if ((tid & 31) == 0) g_red[tid >> 5] = isnan_ ? NAN : v;
             __syncthreads();
             v = 0.0;
             isnan_ = 0;
 #pragma unroll
             for (int w = 0; w < W; w++)
             {
-                double x = sred[w];
+                double x = g_red[w];
                 if (x != x) isnan_ = 1;
                 else v = fmax(v, x);
             }
@@ -122,25 +139,25 @@ struct Ker
     // vector sets: 0 = current iterate (solution record), 1 = step, 2 = iterative-refinement step
     __device__ __forceinline__ double *vux(int set, const StageDesc &s) const
     {
-        return set == 0 ? sol + s.sol.ux : wk + (set == 1 ? s.step.ux : s.itref.ux);
+        return set == 0 ? CX.sol + s.sol.ux : CX.wk + (set == 1 ? s.step.ux : s.itref.ux);
     }
     __device__ __forceinline__ double *vpi(int set, const StageDesc &s) const
     {
-        return set == 0 ? sol + s.sol.pi : wk + (set == 1 ? s.step.pi : s.itref.pi);
+        return set == 0 ? CX.sol + s.sol.pi : CX.wk + (set == 1 ? s.step.pi : s.itref.pi);
     }
     __device__ __forceinline__ double *vlam(int set, const StageDesc &s) const
     {
-        return set == 0 ? sol + s.sol.lam : wk + (set == 1 ? s.step.lam : s.itref.lam);
+        return set == 0 ? CX.sol + s.sol.lam : CX.wk + (set == 1 ? s.step.lam : s.itref.lam);
     }
     __device__ __forceinline__ double *vt(int set, const StageDesc &s) const
     {
-        return set == 0 ? sol + s.sol.t : wk + (set == 1 ? s.step.t : s.itref.t);
+        return set == 0 ? CX.sol + s.sol.t : CX.wk + (set == 1 ? s.step.t : s.itref.t);
     }
     // residual sets: 0 = res, 1 = res_itref
-    __device__ __forceinline__ double *rg(int set, const StageDesc &s) const { return wk + (set == 0 ? s.res.g : s.ires.g); }
-    __device__ __forceinline__ double *rb(int set, const StageDesc &s) const { return wk + (set == 0 ? s.res.b : s.ires.b); }
-    __device__ __forceinline__ double *rd(int set, const StageDesc &s) const { return wk + (set == 0 ? s.res.d : s.ires.d); }
-    __device__ __forceinline__ double *rm(int set, const StageDesc &s) const { return wk + (set == 0 ? s.res.m : s.ires.m); }
+    __device__ __forceinline__ double *rg(int set, const StageDesc &s) const { return CX.wk + (set == 0 ? s.res.g : s.ires.g); }
+    __device__ __forceinline__ double *rb(int set, const StageDesc &s) const { return CX.wk + (set == 0 ? s.res.b : s.ires.b); }
+    __device__ __forceinline__ double *rd(int set, const StageDesc &s) const { return CX.wk + (set == 0 ? s.res.d : s.ires.d); }
+    __device__ __forceinline__ double *rm(int set, const StageDesc &s) const { return CX.wk + (set == 0 ? s.res.m : s.ires.m); }
 
     // iterate over the lower triangle (i >= j, i < n) plus the extra row i == n of an (n+1) x n array,
     // perfectly balanced: column p is paired with column n-1-p (n+3 entries per pair).
@@ -161,45 +178,47 @@ struct Ker
         }
     }
 
-    // ---- asynchronous staging -------------------------------------------------------------------
-    __device__ __forceinline__ void cpa8(double *sdst, const double *gsrc)
+    // ---- global-memory access ---------------------------------------------------------------------
+    // QP records are read-only for the whole launch (ld.global.nc); work / solution records are written by this
+    // CTA between passes and must be read with coherent loads.
+    template <bool RO>
+    __device__ __forceinline__ double ldv(const double *p) const
     {
-        const unsigned sa = (unsigned) __cvta_generic_to_shared(sdst);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc));
+        return RO ? __ldg(p) : __ldca(p);   // ld.global.nc / ld.global.ca: known address space, no generic-address path
     }
-    __device__ __forceinline__ void cpa_wait()
+    // sum_j G[j*ld] * x[j]: G in global memory (row of a column-major matrix when ld = rows, column when ld = 1),
+    // x in shared memory; 4 independent chains, 8 loads in flight
+    template <bool RO>
+    __device__ __forceinline__ double gdot(const double *G, int ld, const double *x, int len) const
     {
-        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-    }
-    // column-major rows x cols block (ld = rows in global) -> shared with leading dimension ldd
-    __device__ __forceinline__ void cpa_mat(double *dst, int ldd, const double *src, int rows, int cols)
-    {
-        if (rows <= 0) return;
-        int e = tid, j = e / rows, i = e - j * rows;
-        const int tot = rows * cols;
-        for (; e < tot; e += NT)
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int j = 0;
+#pragma unroll 2
+        for (; j + 3 < len; j += 4)
         {
-            cpa8(dst + i + ldd * j, src + e);
-            i += NT;
-            while (i >= rows) { i -= rows; j++; }
+            const double a0 = ldv<RO>(G + ld * j), a1 = ldv<RO>(G + ld * (j + 1));
+            const double a2 = ldv<RO>(G + ld * (j + 2)), a3 = ldv<RO>(G + ld * (j + 3));
+            s0 += a0 * x[j]; s1 += a1 * x[j + 1]; s2 += a2 * x[j + 2]; s3 += a3 * x[j + 3];
         }
+        for (; j < len; j++) s0 += ldv<RO>(G + ld * j) * x[j];
+        return (s0 + s1) + (s2 + s3);
     }
-    // symmetric matrix of which only the lower triangle is valid in global memory -> full matrix in shared
-    __device__ __forceinline__ void cpa_sym(double *dst, int ldd, const double *src, int n)
+    // row i of the symmetric n x n matrix H of which the lower triangle is stored (column-major, ld n), times x
+    __device__ __forceinline__ double gdot_sym(const double *H, int n, int i, const double *x) const
     {
-        if (n <= 0) return;
-        int e = tid, j = e / n, i = e - j * n;
-        const int tot = n * n;
-        for (; e < tot; e += NT)
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int j = 0;
+#pragma unroll 2
+        for (; j + 3 < n; j += 4)
         {
-            cpa8(dst + i + ldd * j, i >= j ? src + e : src + j + n * i);
-            i += NT;
-            while (i >= n) { i -= n; j++; }
+            const double a0 = __ldg(H + (j <= i ? i + n * j : j + n * i));
+            const double a1 = __ldg(H + (j + 1 <= i ? i + n * (j + 1) : j + 1 + n * i));
+            const double a2 = __ldg(H + (j + 2 <= i ? i + n * (j + 2) : j + 2 + n * i));
+            const double a3 = __ldg(H + (j + 3 <= i ? i + n * (j + 3) : j + 3 + n * i));
+            s0 += a0 * x[j]; s1 += a1 * x[j + 1]; s2 += a2 * x[j + 2]; s3 += a3 * x[j + 3];
         }
-    }
-    __device__ __forceinline__ void cpa_vec(double *dst, const double *src, int n)
-    {
-        for (int i = tid; i < n; i += NT) cpa8(dst + i, src + i);
+        for (; j < n; j++) s0 += __ldg(H + (j <= i ? i + n * j : j + n * i)) * x[j];
+        return (s0 + s1) + (s2 + s3);
     }
     // L2 prefetch of a 16-byte-multiple chunk (TMA bulk prefetch), issued by one thread
     __device__ __forceinline__ void prefetch_l2(const double *p, unsigned bytes)
@@ -207,7 +226,7 @@ struct Ker
         if (tid == 0 && bytes)
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
     }
-    // sum_c a[c*sa] * b[c*sb], 4 independent chains
+    // sum_c a[c*sa] * b[c*sb] on shared memory operands, 4 independent chains
     __device__ __forceinline__ double dot(const double *a, int sa, const double *b, int sb, int len)
     {
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -225,66 +244,98 @@ struct Ker
 
     // ---------------------------------------------------------------------------------------------
     // residuals (restates OCP_QP_RES_COMPUTE / _LIN, external/hpipm/ocp_qp/x_ocp_qp_res.c:345-683)
-    // lin==0: KKT residuals of the QP at point set `pset` -> residual set `out`; returns mu, obj, gap.
-    // lin==1: residual of the Newton system with rhs set `rhs` at step `pset`, linearised at the iterate.
-    // nrm[4] = inf-norms of (g, b, d, m).
+    // lin==0: KKT residuals of the QP at the iterate -> residual set 0; returns mu, obj, gap, ||res_m - tau_min mask||.
+    //         update!=0 first moves the iterate by alpha_u along the step (UPDATE_VAR_QP, x_core_qp_ipm_aux.c:472-582,
+    //         with the step shortening and the t/lam clipping) -- the two sweeps are fused; and the complementarity
+    //         residual is stored twice: res_m_bkp = lam*t and res_m = lam*t - tau_min (the affine right-hand side of the
+    //         next iteration, BACKUP_RES_M / COMPUTE_TAU_MIN_QP :672-781).
+    // lin==1: residual of the Newton system with rhs set `rhs` at step set `pset`, linearised at the iterate -> set `out`.
+    // nrm[4] = inf-norms of (g, b, d, m).  Lane = row for H ux and A pi, lane = column for A' ux.
     // ---------------------------------------------------------------------------------------------
-    __device__ __noinline__ void res_pass(int lin, int pset, int rhs, int out, double &mu, double &obj, double &gap, double nrm[4])
+    __device__ __noinline__ void res_pass(int lin, int pset, int rhs, int out, int update, double alpha_u, double &mu, double &obj,
+                                          double &gap, double nrm[4], double &res_m_tau)
     {
-        const int N = P.N;
+        const int N = CX.P.N;
         double a_mu = 0.0, a_obj = 0.0, a_gap = 0.0;
-        double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
-        int f0 = 0, f1 = 0, f2 = 0, f3 = 0;
-        double *ux = sV, *x1 = ux + ev(P.nvsmax), *pi = x1 + ev(P.nxmax), *pim = pi + ev(P.nxmax);
-        double *lam = pim + ev(P.nxmax), *lamr = lam + ev(P.ncmax), *t = lamr + ev(P.ncmax), *msk = t + ev(P.ncmax);
-        double *tmp0 = msk + ev(P.ncmax), *tmp1 = tmp0 + ev(P.nbgmax), *g_ = tmp1 + ev(P.nbgmax);
-        double *gv_ = g_ + ev(P.nvsmax), *bv_ = gv_ + ev(P.nvsmax);
+        double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0, m4 = 0.0;
+        int f0 = 0, f1 = 0, f2 = 0, f3 = 0, f4 = 0;
+        double *ux = SV_, *x1 = ux + ev(CX.P.nvsmax), *pi = x1 + ev(CX.P.nxmax), *pim = pi + ev(CX.P.nxmax);
+        double *lam = pim + ev(CX.P.nxmax), *lamr = lam + ev(CX.P.ncmax), *t = lamr + ev(CX.P.ncmax), *msk = t + ev(CX.P.ncmax);
+        double *tmp0 = msk + ev(CX.P.ncmax), *tmp1 = tmp0 + ev(CX.P.nbgmax), *g_ = tmp1 + ev(CX.P.nbgmax);
+        if (update && alpha_u < 1.0) alpha_u = alpha_u * ((1.0 - alpha_u) * 0.99 + alpha_u * 0.9999999);
         for (int k = 0; k <= N; k++)
         {
-            const StageDesc &s = SD[k];
+            const StageDesc &s = CX.SD[k];
             const int n = s.n, nu = s.nu, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1;
-            const int ld = n | 1;
-            const int *idxb = ipool + s.idx_off, *rev = idxb + nb;
-            const double *qk = qp;
-            // ---- stage data to shared memory (asynchronous copies, all in flight together)
-            cpa_sym(sM, ld, qk + s.q_RSQ, n);
-            cpa_vec(ux, vux(pset, s), n + 2 * ns);
-            cpa_vec(gv_, rhs < 0 ? qk + s.q_rq : rg(rhs, s), n);
+            const int *idxb = CX.ipool + s.idx_off, *rev = idxb + nb;
+            const double *qk = CX.qp;
+            // ---- vectors of this stage (optionally moved along the step) to shared memory
+            {
+                double *gu = vux(pset, s);
+                const double *du = CX.wk + s.step.ux;
+                for (int i = tid; i < n + 2 * ns; i += NT)
+                {
+                    double v = gu[i];
+                    if (update) { v += alpha_u * du[i]; gu[i] = v; }
+                    ux[i] = v;
+                }
+            }
             if (k < N)
             {
-                const StageDesc &s1 = SD[k + 1];
-                cpa_mat(sA, ld, qk + s.q_BAt, n, nx1);
-                cpa_vec(x1, vux(pset, s1) + s1.nu, nx1);
-                cpa_vec(pi, vpi(pset, s), nx1);
-                cpa_vec(bv_, rhs < 0 ? qk + s.q_b : rb(rhs, s), nx1);
+                const StageDesc &s1 = CX.SD[k + 1];
+                const double *gu1 = vux(pset, s1) + s1.nu, *du1 = CX.wk + s1.step.ux + s1.nu, *dp = CX.wk + s.step.pi;
+                double *gp = vpi(pset, s);
+                for (int j = tid; j < nx1; j += NT)
+                {
+                    double v = gu1[j], p = gp[j];
+                    if (update) { v += alpha_u * du1[j]; p += alpha_u * dp[j]; gp[j] = p; }
+                    x1[j] = v;
+                    pi[j] = p;
+                }
                 prefetch_l2(qk + s1.q_stage, s1.q_stage_bytes);
+                if (update) prefetch_l2(CX.wk + s1.w_vec, s1.w_vec_bytes);
             }
-            if (k > 0) cpa_vec(pim, vpi(pset, SD[k - 1]), s.nx);
-            if (ng > 0) cpa_mat(sC, ld, qk + s.q_DCt, n, ng);
             {
-                const double *gl = vlam(pset, s), *gt = vt(pset, s), *gm = qk + s.q_dmask;
+                double *gl = vlam(pset, s), *gt = vt(pset, s);
+                const double *gm = qk + s.q_dmask, *dl = CX.wk + s.step.lam, *dtt = CX.wk + s.step.t;
                 for (int i = tid; i < nc; i += NT)
                 {
-                    double l = gl[i], mk = mask_constr ? gm[i] : 1.0;
+                    double l = gl[i], tt = gt[i];
+                    const double mk = CX.mask_constr ? __ldg(gm + i) : 1.0;
+                    if (update)
+                    {
+                        l += alpha_u * dl[i];
+                        tt += alpha_u * dtt[i];
+                        if (CX.o.t_lam_min == 2)
+                        {
+                            l = l <= CX.o.lam_min ? CX.o.lam_min : l;
+                            tt = tt <= CX.o.t_min ? CX.o.t_min : tt;
+                        }
+                        if (CX.mask_constr) l *= mk;
+                        gl[i] = l;
+                        gt[i] = tt;
+                    }
                     lamr[i] = l;
-                    lam[i] = mask_constr ? l * mk : l;
-                    t[i] = gt[i];
+                    lam[i] = CX.mask_constr ? l * mk : l;
+                    t[i] = tt;
                     msk[i] = mk;
                 }
             }
-            cpa_wait();
             sync();
             for (int i = tid; i < nbg; i += NT) tmp0[i] = lam[nbg + i] - lam[i];
             sync();
-            // ---- rows of res_g (lane = row), res_b and C'ux (lane = column)
+            // ---- rows of res_g (lane = row), res_b and C'ux (lane = column), matrices straight from global memory
+            const double *gvec = rhs < 0 ? qk + s.q_rq : rg(rhs, s);
+            const double *bvec = rhs < 0 ? qk + s.q_b : rb(rhs, s);
+            const double *Hg = qk + s.q_RSQ, *Ag = qk + s.q_BAt, *Cg = qk + s.q_DCt;
             double *ob = rb(out, s);
             for (int oo = tid; oo < n + nx1 + ng; oo += NT)
             {
                 if (oo < n)
                 {
                     const int i = oo;
-                    const double acc = dot(sM + i, ld, ux, 1, n);
-                    const double gv = gv_[i];
+                    const double acc = gdot_sym(Hg, n, i, ux);
+                    const double gv = gvec[i];
                     double r;
                     if (!lin)
                     {
@@ -296,15 +347,15 @@ struct Ker
                     else
                         r = acc + gv;
                     if (k > 0 && i >= nu) r -= pim[i - nu];
-                    r += dot(sA + i, ld, pi, 1, nx1);
-                    for (int g = 0; g < ng; g++) r += sC[i + ld * g] * tmp0[nb + g];
+                    r += gdot<true>(Ag + i, n, pi, nx1);
+                    for (int g = 0; g < ng; g++) r += __ldg(Cg + i + n * g) * tmp0[nb + g];
                     g_[i] = r;
                 }
                 else if (oo < n + nx1)
                 {
                     const int j = oo - n;
-                    const double acc = dot(sA + ld * j, 1, ux, 1, n);
-                    const double bv = bv_[j];
+                    const double acc = gdot<true>(Ag + n * j, 1, ux, n);
+                    const double bv = bvec[j];
                     const double r = bv - x1[j] + acc;
                     ob[j] = r;
                     const double a = fabs(r);
@@ -315,7 +366,7 @@ struct Ker
                 else
                 {
                     const int g = oo - n - nx1;
-                    tmp1[nb + g] = dot(sC + ld * g, 1, ux, 1, n);
+                    tmp1[nb + g] = gdot<true>(Cg + n * g, 1, ux, n);
                 }
             }
             sync();
@@ -361,9 +412,9 @@ struct Ker
             // ---- res_d, res_m
             {
                 const double *dvec = rhs < 0 ? qk + s.q_d : rd(rhs, s);
-                double *od = rd(out, s), *om = rm(out, s);
+                double *od = rd(out, s), *om = rm(out, s), *obk = CX.wk + s.w_rmb;
                 const double *mv = lin ? rm(rhs, s) : nullptr;
-                const double *Lam = lin ? sol + s.sol.lam : nullptr, *T = lin ? sol + s.sol.t : nullptr;
+                const double *Lam = lin ? CX.sol + s.sol.lam : nullptr, *T = lin ? CX.sol + s.sol.t : nullptr;
                 for (int i = tid; i < nc; i += NT)
                 {
                     const double dv = dvec[i];
@@ -377,7 +428,7 @@ struct Ker
                     }
                     else
                         r = t[i] - ux[n + (i - 2 * nbg)] + dv;
-                    if (mask_constr) r *= msk[i];
+                    if (CX.mask_constr) r *= msk[i];
                     od[i] = r;
                     double a = fabs(r);
                     m2 = fmax(m2, a);
@@ -387,15 +438,22 @@ struct Ker
                     {
                         a_gap -= dv * lam[i];
                         mm = lam[i] * t[i];
-                        if (mask_constr) mm *= msk[i];
+                        if (CX.mask_constr) mm *= msk[i];
                         a_mu += fabs(mm);
+                        obk[i] = mm;
+                        double ma = mm - CX.o.tau_min;
+                        if (CX.mask_constr) ma *= msk[i];
+                        om[i] = ma;                                  // affine rhs of the next iteration
+                        const double a4 = fabs(mm - CX.o.tau_min * msk[i]);
+                        m4 = fmax(m4, a4);
+                        f4 |= (a4 != a4);
                     }
                     else
                     {
                         mm = mv[i] + Lam[i] * t[i] + lamr[i] * T[i];
-                        if (mask_constr) mm *= msk[i];
+                        if (CX.mask_constr) mm *= msk[i];
+                        om[i] = mm;
                     }
-                    om[i] = mm;
                     a = fabs(mm);
                     m3 = fmax(m3, a);
                     f3 |= (a != a);
@@ -411,6 +469,8 @@ struct Ker
                 }
             }
             sync();
+            for (int j = tid; j < nx1; j += NT) pim[j] = pi[j];      // pi_k is "pi_{k-1}" of the next stage
+            sync();
         }
         nrm[0] = rmax_nan(m0, f0);
         nrm[1] = rmax_nan(m1, f1);
@@ -418,9 +478,10 @@ struct Ker
         nrm[3] = rmax_nan(m3, f3);
         if (!lin)
         {
-            mu = rsum(a_mu) * nc_mask_inv;
+            mu = rsum(a_mu) * CX.nc_mask_inv;
             obj = rsum(a_obj);
             gap = rsum(a_gap);
+            res_m_tau = rmax_nan(m4, f4);
         }
     }
 
@@ -433,13 +494,13 @@ struct Ker
                                 double *Zi, double *ds, double *tmp0, double *tmp1)
     {
         const int nb = s.nb, ns = s.ns, nbg = s.nbg;
-        const int *rev = ipool + s.idx_off + nb;
-        const double *Z = qp + s.q_Z;
+        const int *rev = CX.ipool + s.idx_off + nb;
+        const double *Z = CX.qp + s.q_Z;
         for (int j = tid; j < 2 * ns; j += NT)
         {
             const int jj = j < ns ? j : j - ns, offc = j < ns ? 0 : nbg;
             double zi = 0.0, d = rgs[j] + gam[2 * nbg + j];
-            if (fact) zi = Z[j] + o.reg_prim + Gam[2 * nbg + j];
+            if (fact) zi = Z[j] + CX.o.reg_prim + Gam[2 * nbg + j];
             for (int i = 0; i < nbg; i++)
                 if (rev[i] == jj)
                 {
@@ -475,48 +536,65 @@ struct Ker
     // rhs = residual set 0.  Writes L, Linv, lrow, Pb, Zs_inv (and the slack part of the step rhs).
     //
     // Thread r owns row r of the (n+1) x n stage block (row n carries the gradient).  Per stage:
-    //   [A; b'] -> sAL, then in place  AL = [A; b'] * Lxx_{k+1}         (TRMM_RLNN)
+    //   [A; b'] -> SAL_, then in place  AL = [A; b'] * Lxx_{k+1}         (TRMM_RLNN)
     //   column tiles of 4:  acc = H + diag + AL AL' - (already factored columns)   (SYRK + left-looking POTRF)
     //   the 4x4 diagonal block is factorised redundantly by every thread, the panel scaled, columns stored.
-    // sM holds L_{k+1} (rows 0..n1, row n1 = its gradient row) when the stage starts and L_k when it ends.
+    // SM_ holds L_{k+1} (rows 0..n1, row n1 = its gradient row) when the stage starts and L_k when it ends.
     // ---------------------------------------------------------------------------------------------
     __device__ __noinline__ void fact_backward()
     {
-        const int N = P.N;
-        double *Gam = sV, *gam = Gam + ev(P.ncmax), *tmp0 = gam + ev(P.ncmax), *tmp1 = tmp0 + ev(P.nbgmax);
-        double *dadd = tmp1 + ev(P.nbgmax), *rowv = dadd + ev(P.nmax), *Linv = rowv + ev(P.nmax);
-        double *Zi = Linv + ev(P.nmax), *ds = Zi + ev(2 * P.nsmax), *D = ds + ev(2 * P.nsmax);   // D: 4 x 4 diagonal block
-        double *sCb = sC + ev((P.nmax + 2) * P.ngmax);
+        const int N = CX.P.N;
+        double *Gam = SV_, *gam = Gam + ev(CX.P.ncmax), *tmp0 = gam + ev(CX.P.ncmax), *tmp1 = tmp0 + ev(CX.P.nbgmax);
+        double *dadd = tmp1 + ev(CX.P.nbgmax), *rowv = dadd + ev(CX.P.nmax), *Linv = rowv + ev(CX.P.nmax);
+        double *Zi = Linv + ev(CX.P.nmax), *ds = Zi + ev(2 * CX.P.nsmax), *D = ds + ev(2 * CX.P.nsmax);   // D: 4 x 4 diagonal block
+        double *sCb = SC_ + ev((CX.P.nmax + 2) * CX.P.ngmax);
         int ldm_prev = 0;
         for (int k = N; k >= 0; k--)
         {
-            const StageDesc &s = SD[k];
+            const StageDesc &s = CX.SD[k];
             const int n = s.n, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1, nu1 = s.nu1, n1 = s.n1;
-            const int *idxb = ipool + s.idx_off;
+            const int *idxb = CX.ipool + s.idx_off;
             const int ldal = ev(n + 1), ldm = ev(n + 1);
             const int kc = k < N ? nx1 : 0;
-            // ---- stage inputs: [A; b'] into sAL (asynchronous), constraint quantities
+            // ---- stage inputs: [A; b'] into SAL_ (asynchronous), constraint quantities
             if (k < N)
             {
-                cpa_mat(sAL, ldal, qp + s.q_BAt, n, nx1);
-                const double *b_ = rb(0, s);
-                for (int j = tid; j < nx1; j += NT) cpa8(sAL + n + ldal * j, b_ + j);
+                // [A; b'] into SAL_: thread r copies row r (coalesced across threads, 8 loads in flight)
+                const double *Ag = CX.qp + s.q_BAt, *b_ = rb(0, s);
+                for (int r = tid; r <= n; r += NT)
+                {
+                    if (r < n)
+                    {
+                        int c = 0;
+#pragma unroll 2
+                        for (; c + 3 < nx1; c += 4)
+                        {
+                            const double a0 = __ldg(Ag + r + n * c), a1 = __ldg(Ag + r + n * (c + 1));
+                            const double a2 = __ldg(Ag + r + n * (c + 2)), a3 = __ldg(Ag + r + n * (c + 3));
+                            SAL_[r + ldal * c] = a0; SAL_[r + ldal * (c + 1)] = a1;
+                            SAL_[r + ldal * (c + 2)] = a2; SAL_[r + ldal * (c + 3)] = a3;
+                        }
+                        for (; c < nx1; c++) SAL_[r + ldal * c] = __ldg(Ag + r + n * c);
+                    }
+                    else
+                        for (int c = 0; c < nx1; c++) SAL_[n + ldal * c] = b_[c];
+                }
             }
             if (k > 0)
             {
-                const StageDesc &sp = SD[k - 1];
-                prefetch_l2(qp + sp.q_stage, sp.q_stage_bytes);
-                prefetch_l2(wk + sp.w_vec, sp.w_vec_bytes);
+                const StageDesc &sp = CX.SD[k - 1];
+                prefetch_l2(CX.qp + sp.q_stage, sp.q_stage_bytes);
+                prefetch_l2(CX.wk + sp.w_vec, sp.w_vec_bytes);
             }
             {
                 // Gamma, gamma (COMPUTE_GAMMA_GAMMA_QP, x_core_qp_ipm_aux.c:38-86)
-                const double *gl = sol + s.sol.lam, *gt = sol + s.sol.t, *grd = rd(0, s), *grm = rm(0, s);
-                const double t_min_inv = o.t_min > 0 ? 1.0 / o.t_min : 1e30;
+                const double *gl = CX.sol + s.sol.lam, *gt = CX.sol + s.sol.t, *grd = rd(0, s), *grm = rm(0, s);
+                const double t_min_inv = CX.o.t_min > 0 ? 1.0 / CX.o.t_min : 1e30;
                 for (int i = tid; i < nc; i += NT)
                 {
                     const double l = gl[i], tt = gt[i], ti = 1.0 / tt;
-                    if (o.t_lam_min == 1)
-                        Gam[i] = (tt < o.t_min ? t_min_inv : ti) * (l < o.lam_min ? o.lam_min : l);
+                    if (CX.o.t_lam_min == 1)
+                        Gam[i] = (tt < CX.o.t_min ? t_min_inv : ti) * (l < CX.o.lam_min ? CX.o.lam_min : l);
                     else
                         Gam[i] = ti * l;
                     gam[i] = ti * (grm[i] - l * grd[i]);
@@ -524,7 +602,7 @@ struct Ker
                 const double *g_ = rg(0, s);
                 for (int i = tid; i < n; i += NT)
                 {
-                    dadd[i] = o.reg_prim;
+                    dadd[i] = CX.o.reg_prim;
                     rowv[i] = g_[i];
                 }
             }
@@ -535,8 +613,8 @@ struct Ker
                 sync();
                 for (int j = tid; j < 2 * ns; j += NT)
                 {
-                    (wk + s.w_Zsi)[j] = Zi[j];
-                    (wk + s.step.ux + n)[j] = ds[j];
+                    (CX.wk + s.w_Zsi)[j] = Zi[j];
+                    (CX.wk + s.step.ux + n)[j] = ds[j];
                 }
             }
             else
@@ -562,15 +640,14 @@ struct Ker
                     dadd[ix] += tmp0[i];
                     rowv[ix] += tmp1[i];
                 }
-            cpa_wait();
             sync();
             if (k < N)
             {
                 // ---- in place: AL = [A; b'] * Lxx   (row r, column tiles of 4; columns only read at c >= tile start)
-                const double *Lx = sM + nu1 + ldm_prev * nu1;       // Lxx(c, j) = Lx[c + ldm_prev*j], zero above the diagonal
+                const double *Lx = SM_ + nu1 + ldm_prev * nu1;       // Lxx(c, j) = Lx[c + ldm_prev*j], zero above the diagonal
                 for (int r = tid; r <= n; r += NT)
                 {
-                    double *arow = sAL + r;
+                    double *arow = SAL_ + r;
                     for (int jt = 0; jt < nx1; jt += 4)
                     {
                         const int j1 = min(jt + 1, nx1 - 1), j2 = min(jt + 2, nx1 - 1), j3 = min(jt + 3, nx1 - 1);
@@ -593,27 +670,27 @@ struct Ker
                 sync();
                 // Pb = Lxx * (Lxx' b),  then the gradient row gets l_{k+1}
                 {
-                    double *Pb = wk + s.w_Pb;
-                    for (int i = tid; i < nx1; i += NT) Pb[i] = dot(Lx + i, ldm_prev, sAL + n, ldal, i + 1);
+                    double *Pb = CX.wk + s.w_Pb;
+                    for (int i = tid; i < nx1; i += NT) Pb[i] = dot(Lx + i, ldm_prev, SAL_ + n, ldal, i + 1);
                 }
                 sync();
-                for (int j = tid; j < nx1; j += NT) sAL[n + ldal * j] += sM[n1 + ldm_prev * (nu1 + j)];
+                for (int j = tid; j < nx1; j += NT) SAL_[n + ldal * j] += SM_[n1 + ldm_prev * (nu1 + j)];
             }
             if (ng > 0)
             {
                 // general constraints enter the rank update as extra columns: own-row operand C diag(tmp0) (row n: tmp1),
                 // broadcast operand C
-                const double *Cg = qp + s.q_DCt;
+                const double *Cg = CX.qp + s.q_DCt;
                 for (int e = tid; e < (n + 1) * ng; e += NT)
                 {
                     const int g = e / (n + 1), i = e - g * (n + 1);
-                    sAL[i + ldal * (kc + g)] = i < n ? Cg[i + n * g] * tmp0[nb + g] : tmp1[nb + g];
+                    SAL_[i + ldal * (kc + g)] = i < n ? Cg[i + n * g] * tmp0[nb + g] : tmp1[nb + g];
                     if (i < n) sCb[i + ldal * g] = Cg[i + n * g];
                 }
             }
             sync();
             // ---- column tiles: SYRK + left-looking Cholesky, rows r >= jt (row n = gradient row)
-            const double *Hg = qp + s.q_RSQ;
+            const double *Hg = CX.qp + s.q_RSQ;
             for (int jt = 0; jt < n; jt += 4)
             {
                 const int w4 = min(4, n - jt);
@@ -645,7 +722,7 @@ struct Ker
                     }
                     double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
                     {
-                        const double *own = sAL + r, *bc = sAL + jt;
+                        const double *own = SAL_ + r, *bc = SAL_ + jt;
                         for (int c = 0; c < kc; c++)
                         {
                             const double a = own[ldal * c];
@@ -661,7 +738,7 @@ struct Ker
                         }
                     }
                     {
-                        const double *own = sM + r, *bc = sM + jt;
+                        const double *own = SM_ + r, *bc = SM_ + jt;
                         double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
                         for (int c = 0; c < jt; c++)
                         {
@@ -674,7 +751,7 @@ struct Ker
                     }
                     c0 += h0; c1 += h1; c2 += h2; c3 += h3;
                     // park the raw panel row (rows of the diagonal block are read back by everybody)
-                    double *mr = sM + r + ldm * jt;
+                    double *mr = SM_ + r + ldm * jt;
                     mr[0] = c0;
                     if (w4 > 1) mr[ldm] = c1;
                     if (w4 > 2) mr[2 * ldm] = c2;
@@ -683,7 +760,7 @@ struct Ker
                 sync();
                 // ---- 4x4 diagonal block (pivot rule blasfeo_ref/x_lapack_ref.c:84-91), redundantly per thread
                 {
-                    const double *dg = sM + jt + ldm * jt;
+                    const double *dg = SM_ + jt + ldm * jt;
                     double d00 = dg[0], d10 = 0, d20 = 0, d30 = 0, d11 = 0, d21 = 0, d31 = 0, d22 = 0, d32 = 0, d33 = 0;
                     if (w4 > 1) { d10 = dg[1]; d11 = dg[1 + ldm]; }
                     if (w4 > 2) { d20 = dg[2]; d21 = dg[2 + ldm]; d22 = dg[2 + 2 * ldm]; }
@@ -701,7 +778,7 @@ struct Ker
                     sync();   // everybody has read the raw block before it is overwritten
                     for (int r = jt + tid; r <= n; r += NT)
                     {
-                        double *mr = sM + r + ldm * jt;
+                        double *mr = SM_ + r + ldm * jt;
                         const int rr = r - jt;     // position inside the panel: rows 0..3 form the diagonal block
                         double x0 = mr[0] * i0;
                         if (rr == 0) x0 = d00 * i0;
@@ -732,26 +809,22 @@ struct Ker
                 }
                 sync();
             }
-            // rows above the diagonal inside a tile were written as zeros; rows r < jt of later tiles were never
-            // touched: clear the strict upper triangle so that Lxx can be used as a full matrix by the next stage
-            for (int e = tid; e < n * n; e += NT)
+            // ---- keep the factor (global: column-major n x n, ld n, zeros above the diagonal) and clear the strict upper
+            // triangle on chip too (rows r < jt of later tiles were never written): the next stage uses Lxx as a full matrix
             {
-                const int j = e / n, i = e - j * n;
-                if (i < j) sM[i + ldm * j] = 0.0;
-            }
-            sync();
-            // ---- keep the factor (global: column-major n x n, ld n)
-            {
-                double *Lg = wk + s.w_L;
-                for (int e = tid; e < n * n; e += NT)
-                {
-                    const int j = e / n, i = e - j * n;
-                    Lg[e] = sM[i + ldm * j];
-                }
-                double *lr = wk + s.w_lrow, *li = wk + s.w_Linv;
+                double *Lg = CX.wk + s.w_L;
+                for (int r = tid; r < n; r += NT)
+                    for (int j = 0; j < n; j++)
+                    {
+                        double v = 0.0;
+                        if (r >= j) v = SM_[r + ldm * j];
+                        else SM_[r + ldm * j] = 0.0;
+                        Lg[r + n * j] = v;
+                    }
+                double *lr = CX.wk + s.w_lrow, *li = CX.wk + s.w_Linv;
                 for (int j = tid; j < n; j += NT)
                 {
-                    lr[j] = sM[n + ldm * j];
+                    lr[j] = SM_[n + ldm * j];
                     li[j] = Linv[j];
                 }
             }
@@ -763,55 +836,57 @@ struct Ker
     // ---------------------------------------------------------------------------------------------
     // backward substitution with an existing factorisation (OCP_QP_SOLVE_KKT_STEP, x_ocp_qp_kkt.c:1582-1680)
     // rhs residual set `rhs`, result (backward quantities) into step set `dst`.
+    // rm_mode fuses the complementarity right-hand side update of the corrector into this sweep
+    // (x_core_qp_ipm_aux.c:695-754): 0 keep res_m; 1 res_m = bkp + dt*dlam - sigma_mu; 2 res_m = bkp - sigma_mu.
+    // Matrices are read straight from global memory (lane = row).
     // ---------------------------------------------------------------------------------------------
-    __device__ __noinline__ void solve_backward(int rhs, int dst, int use_Pb)
+    __device__ __noinline__ void solve_backward(int rhs, int dst, int use_Pb, int rm_mode, double sigma_mu)
     {
-        const int N = P.N;
-        double *v = sV, *gam = v + ev(P.nvsmax), *Gam = gam + ev(P.ncmax), *tmp0 = Gam + ev(P.ncmax);
-        double *tmp1 = tmp0 + ev(P.nbgmax), *Zi = tmp1 + ev(P.nbgmax), *ds = Zi + ev(2 * P.nsmax);
-        double *xprev = ds + ev(2 * P.nsmax), *tmpx = xprev + ev(P.nxmax), *tmpl = tmpx + ev(P.nxmax);
-        double *Linv = tmpl + ev(P.nxmax), *pbv = Linv + ev(P.nmax);
-        double *Lcur = sM, *Lnext = sAL;   // two factor buffers (Lnext only needed when !use_Pb)
-        int ld_next = 1;
+        const int N = CX.P.N;
+        double *v = SV_, *gam = v + ev(CX.P.nvsmax), *Gam = gam + ev(CX.P.ncmax), *tmp0 = Gam + ev(CX.P.ncmax);
+        double *tmp1 = tmp0 + ev(CX.P.nbgmax), *Zi = tmp1 + ev(CX.P.nbgmax), *ds = Zi + ev(2 * CX.P.nsmax);
+        double *xprev = ds + ev(2 * CX.P.nsmax), *tmpx = xprev + ev(CX.P.nxmax), *tmpl = tmpx + ev(CX.P.nxmax);
         for (int k = N; k >= 0; k--)
         {
-            const StageDesc &s = SD[k];
-            const int n = s.n, nu = s.nu, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1, nu1 = s.nu1;
-            const int *idxb = ipool + s.idx_off;
+            const StageDesc &s = CX.SD[k];
+            const int n = s.n, nu = s.nu, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1, nu1 = s.nu1, n1 = s.n1;
+            const int *idxb = CX.ipool + s.idx_off;
             const int nsolve = k == 0 ? n : nu;
-            const int ld = n | 1;
-            if (!use_Pb && k < N)
-            {   // previous stage's factor becomes "next"
-                double *tt = Lcur; Lcur = Lnext; Lnext = tt;
-            }
-            cpa_vec(v, rg(rhs, s), n);
-            cpa_mat(Lcur, ld, wk + s.w_L, n, nsolve);
-            cpa_vec(Linv, wk + s.w_Linv, n);
-            if (k < N)
-            {
-                cpa_mat(sA, ld, qp + s.q_BAt, n, nx1);
-                if (use_Pb) cpa_vec(pbv, wk + s.w_Pb, nx1);
-            }
-            if (ng > 0) cpa_mat(sC, ld, qp + s.q_DCt, n, ng);
-            if (ns > 0) cpa_vec(Zi, wk + s.w_Zsi, 2 * ns);
+            const double *Lg = CX.wk + s.w_L, *Li = CX.wk + s.w_Linv;
             if (k > 0)
             {
-                const StageDesc &sp = SD[k - 1];
-                prefetch_l2(qp + sp.q_stage, sp.q_stage_bytes);
-                prefetch_l2(wk + sp.w_fac, sp.w_fac_bytes);
+                const StageDesc &sp = CX.SD[k - 1];
+                prefetch_l2(CX.qp + sp.q_BAt, (unsigned) (ev(sp.n * sp.nx1) * sizeof(double)));
+                prefetch_l2(CX.wk + sp.w_fac, sp.w_fac_bytes);
             }
             {
-                const double *gl = sol + s.sol.lam, *gt = sol + s.sol.t, *grd = rd(rhs, s), *grm = rm(rhs, s);
-                const double t_min_inv = o.t_min > 0 ? 1.0 / o.t_min : 1e30;
+                const double *g_ = rg(rhs, s);
+                for (int i = tid; i < n; i += NT) v[i] = g_[i];
+                const double *gl = CX.sol + s.sol.lam, *gt = CX.sol + s.sol.t, *grd = rd(rhs, s), *gm = CX.qp + s.q_dmask;
+                double *grm = rm(rhs, s);
+                const double *bk = CX.wk + s.w_rmb, *dl = CX.wk + s.step.lam, *dtt = CX.wk + s.step.t;
+                const double t_min_inv = CX.o.t_min > 0 ? 1.0 / CX.o.t_min : 1e30;
                 for (int i = tid; i < nc; i += NT)
                 {
                     const double l = gl[i], tt = gt[i], ti = 1.0 / tt;
+                    double m;
+                    if (rm_mode == 0) m = grm[i];
+                    else
+                    {
+                        m = rm_mode == 1 ? bk[i] + dtt[i] * dl[i] - sigma_mu : bk[i] - sigma_mu;
+                        if (CX.mask_constr) m *= __ldg(gm + i);
+                        grm[i] = m;
+                    }
                     // the slack elimination needs the Gamma of the factorisation (clipped when t_lam_min==1)
-                    Gam[i] = (ns > 0 && o.t_lam_min == 1) ? (tt < o.t_min ? t_min_inv : ti) * (l < o.lam_min ? o.lam_min : l) : ti * l;
-                    gam[i] = ti * (grm[i] - l * grd[i]);
+                    Gam[i] = (ns > 0 && CX.o.t_lam_min == 1) ? (tt < CX.o.t_min ? t_min_inv : ti) * (l < CX.o.lam_min ? CX.o.lam_min : l) : ti * l;
+                    gam[i] = ti * (m - l * grd[i]);
+                }
+                if (ns > 0)
+                {
+                    const double *z_ = CX.wk + s.w_Zsi;
+                    for (int j = tid; j < 2 * ns; j += NT) Zi[j] = z_[j];
                 }
             }
-            cpa_wait();
             sync();
             if (ns > 0)
             {
@@ -832,23 +907,29 @@ struct Ker
             if (k < N)
             {
                 if (use_Pb)
-                    for (int j = tid; j < nx1; j += NT) tmpx[j] = xprev[j] + pbv[j];
-                else
                 {
-                    const double *b_ = rb(rhs, s);
-                    const double *Lx = Lnext + nu1 + ld_next * nu1;
-                    for (int j = tid; j < nx1; j += NT) tmpl[j] = dot(Lx + j + ld_next * j, 1, b_ + j, 1, nx1 - j);
+                    const double *pb = CX.wk + s.w_Pb;
+                    for (int j = tid; j < nx1; j += NT) tmpx[j] = xprev[j] + pb[j];
+                }
+                else
+                {   // P b = Lxx (Lxx' b) from the factor of stage k+1 in global memory
+                    const double *L1 = CX.wk + CX.SD[k + 1].w_L + nu1 + n1 * nu1, *b_ = rb(rhs, s);
+                    for (int j = tid; j < nx1; j += NT) tmpx[j] = b_[j];
                     sync();
-                    for (int i = tid; i < nx1; i += NT) tmpx[i] = dot(Lx + i, ld_next, tmpl, 1, i + 1) + xprev[i];
+                    for (int j = tid; j < nx1; j += NT) tmpl[j] = gdot<false>(L1 + j + n1 * j, 1, tmpx + j, nx1 - j);
+                    sync();
+                    for (int i = tid; i < nx1; i += NT) tmpx[i] = gdot<false>(L1 + i, n1, tmpl, i + 1) + xprev[i];
                 }
             }
             sync();
-            for (int i = tid; i < n; i += NT)
             {
-                double acc = v[i];
-                for (int g = 0; g < ng; g++) acc += sC[i + ld * g] * tmp1[nb + g];
-                acc += dot(sA + i, ld, tmpx, 1, nx1);
-                v[i] = acc;
+                const double *Ag = CX.qp + s.q_BAt, *Cg = CX.qp + s.q_DCt;
+                for (int i = tid; i < n; i += NT)
+                {
+                    double acc = v[i] + gdot<true>(Ag + i, n, tmpx, nx1);
+                    for (int g = 0; g < ng; g++) acc += __ldg(Cg + i + n * g) * tmp1[nb + g];
+                    v[i] = acc;
+                }
             }
             sync();
             // TRSV_LNN(_MN): forward substitution on the first nsolve columns
@@ -857,27 +938,20 @@ struct Ker
                 for (int j = 0; j < nsolve; j++)
                 {
                     double part = 0.0;
-                    for (int c = tid; c < j; c += 32) part += Lcur[j + ld * c] * v[c];
+                    for (int c = tid; c < j; c += 32) part += Lg[j + n * c] * v[c];
                     part = wsum(part);
-                    if (tid == 0) v[j] = (v[j] - part) * Linv[j];
+                    if (tid == 0) v[j] = (v[j] - part) * Li[j];
                     __syncwarp();
                 }
             }
             sync();
-            for (int i = nsolve + tid; i < n; i += NT) v[i] -= dot(Lcur + i, ld, v, 1, nsolve);
+            for (int i = nsolve + tid; i < n; i += NT) v[i] -= gdot<false>(Lg + i, n, v, nsolve);
             sync();
             {
                 double *o_ = vux(dst, s);
                 for (int i = tid; i < n; i += NT) o_[i] = v[i];
                 for (int j = tid; j < s.nx; j += NT) xprev[j] = v[nu + j];
             }
-            if (!use_Pb && k > 0)
-            {   // stage k-1 needs the xx block of this factor
-                sync();
-                cpa_mat(Lcur, ld, wk + s.w_L, n, n);
-                cpa_wait();
-            }
-            ld_next = ld;
             sync();
         }
     }
@@ -887,55 +961,51 @@ struct Ker
     // (:1176-1193, EXPAND_SLACKS :524-598, COMPUTE_LAM_T_QP x_core_qp_ipm_aux.c:164-189) + the
     // ratio test (COMPUTE_ALPHA_QP :375-398).  after_fact: start from -lrow, pi = P x + p with p from lrow;
     // else: start from the backward quantities stored in the step set, pi = p_backward + P x.
-    // Returns the step length alpha of this step set.
+    // do_lin: the residual of the linear system (OCP_QP_RES_COMPUTE_LIN) of this step is evaluated in the same
+    // sweep -> residual set 1, norms in lin_nrm (only res_g needs matrix work: the other three parts vanish up to
+    // round-off by construction of x_{k+1}, dt and dlam and are evaluated with the reference's formulas).
+    // Returns the step length alpha of this step set.  Matrices straight from global memory.
     // ---------------------------------------------------------------------------------------------
-    __device__ __noinline__ double forward_pass(int rhs, int dst, int after_fact, int mask_out)
+    __device__ __noinline__ double forward_pass(int rhs, int dst, int after_fact, int mask_out, int do_lin, double lin_nrm[4])
     {
-        const int N = P.N;
-        double *v = sV, *x1 = v + ev(P.nvsmax), *tmp = x1 + ev(P.nxmax), *Linv = tmp + ev(P.nxmax);
-        double *p1 = Linv + ev(P.nmax), *Gam = p1 + ev(P.nxmax), *dt = Gam + ev(P.ncmax), *lam = dt + ev(P.ncmax);
-        double *Zi = lam + ev(P.ncmax), *ds = Zi + ev(2 * P.nsmax), *bv_ = ds + ev(2 * P.nsmax);
-        double *Lcur = sM, *Lnext = sAL;
+        const int N = CX.P.N;
+        double *v = SV_, *x1 = v + ev(CX.P.nvsmax), *tmp = x1 + ev(CX.P.nxmax), *p1 = tmp + ev(CX.P.nxmax), *pik = p1 + ev(CX.P.nxmax);
+        double *pim = pik + ev(CX.P.nxmax), *Gam = pim + ev(CX.P.nxmax), *dt = Gam + ev(CX.P.ncmax), *lam = dt + ev(CX.P.ncmax);
+        double *dlm = lam + ev(CX.P.ncmax), *Zi = dlm + ev(CX.P.ncmax), *ds = Zi + ev(2 * CX.P.nsmax), *g_ = ds + ev(2 * CX.P.nsmax);
+        double *tmp0 = g_ + ev(CX.P.nvsmax);
         double alpha = 1.0;
-        // stage 0 factor
-        {
-            const StageDesc &s = SD[0];
-            cpa_mat(Lcur, s.n | 1, wk + s.w_L, s.n, s.n);
-        }
+        double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+        int f0 = 0, f1 = 0, f2 = 0, f3 = 0;
         for (int k = 0; k <= N; k++)
         {
-            const StageDesc &s = SD[k];
-            const int n = s.n, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1, nu1 = s.nu1, n1 = s.n1;
-            const int *idxb = ipool + s.idx_off, *rev = idxb + nb;
-            const int nsolve = k == 0 ? n : s.nu;
-            const int ld = n | 1, ld1 = n1 | 1;
-            cpa_vec(Linv, wk + s.w_Linv, n);
+            const StageDesc &s = CX.SD[k];
+            const int n = s.n, nu = s.nu, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1, nu1 = s.nu1, n1 = s.n1;
+            const int *idxb = CX.ipool + s.idx_off, *rev = idxb + nb;
+            const int nsolve = k == 0 ? n : nu;
+            const double *Lg = CX.wk + s.w_L, *Li = CX.wk + s.w_Linv;
+            const double *Ag = CX.qp + s.q_BAt, *Cg = CX.qp + s.q_DCt;
             {
-                const double *src = after_fact ? wk + s.w_lrow : vux(dst, s);
+                const double *src = after_fact ? CX.wk + s.w_lrow : vux(dst, s);
                 for (int i = tid; i < nsolve; i += NT) v[i] = -src[i];
                 // x part (k>0) was written into v by the previous stage
             }
             if (k < N)
             {
-                const StageDesc &s1 = SD[k + 1];
-                cpa_mat(sA, ld, qp + s.q_BAt, n, nx1);
-                cpa_mat(Lnext, ld1, wk + s1.w_L, n1, n1);
-                cpa_vec(p1, after_fact ? wk + s1.w_lrow + nu1 : vux(dst, s1) + nu1, nx1);   // p part / backward value of x_{k+1}
-                cpa_vec(bv_, rb(rhs, s), nx1);
+                const StageDesc &s1 = CX.SD[k + 1];
+                const double *ps = after_fact ? CX.wk + s1.w_lrow + nu1 : vux(dst, s1) + nu1;   // p part / backward value of x_{k+1}
+                for (int j = tid; j < nx1; j += NT) p1[j] = ps[j];
+                prefetch_l2(CX.qp + s1.q_stage, s1.q_stage_bytes);
                 if (k + 1 < N)
                 {
-                    const StageDesc &s2 = SD[k + 2];
-                    prefetch_l2(wk + s2.w_fac, s2.w_fac_bytes);
+                    const StageDesc &s2 = CX.SD[k + 2];
+                    prefetch_l2(CX.wk + s2.w_fac, s2.w_fac_bytes);
                 }
-                prefetch_l2(qp + s1.q_stage, s1.q_stage_bytes);
             }
-            if (ng > 0) cpa_mat(sC, ld, qp + s.q_DCt, n, ng);
             if (ns > 0)
             {
-                cpa_vec(Zi, wk + s.w_Zsi, 2 * ns);
-                cpa_vec(ds, vux(dst, s) + n, 2 * ns);
+                const double *z_ = CX.wk + s.w_Zsi, *d_ = vux(dst, s) + n;
+                for (int j = tid; j < 2 * ns; j += NT) { Zi[j] = z_[j]; ds[j] = d_[j]; }
             }
-            cpa_wait();
             sync();
             // TRSV_LTN(_MN): back substitution with the transposed factor on the first nsolve unknowns
             if (tid < 32)
@@ -943,9 +1013,9 @@ struct Ker
                 for (int j = nsolve - 1; j >= 0; j--)
                 {
                     double part = 0.0;
-                    for (int i = j + 1 + tid; i < n; i += 32) part += Lcur[i + ld * j] * v[i];
+                    for (int i = j + 1 + tid; i < n; i += 32) part += Lg[i + n * j] * v[i];
                     part = wsum(part);
-                    if (tid == 0) v[j] = (v[j] - part) * Linv[j];
+                    if (tid == 0) v[j] = (v[j] - part) * Li[j];
                     __syncwarp();
                 }
             }
@@ -956,36 +1026,53 @@ struct Ker
             }
             if (k < N)
             {
-                const double *Lx = Lnext + nu1 + ld1 * nu1;
-                for (int j = tid; j < nx1; j += NT) x1[j] = bv_[j] + dot(sA + ld * j, 1, v, 1, n);
+                const double *L1 = CX.wk + CX.SD[k + 1].w_L + nu1 + n1 * nu1;      // Lxx of stage k+1: L1[i + n1*j]
+                const double *b_ = rb(rhs, s);
+                double *ob = rb(1, s);
+                for (int j = tid; j < nx1; j += NT)
+                {
+                    const double acc = gdot<true>(Ag + n * j, 1, v, n), bv = b_[j];
+                    const double xj = bv + acc;
+                    x1[j] = xj;
+                    if (do_lin)
+                    {
+                        const double r = bv - xj + acc;
+                        ob[j] = r;
+                        const double a = fabs(r);
+                        m1 = fmax(m1, a);
+                        f1 |= (a != a);
+                    }
+                }
                 sync();
                 for (int j = tid; j < nx1; j += NT)
                 {
-                    const double acc = dot(Lx + j + ld1 * j, 1, x1 + j, 1, nx1 - j);
+                    const double acc = gdot<false>(L1 + j + n1 * j, 1, x1 + j, nx1 - j);
                     tmp[j] = after_fact ? acc + p1[j] : acc;
                 }
                 sync();
                 double *pi = vpi(dst, s);
                 for (int i = tid; i < nx1; i += NT)
                 {
-                    const double acc = dot(Lx + i, ld1, tmp, 1, i + 1);
-                    pi[i] = after_fact ? acc : acc + p1[i];
+                    const double acc = gdot<false>(L1 + i, n1, tmp, i + 1);
+                    const double pv = after_fact ? acc : acc + p1[i];
+                    pi[i] = pv;
+                    pik[i] = pv;
                 }
             }
             // ---- constraint part of the step at this stage
             {
-                const double *gl = sol + s.sol.lam, *gt = sol + s.sol.t;
-                const double t_min_inv = o.t_min > 0 ? 1.0 / o.t_min : 1e30;
+                const double *gl = CX.sol + s.sol.lam, *gt = CX.sol + s.sol.t;
+                const double t_min_inv = CX.o.t_min > 0 ? 1.0 / CX.o.t_min : 1e30;
                 for (int i = tid; i < nc; i += NT)
                 {
                     const double l = gl[i], tt = gt[i];
                     lam[i] = l;
-                    Gam[i] = (ns > 0 && o.t_lam_min == 1) ? (tt < o.t_min ? t_min_inv : 1.0 / tt) * (l < o.lam_min ? o.lam_min : l)
+                    Gam[i] = (ns > 0 && CX.o.t_lam_min == 1) ? (tt < CX.o.t_min ? t_min_inv : 1.0 / tt) * (l < CX.o.lam_min ? CX.o.lam_min : l)
                                                           : (1.0 / tt) * l;
                 }
                 for (int i = tid; i < nbg; i += NT)
                 {
-                    const double a = i < nb ? v[idxb[i]] : dot(sC + ld * (i - nb), 1, v, 1, n);
+                    const double a = i < nb ? v[idxb[i]] : gdot<true>(Cg + n * (i - nb), 1, v, n);
                     dt[i] = a;
                     dt[nbg + i] = -a;
                 }
@@ -1012,35 +1099,105 @@ struct Ker
                     for (int j = tid; j < 2 * ns; j += NT) o_[j] = ds[j];
                 }
                 sync();
-                const double *grd = rd(rhs, s), *grm = rm(rhs, s), *gm = qp + s.q_dmask;
-                double *odl = vlam(dst, s), *odt = vt(dst, s);
+                const double *grd = rd(rhs, s), *grm = rm(rhs, s), *gm = CX.qp + s.q_dmask;
+                double *odl = vlam(dst, s), *odt = vt(dst, s), *ld_ = rd(1, s), *lm_ = rm(1, s);
                 for (int i = tid; i < nc; i += NT)
                 {
-                    const double l = lam[i], tt = gt[i], ti = 1.0 / tt, rdi = grd[i];
-                    double dl = -ti * (grm[i] + (l * dt[i]) - (l * rdi));
-                    double dti = dt[i] - rdi;
-                    if (mask_constr && mask_out)
+                    const double l = lam[i], tt = gt[i], ti = 1.0 / tt, rdi = grd[i], rmi = grm[i];
+                    const double dtr = dt[i];
+                    double dl = -ti * (rmi + (l * dtr) - (l * rdi));
+                    double dti = dtr - rdi;
+                    const double mk = CX.mask_constr ? __ldg(gm + i) : 1.0;
+                    if (CX.mask_constr && mask_out)
                     {
-                        const double mk = gm[i];
                         dl *= mk;
                         dti *= mk;
                     }
                     odl[i] = dl;
                     odt[i] = dti;
+                    dlm[i] = CX.mask_constr ? dl * mk : dl;     // masked step multipliers (tmp_lam_mask of the linear residual)
                     if (dst == 1)
                     {   // ratio test on the main step (min over constraints, see COMPUTE_ALPHA_QP)
                         if (l + dl < 0.0) alpha = fmin(alpha, -l / dl);
                         if (tt + dti < 0.0) alpha = fmin(alpha, -tt / dti);
                     }
+                    if (do_lin)
+                    {
+                        // res_d = rhs_d + dt -/+ (v[idxb] | C'v) [- ds] = rhs_d + dt - dtr ;  res_m = rhs_m + lam dt + dlam t
+                        double r = (dti + rdi) - dtr;
+                        if (CX.mask_constr) r *= mk;
+                        ld_[i] = r;
+                        double a = fabs(r);
+                        m2 = fmax(m2, a);
+                        f2 |= (a != a);
+                        double mm = rmi + l * dti + dl * tt;
+                        if (CX.mask_constr) mm *= mk;
+                        lm_[i] = mm;
+                        a = fabs(mm);
+                        m3 = fmax(m3, a);
+                        f3 |= (a != a);
+                    }
                 }
             }
             sync();
+            if (do_lin)
+            {
+                // ---- res_g of the linear system (lane = row): H dux + rhs_g - dpi_{k-1} + A dpi_k + constraint multipliers
+                const double *Hg = CX.qp + s.q_RSQ, *gv = rg(rhs, s);
+                for (int i = tid; i < nbg; i += NT) tmp0[i] = dlm[nbg + i] - dlm[i];
+                sync();
+                for (int i = tid; i < n; i += NT)
+                {
+                    double r = gdot_sym(Hg, n, i, v) + gv[i];
+                    if (k > 0 && i >= nu) r -= pim[i - nu];
+                    r += gdot<true>(Ag + i, n, pik, nx1);
+                    for (int g = 0; g < ng; g++) r += __ldg(Cg + i + n * g) * tmp0[nb + g];
+                    g_[i] = r;
+                }
+                sync();
+                if (!s.dup_idxb)
+                    for (int i = tid; i < nb; i += NT) g_[idxb[i]] += tmp0[i];
+                else if (tid == 0)
+                    for (int i = 0; i < nb; i++) g_[idxb[i]] += tmp0[i];
+                if (ns > 0)
+                {
+                    const double *Z = CX.qp + s.q_Z, *zv = rg(rhs, s) + n;
+                    for (int j = tid; j < 2 * ns; j += NT)
+                    {
+                        double r = Z[j] * ds[j] + zv[j] - dlm[2 * nbg + j];
+                        const int jj = j < ns ? j : j - ns, offl = j < ns ? 0 : nbg;
+                        for (int i = 0; i < nbg; i++)
+                            if (rev[i] == jj) r -= dlm[offl + i];
+                        g_[n + j] = r;
+                    }
+                }
+                sync();
+                double *og = rg(1, s);
+                for (int i = tid; i < n + 2 * ns; i += NT)
+                {
+                    const double r = g_[i];
+                    og[i] = r;
+                    const double a = fabs(r);
+                    m0 = fmax(m0, a);
+                    f0 |= (a != a);
+                }
+            }
             if (k < N)
             {
-                for (int j = tid; j < nx1; j += NT) v[nu1 + j] = x1[j];
-                double *tt = Lcur; Lcur = Lnext; Lnext = tt;
+                for (int j = tid; j < nx1; j += NT)
+                {
+                    v[nu1 + j] = x1[j];
+                    pim[j] = pik[j];
+                }
             }
             sync();
+        }
+        if (do_lin)
+        {
+            lin_nrm[0] = rmax_nan(m0, f0);
+            lin_nrm[1] = rmax_nan(m1, f1);
+            lin_nrm[2] = rmax_nan(m2, f2);
+            lin_nrm[3] = rmax_nan(m3, f3);
         }
         return rmin(alpha);
     }
@@ -1049,10 +1206,10 @@ struct Ker
     __device__ __noinline__ double alpha_pass()
     {
         double alpha = 1.0;
-        for (int k = 0; k <= P.N; k++)
+        for (int k = 0; k <= CX.P.N; k++)
         {
-            const StageDesc s = SD[k];
-            const double *l = sol + s.sol.lam, *t = sol + s.sol.t, *dl = wk + s.step.lam, *dt = wk + s.step.t;
+            const StageDesc s = CX.SD[k];
+            const double *l = CX.sol + s.sol.lam, *t = CX.sol + s.sol.t, *dl = CX.wk + s.step.lam, *dt = CX.wk + s.step.t;
             for (int i = tid; i < s.nc; i += NT)
             {
                 if (l[i] + dl[i] < 0.0) alpha = fmin(alpha, -l[i] / dl[i]);
@@ -1066,13 +1223,13 @@ struct Ker
     __device__ __noinline__ double mu_aff_pass(double alpha)
     {
         double acc = 0.0;
-        for (int k = 0; k <= P.N; k++)
+        for (int k = 0; k <= CX.P.N; k++)
         {
-            const StageDesc s = SD[k];
-            const double *l = sol + s.sol.lam, *t = sol + s.sol.t, *dl = wk + s.step.lam, *dt = wk + s.step.t;
+            const StageDesc s = CX.SD[k];
+            const double *l = CX.sol + s.sol.lam, *t = CX.sol + s.sol.t, *dl = CX.wk + s.step.lam, *dt = CX.wk + s.step.t;
             for (int i = tid; i < s.nc; i += NT) acc += fabs((l[i] + alpha * dl[i]) * (t[i] + alpha * dt[i]));
         }
-        return rsum(acc) * nc_mask_inv;
+        return rsum(acc) * CX.nc_mask_inv;
     }
 
     // res_m updates of one IPM iteration (x_core_qp_ipm_aux.c:672-781):
@@ -1081,11 +1238,11 @@ struct Ker
     // mode 2: res_m <- bkp - sigma_mu                   (pure centring)
     __device__ __noinline__ void res_m_pass(int mode, double sigma_mu)
     {
-        for (int k = 0; k <= P.N; k++)
+        for (int k = 0; k <= CX.P.N; k++)
         {
-            const StageDesc s = SD[k];
-            double *m = rm(0, s), *bk = wk + s.w_rmb;
-            const double *dl = wk + s.step.lam, *dt = wk + s.step.t, *gm = qp + s.q_dmask;
+            const StageDesc s = CX.SD[k];
+            double *m = rm(0, s), *bk = CX.wk + s.w_rmb;
+            const double *dl = CX.wk + s.step.lam, *dt = CX.wk + s.step.t, *gm = CX.qp + s.q_dmask;
             for (int i = tid; i < s.nc; i += NT)
             {
                 double r;
@@ -1093,13 +1250,13 @@ struct Ker
                 {
                     const double b = m[i];
                     bk[i] = b;
-                    r = b - o.tau_min;
+                    r = b - CX.o.tau_min;
                 }
                 else if (mode == 1)
                     r = bk[i] + dt[i] * dl[i] - sigma_mu;
                 else
                     r = bk[i] - sigma_mu;
-                if (mask_constr) r *= gm[i];
+                if (CX.mask_constr) r *= gm[i];
                 m[i] = r;
             }
         }
@@ -1109,17 +1266,17 @@ struct Ker
     // step <- step + itref
     __device__ __noinline__ void add_itref()
     {
-        for (int k = 0; k <= P.N; k++)
+        for (int k = 0; k <= CX.P.N; k++)
         {
-            const StageDesc s = SD[k];
-            double *a = wk + s.step.ux;
-            const double *b = wk + s.itref.ux;
+            const StageDesc s = CX.SD[k];
+            double *a = CX.wk + s.step.ux;
+            const double *b = CX.wk + s.itref.ux;
             for (int i = tid; i < s.n + 2 * s.ns; i += NT) a[i] += b[i];
-            a = wk + s.step.pi; b = wk + s.itref.pi;
+            a = CX.wk + s.step.pi; b = CX.wk + s.itref.pi;
             for (int i = tid; i < s.nx1; i += NT) a[i] += b[i];
-            a = wk + s.step.lam; b = wk + s.itref.lam;
+            a = CX.wk + s.step.lam; b = CX.wk + s.itref.lam;
             for (int i = tid; i < s.nc; i += NT) a[i] += b[i];
-            a = wk + s.step.t; b = wk + s.itref.t;
+            a = CX.wk + s.step.t; b = CX.wk + s.itref.t;
             for (int i = tid; i < s.nc; i += NT) a[i] += b[i];
         }
         sync();
@@ -1129,25 +1286,25 @@ struct Ker
     __device__ __noinline__ void update_var(double alpha)
     {
         if (alpha < 1.0) alpha = alpha * ((1.0 - alpha) * 0.99 + alpha * 0.9999999);
-        for (int k = 0; k <= P.N; k++)
+        for (int k = 0; k <= CX.P.N; k++)
         {
-            const StageDesc s = SD[k];
-            double *a = sol + s.sol.ux;
-            const double *b = wk + s.step.ux;
+            const StageDesc s = CX.SD[k];
+            double *a = CX.sol + s.sol.ux;
+            const double *b = CX.wk + s.step.ux;
             for (int i = tid; i < s.n + 2 * s.ns; i += NT) a[i] += alpha * b[i];
-            a = sol + s.sol.pi; b = wk + s.step.pi;
+            a = CX.sol + s.sol.pi; b = CX.wk + s.step.pi;
             for (int i = tid; i < s.nx1; i += NT) a[i] += alpha * b[i];
-            double *l = sol + s.sol.lam, *t = sol + s.sol.t;
-            const double *dl = wk + s.step.lam, *dt = wk + s.step.t, *gm = qp + s.q_dmask;
+            double *l = CX.sol + s.sol.lam, *t = CX.sol + s.sol.t;
+            const double *dl = CX.wk + s.step.lam, *dt = CX.wk + s.step.t, *gm = CX.qp + s.q_dmask;
             for (int i = tid; i < s.nc; i += NT)
             {
                 double ln = l[i] + alpha * dl[i], tn = t[i] + alpha * dt[i];
-                if (o.t_lam_min == 2)
+                if (CX.o.t_lam_min == 2)
                 {
-                    ln = ln <= o.lam_min ? o.lam_min : ln;
-                    tn = tn <= o.t_min ? o.t_min : tn;
+                    ln = ln <= CX.o.lam_min ? CX.o.lam_min : ln;
+                    tn = tn <= CX.o.t_min ? CX.o.t_min : tn;
                 }
-                if (mask_constr) ln *= gm[i];
+                if (CX.mask_constr) ln *= gm[i];
                 l[i] = ln;
                 t[i] = tn;
             }
@@ -1159,16 +1316,16 @@ struct Ker
     __device__ __noinline__ void init_var()
     {
         const double thr0 = 0.1;
-        const int N = P.N;
+        const int N = CX.P.N;
         // the reference's plugin zeroes the primal iterate before every solve, whatever warm_start says
         // (acados/ocp_qp/ocp_qp_hpipm.c:333-336): warm starts carry over pi, lam and t only
-        if (o.warm_start >= 2)
+        if (CX.o.warm_start >= 2)
         {
-            const double lmin = o.warm_start >= 3 ? o.lam0_min : thr0, tmin = o.warm_start >= 3 ? o.t0_min : thr0;
+            const double lmin = CX.o.warm_start >= 3 ? CX.o.lam0_min : thr0, tmin = CX.o.warm_start >= 3 ? CX.o.t0_min : thr0;
             for (int k = 0; k <= N; k++)
             {
-                const StageDesc s = SD[k];
-                double *l = sol + s.sol.lam, *t = sol + s.sol.t, *gux = sol + s.sol.ux;
+                const StageDesc s = CX.SD[k];
+                double *l = CX.sol + s.sol.lam, *t = CX.sol + s.sol.t, *gux = CX.sol + s.sol.ux;
                 for (int i = tid; i < s.n + 2 * s.ns; i += NT) gux[i] = 0.0;
                 for (int i = tid; i < s.nc; i += NT)
                 {
@@ -1179,18 +1336,18 @@ struct Ker
             sync();
             return;
         }
-        double *ux = sV, *tt = ux + ev(P.nvsmax), *cg = tt + ev(P.ncmax);
+        double *ux = SV_, *tt = ux + ev(CX.P.nvsmax), *cg = tt + ev(CX.P.ncmax);
         for (int k = 0; k <= N; k++)
         {
-            const StageDesc s = SD[k];
+            const StageDesc s = CX.SD[k];
             const int n = s.n, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc;
-            const int *idxb = ipool + s.idx_off, *rev = idxb + nb;
-            const double *d = qp + s.q_d;
-            double *gux = sol + s.sol.ux, *gpi = sol + s.sol.pi, *gl = sol + s.sol.lam, *gt = sol + s.sol.t;
+            const int *idxb = CX.ipool + s.idx_off, *rev = idxb + nb;
+            const double *d = CX.qp + s.q_d;
+            double *gux = CX.sol + s.sol.ux, *gpi = CX.sol + s.sol.pi, *gl = CX.sol + s.sol.lam, *gt = CX.sol + s.sol.t;
             for (int i = tid; i < s.nx1; i += NT) gpi[i] = 0.0;
-            if (o.t0_init == 0 || o.t0_init == 1)
+            if (CX.o.t0_init == 0 || CX.o.t0_init == 1)
             {
-                const double l0 = o.t0_init == 0 ? sqrt(o.mu0) : o.mu0, t0 = o.t0_init == 0 ? sqrt(o.mu0) : 1.0;
+                const double l0 = CX.o.t0_init == 0 ? sqrt(CX.o.mu0) : CX.o.mu0, t0 = CX.o.t0_init == 0 ? sqrt(CX.o.mu0) : 1.0;
                 for (int i = tid; i < n + 2 * ns; i += NT) gux[i] = 0.0;
                 for (int i = tid; i < nc; i += NT) { gl[i] = l0; gt[i] = t0; }
                 continue;
@@ -1240,7 +1397,7 @@ struct Ker
             sync();
             if (ng > 0)
             {
-                const double *Cm = qp + s.q_DCt;
+                const double *Cm = CX.qp + s.q_DCt;
                 for (int g = tid; g < ng; g += NT)
                 {
                     double acc = 0.0;
@@ -1263,7 +1420,7 @@ struct Ker
             for (int i = tid; i < nc; i += NT)
             {
                 gt[i] = tt[i];
-                gl[i] = o.mu0 / tt[i];
+                gl[i] = CX.o.mu0 / tt[i];
             }
             sync();
         }
@@ -1275,149 +1432,145 @@ struct Ker
     // ---------------------------------------------------------------------------------------------
     __device__ __noinline__ void solve(cuipm_info *info, double *stat)
     {
-        const int N = P.N;
+        const int N = CX.P.N;
         const int SM = CUIPM_STAT_M;
         double res_max[4] = {0, 0, 0, 0}, mu = 0.0, obj = 0.0, gap = 0.0;
         int lq_count = 0, status, iter = 0;
         if (stat)
-            for (int i = tid; i < SM * (o.stat_max + 1); i += NT) stat[i] = 0.0;
+            for (int i = tid; i < SM * (CX.o.stat_max + 1); i += NT) stat[i] = 0.0;
 #ifdef CUIPM_PROFILE
         if (tid == 0)
-            for (int i = 0; i < 16; i++) prof[i] = 0;
+            for (int i = 0; i < 16; i++) CX.prof[i] = 0;
 #endif
 
         // constraint mask census (x_ocp_qp_ipm.c:2774-2806)
         int cnt = 0;
         for (int k = 0; k <= N; k++)
         {
-            const StageDesc s = SD[k];
-            const double *gm = qp + s.q_dmask;
+            const StageDesc s = CX.SD[k];
+            const double *gm = CX.qp + s.q_dmask;
             for (int i = tid; i < s.nc; i += NT) cnt += gm[i] != 0.0;
         }
         const int nc_mask = (int) (rsum((double) cnt) + 0.5);
-        mask_constr = nc_mask < P.nct;
-        nc_mask_inv = nc_mask > 0 ? 1.0 / nc_mask : 0.0;
+        CX.mask_constr = nc_mask < CX.P.nct;
+        CX.nc_mask_inv = nc_mask > 0 ? 1.0 / nc_mask : 0.0;
 
-        if (P.nct == 0 || nc_mask == 0)
+        if (CX.P.nct == 0 || nc_mask == 0)
         {
             // no (active) constraints: one Riccati pass on the QP data (OCP_QP_FACT_SOLVE_KKT_UNCONSTR, x_ocp_qp_kkt.c:39-137)
             for (int k = 0; k <= N; k++)
             {
-                const StageDesc s = SD[k];
-                double *l = sol + s.sol.lam, *t = sol + s.sol.t, *d_ = rd(0, s), *m_ = rm(0, s), *g_ = rg(0, s), *b_ = rb(0, s);
+                const StageDesc s = CX.SD[k];
+                double *l = CX.sol + s.sol.lam, *t = CX.sol + s.sol.t, *d_ = rd(0, s), *m_ = rm(0, s), *g_ = rg(0, s), *b_ = rb(0, s);
                 for (int i = tid; i < s.nc; i += NT) { l[i] = 0.0; t[i] = 1.0; d_[i] = 0.0; m_[i] = 0.0; }
-                for (int i = tid; i < s.n; i += NT) g_[i] = (qp + s.q_rq)[i];
-                for (int i = tid; i < 2 * s.ns; i += NT) g_[s.n + i] = (qp + s.q_z)[i];
-                for (int i = tid; i < s.nx1; i += NT) b_[i] = (qp + s.q_b)[i];
+                for (int i = tid; i < s.n; i += NT) g_[i] = (CX.qp + s.q_rq)[i];
+                for (int i = tid; i < 2 * s.ns; i += NT) g_[s.n + i] = (CX.qp + s.q_z)[i];
+                for (int i = tid; i < s.nx1; i += NT) b_[i] = (CX.qp + s.q_b)[i];
             }
             sync();
             fact_backward();
-            forward_pass(0, 1, 1, 1);
+            double dmy4[4], dmy;
+            forward_pass(0, 1, 1, 1, 0, dmy4);
             for (int k = 0; k <= N; k++)
             {
-                const StageDesc s = SD[k];
-                cp(sol + s.sol.ux, wk + s.step.ux, s.n + 2 * s.ns);
-                cp(sol + s.sol.pi, wk + s.step.pi, s.nx1);
+                const StageDesc s = CX.SD[k];
+                cp(CX.sol + s.sol.ux, CX.wk + s.step.ux, s.n + 2 * s.ns);
+                cp(CX.sol + s.sol.pi, CX.wk + s.step.pi, s.nx1);
             }
             sync();
-            res_pass(0, 0, -1, 0, mu, obj, gap, res_max);
-            if (stat && 0 < o.stat_max && tid == 0)
+            res_pass(0, 0, -1, 0, 0, 0.0, mu, obj, gap, res_max, dmy);
+            if (stat && 0 < CX.o.stat_max && tid == 0)
             {   // column quirk of the reference's unconstrained branch (x_ocp_qp_ipm.c:2822-2829)
                 stat[6] = res_max[0]; stat[7] = res_max[1]; stat[8] = res_max[2]; stat[9] = res_max[3];
                 stat[10] = gap; stat[11] = obj;
             }
-            const double u0 = sol[SD[0].sol.ux];
+            const double u0 = CX.sol[CX.SD[0].sol.ux];
             status = (u0 != u0) ? CUIPM_NAN_SOL : CUIPM_SUCCESS;
         }
         else
         {
             init_var();
-            if (mask_constr)
+            if (CX.mask_constr)
             {
                 for (int k = 0; k <= N; k++)
                 {
-                    const StageDesc s = SD[k];
-                    double *l = sol + s.sol.lam;
-                    const double *gm = qp + s.q_dmask;
+                    const StageDesc s = CX.SD[k];
+                    double *l = CX.sol + s.sol.lam;
+                    const double *gm = CX.qp + s.q_dmask;
                     for (int i = tid; i < s.nc; i += NT) l[i] *= gm[i];
                 }
                 sync();
             }
-            double alpha = 1.0;
-            res_pass(0, 0, -1, 0, mu, obj, gap, res_max);
-            if (stat && 0 < o.stat_max && tid == 0)
+            double alpha = 1.0, res_m_tau = 0.0;
+            res_pass(0, 0, -1, 0, 0, 0.0, mu, obj, gap, res_max, res_m_tau);
+            if (stat && 0 < CX.o.stat_max && tid == 0)
             {
                 stat[7] = res_max[0]; stat[8] = res_max[1]; stat[9] = res_max[2]; stat[10] = res_max[3];
                 stat[11] = gap; stat[12] = obj;
             }
-            double res_m_tau = res_m_tau_norm();
             int kk;
-            for (kk = 0; kk < o.iter_max && alpha > o.alpha_min
-                         && (res_max[0] > o.res_g_max || res_max[1] > o.res_b_max || res_max[2] > o.res_d_max
-                             || res_m_tau > o.res_m_max || gap > o.dual_gap_max);
+            for (kk = 0; kk < CX.o.iter_max && alpha > CX.o.alpha_min
+                         && (res_max[0] > CX.o.res_g_max || res_max[1] > CX.o.res_b_max || res_max[2] > CX.o.res_d_max
+                             || res_m_tau > CX.o.res_m_max || gap > CX.o.dual_gap_max);
                  kk++)
             {
-                double *st = (stat && kk + 1 < o.stat_max) ? stat + SM * (size_t) (kk + 1) : nullptr;
+                double *st = (stat && kk + 1 < CX.o.stat_max) ? stat + SM * (size_t) (kk + 1) : nullptr;
                 double nrm[4] = {0, 0, 0, 0}, dmy;
                 PROF_T0();
-                res_m_pass(0, 0.0);
-                PROF_ADD(5);
+                // affine direction: res_m already holds lam*t - tau_min (written by the residual sweep)
                 fact_backward();
                 PROF_ADD(2);
-                alpha = forward_pass(0, 1, 1, 1);
+                alpha = forward_pass(0, 1, 1, 1, CX.o.lq_fact == 1, nrm);
                 PROF_ADD(3);
-                if (o.lq_fact == 1)
+                if (CX.o.lq_fact == 1)
                 {
-                    res_pass(1, 1, 0, 1, dmy, dmy, dmy, nrm);
-                    PROF_ADD(1);
-                    const double g00 = (wk + SD[0].ires.g)[0];
+                    const double g00 = (CX.wk + CX.SD[0].ires.g)[0];
                     if ((nrm[0] == 0.0 && g00 != g00) || nrm[0] > 1e-5 || nrm[1] > 1e-5 || nrm[2] > 1e-5 || nrm[3] > 1e-5)
                         lq_count++;
                 }
                 if (st && tid == 0) { st[0] = alpha; st[1] = alpha; }
                 int itref1 = 0;
-                if (o.pred_corr == 1)
+                if (CX.o.pred_corr == 1)
                 {
                     double mu_aff = mu_aff_pass(alpha);
                     const double tmp = mu_aff / mu;
                     const double sigma = tmp * tmp * tmp;
                     double sigma_mu = sigma * mu;
-                    sigma_mu = sigma_mu > o.tau_min ? sigma_mu : o.tau_min;
+                    sigma_mu = sigma_mu > CX.o.tau_min ? sigma_mu : CX.o.tau_min;
                     if (st && tid == 0) { st[2] = mu_aff; st[3] = sigma; }
-                    res_m_pass(1, sigma_mu);
                     PROF_ADD(5);
-                    solve_backward(0, 1, 1);
+                    solve_backward(0, 1, 1, 1, sigma_mu);
                     PROF_ADD(4);
-                    alpha = forward_pass(0, 1, 0, 1);
+                    const int want_lin = CX.o.itref_corr_max > 0;
+                    alpha = forward_pass(0, 1, 0, 1, want_lin, nrm);
                     PROF_ADD(3);
-                    if (o.cond_pred_corr == 1)
+                    if (CX.o.cond_pred_corr == 1)
                     {
                         const double mu_aff0 = mu_aff;
                         mu_aff = mu_aff_pass(alpha);
                         if (mu_aff > 2.0 * mu_aff0)
                         {
-                            res_m_pass(2, sigma_mu);
-                            solve_backward(0, 1, 1);
-                            alpha = forward_pass(0, 1, 0, 1);
+                            solve_backward(0, 1, 1, 2, sigma_mu);
+                            alpha = forward_pass(0, 1, 0, 1, want_lin, nrm);
                         }
                     }
                     int iter_ref_step = 0;
-                    if (o.itref_corr_max > 0)
+                    if (CX.o.itref_corr_max > 0)
                     {
-                        for (itref1 = 0; itref1 < o.itref_corr_max; itref1++)
+                        for (itref1 = 0; itref1 < CX.o.itref_corr_max; itref1++)
                         {
                             PROF_ADD(5);
-                            res_pass(1, 1, 0, 1, dmy, dmy, dmy, nrm);
-                            PROF_ADD(1);
-                            if ((nrm[0] < o.res_g_max || nrm[0] < 1e-3 * res_max[0]) && (nrm[1] < o.res_b_max || nrm[1] < 1e-3 * res_max[1])
-                                && (nrm[2] < o.res_d_max || nrm[2] < 1e-3 * res_max[2]) && (nrm[3] < o.res_m_max || nrm[3] < 1e-3 * res_max[3]))
+                            // nrm = norms of the linear residual of the current step (from the fused sweep, or recomputed below)
+                            if ((nrm[0] < CX.o.res_g_max || nrm[0] < 1e-3 * res_max[0]) && (nrm[1] < CX.o.res_b_max || nrm[1] < 1e-3 * res_max[1])
+                                && (nrm[2] < CX.o.res_d_max || nrm[2] < 1e-3 * res_max[2]) && (nrm[3] < CX.o.res_m_max || nrm[3] < 1e-3 * res_max[3]))
                                 break;
-                            solve_backward(1, 2, 0);
-                            forward_pass(1, 2, 0, 0);
+                            solve_backward(1, 2, 0, 0, 0.0);
+                            forward_pass(1, 2, 0, 0, 0, nrm);
                             iter_ref_step = 1;
                             add_itref();
+                            res_pass(1, 1, 0, 1, 0, 0.0, dmy, dmy, dmy, nrm, dmy);
+                            PROF_ADD(1);
                         }
-                        if (itref1 == o.itref_corr_max) res_pass(1, 1, 0, 1, dmy, dmy, dmy, nrm);
                         if (st && tid == 0) { st[16] = nrm[0]; st[17] = nrm[1]; st[18] = nrm[2]; st[19] = nrm[3]; }
                     }
                     if (iter_ref_step) alpha = alpha_pass();
@@ -1425,26 +1578,24 @@ struct Ker
                 }
                 if (st && tid == 0) st[15] = itref1;
                 PROF_ADD(5);
-                update_var(alpha);
-                PROF_ADD(5);
-                res_pass(0, 0, -1, 0, mu, obj, gap, res_max);
+                // move along the step and evaluate the residuals of the new iterate in one sweep
+                res_pass(0, 0, -1, 0, 1, alpha, mu, obj, gap, res_max, res_m_tau);
                 PROF_ADD(0);
                 if (st && tid == 0)
                 {
                     st[6] = mu; st[7] = res_max[0]; st[8] = res_max[1]; st[9] = res_max[2]; st[10] = res_max[3];
                     st[11] = gap; st[12] = obj;
                 }
-                res_m_tau = res_m_tau_norm();
             }
             iter = kk;
-            if (kk == o.iter_max) status = CUIPM_MAX_ITER;
-            else if (alpha <= o.alpha_min) status = CUIPM_MIN_STEP;
+            if (kk == CX.o.iter_max) status = CUIPM_MAX_ITER;
+            else if (alpha <= CX.o.alpha_min) status = CUIPM_MIN_STEP;
             else if (mu != mu) status = CUIPM_NAN_SOL;
             else status = CUIPM_SUCCESS;
         }
 #ifdef CUIPM_PROFILE
         if (stat && tid == 0)
-            for (int i = 0; i < 16; i++) stat[SM * (size_t) o.stat_max + i] = (double) prof[i];
+            for (int i = 0; i < 16; i++) stat[SM * (size_t) CX.o.stat_max + i] = (double) CX.prof[i];
 #endif
         if (tid == 0)
         {
@@ -1464,13 +1615,13 @@ struct Ker
     {
         double m = 0.0;
         int f = 0;
-        for (int k = 0; k <= P.N; k++)
+        for (int k = 0; k <= CX.P.N; k++)
         {
-            const StageDesc s = SD[k];
-            const double *r = rm(0, s), *gm = qp + s.q_dmask;
+            const StageDesc s = CX.SD[k];
+            const double *r = rm(0, s), *gm = CX.qp + s.q_dmask;
             for (int i = tid; i < s.nc; i += NT)
             {
-                const double a = fabs(r[i] - o.tau_min * gm[i]);
+                const double a = fabs(r[i] - CX.o.tau_min * gm[i]);
                 m = fmax(m, a);
                 f |= (a != a);
             }
@@ -1482,29 +1633,21 @@ struct Ker
 template <int W>
 __global__ void __launch_bounds__(32 * W) cuipm_solve_kernel(const LaunchArgs a)
 {
-    extern __shared__ __align__(16) double smem[];
-    __shared__ double sred[W > 1 ? W : 1];
-    __shared__ Ker<W> K;
     if (threadIdx.x == 0)
     {
-        K.P = a.P;
-        K.SD = a.sd;
-        K.ipool = a.ipool;
-        K.o = a.o;
-        K.sM = smem;
-        K.sA = K.sM + a.P.sm_M;
-        K.sAL = K.sA + a.P.sm_A;
-        K.sC = K.sAL + a.P.sm_AL;
-        K.sV = K.sC + a.P.sm_C;
-        K.sred = sred;
+        CX.P = a.P;
+        CX.SD = a.sd;
+        CX.ipool = a.ipool;
+        CX.o = a.o;
     }
+    Ker<W> K;
     for (int q = blockIdx.x; q < a.nbatch; q += gridDim.x)
     {
         if (threadIdx.x == 0)
         {
-            K.qp = a.qp + (size_t) q * a.P.qp_stride;
-            K.sol = a.sol + (size_t) q * a.P.sol_stride;
-            K.wk = a.work + (size_t) q * a.P.work_stride;
+            CX.qp = a.qp + (size_t) q * a.P.qp_stride;
+            CX.sol = a.sol + (size_t) q * a.P.sol_stride;
+            CX.wk = a.work + (size_t) q * a.P.work_stride;
         }
         K.sync();
         K.solve(a.info + q, a.stat ? a.stat + (size_t) q * CUIPM_STAT_M * (a.o.stat_max + 1) : nullptr);
