@@ -106,6 +106,15 @@ static int build_desc(cuipm_solver *s, const cuipm_shape *sh)
         P.nvsmax = std::max(P.nvsmax, (int) nvs);
         P.nct += d.nc;
     }
+    // uniform interior stages? (stages 1..N-1 share (nx, nu); stage N has the same nx) -> compile-time specialised sweeps
+    P.mid_nx = P.mid_nu = 0;
+    if (N >= 3)
+    {
+        bool uni = true;
+        for (int k = 1; k <= N - 1; k++) uni = uni && sh->nx[k] == sh->nx[1] && sh->nu[k] == sh->nu[1];
+        uni = uni && sh->nx[N] == sh->nx[1];
+        if (uni) { P.mid_nx = sh->nx[1]; P.mid_nu = sh->nu[1]; }
+    }
     if (w >= (size_t) 1 << 32 || l->qp_stride >= (size_t) 1 << 32) { set_error("QP record too large for 32-bit offsets"); return CUIPM_ERR_TOO_LARGE; }
     P.qp_stride = l->qp_stride; P.sol_stride = l->sol_stride; P.work_stride = w;
     auto e = [](int n) { return (n + 1) & ~1; };

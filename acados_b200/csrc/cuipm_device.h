@@ -34,6 +34,7 @@ struct ProbDesc
     int N;
     int nmax, nxmax, ngmax, nsmax, nbgmax, ncmax, nvsmax;  // maxima over stages (nvs = n + 2 ns)
     int nct;                                               // total constraint count
+    int mid_nx, mid_nu;                                    // (nx, nu) shared by stages 1..N-1 and nx of stage N, or 0,0 if not uniform
     int pad_;
     size_t qp_stride, sol_stride, work_stride;
     // shared-memory carve (doubles)

@@ -58,10 +58,33 @@ extern __shared__ __align__(16) double g_smem[];
 #define PROF_ADD(slot) do {} while (0)
 #endif
 
-template <int W>
+// Stage dimensions seen by the sweep bodies: RDims reads them from the stage descriptor at run time, SDims<..> makes
+// them compile-time constants for the interior stages of a uniform horizon, so that every dot product is fully
+// unrolled with immediate address offsets (the generic path spends ~5 integer instructions per matrix element on
+// 64-bit address arithmetic).
+struct RDims
+{
+    __device__ __forceinline__ int n(const StageDesc &s) const { return s.n; }
+    __device__ __forceinline__ int nu(const StageDesc &s) const { return s.nu; }
+    __device__ __forceinline__ int nx1(const StageDesc &s) const { return s.nx1; }
+    __device__ __forceinline__ int nu1(const StageDesc &s) const { return s.nu1; }
+    __device__ __forceinline__ int n1(const StageDesc &s) const { return s.n1; }
+};
+template <int NX_, int NU_>
+struct SDims   // interior stage k (1 <= k <= N-2) of a horizon with uniform (nx, nu): stage k+1 has the same dims
+{
+    __device__ __forceinline__ constexpr int n(const StageDesc &) const { return NX_ + NU_; }
+    __device__ __forceinline__ constexpr int nu(const StageDesc &) const { return NU_; }
+    __device__ __forceinline__ constexpr int nx1(const StageDesc &) const { return NX_; }
+    __device__ __forceinline__ constexpr int nu1(const StageDesc &) const { return NU_; }
+    __device__ __forceinline__ constexpr int n1(const StageDesc &) const { return NX_ + NU_; }
+};
+
+template <int W, int SNX, int SNU>
 struct Ker
 {
     static constexpr int NT = 32 * W;
+    using SMid = SDims<SNX, SNU>;
 
     // ---- CTA primitives -------------------------------------------------------------------------
     __device__ __forceinline__ void sync()
@@ -71,11 +94,11 @@ struct Ker
     }
     __device__ __forceinline__ double wsum(double v)
     {
-#pragma unroll
+#pragma unroll 2
         for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
         return v;
     }
-    __device__ double rsum(double v)
+    __device__ __noinline__ double rsum(double v)
     {
         v = wsum(v);
         if (W > 1)
@@ -83,31 +106,31 @@ struct Ker
             if ((tid & 31) == 0) g_red[tid >> 5] = v;
             __syncthreads();
             v = 0.0;
-#pragma unroll
+#pragma unroll 2
             for (int w = 0; w < W; w++) v += g_red[w];
             __syncthreads();
         }
         return v;
     }
-    __device__ double rmin(double v)
+    __device__ __noinline__ double rmin(double v)
     {
-#pragma unroll
+#pragma unroll 2
         for (int m = 16; m > 0; m >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, m));
         if (W > 1)
         {
             if ((tid & 31) == 0) g_red[tid >> 5] = v;
             __syncthreads();
             v = g_red[0];
-#pragma unroll
+#pragma unroll 2
             for (int w = 1; w < W; w++) v = fmin(v, g_red[w]);
             __syncthreads();
         }
         return v;
     }
     // max of non-negative values; NaN is propagated (BLASFEO VECNRM_INF semantics, d_aux_lib4.c:4893-4995)
-    __device__ double rmax_nan(double v, int isnan_)
+    __device__ __noinline__ double rmax_nan(double v, int isnan_)
     {
-#pragma unroll
+#pragma unroll 2
         for (int m = 16; m > 0; m >>= 1)
         {
             v = fmax(v, __shfl_xor_sync(0xffffffffu, v, m));
@@ -119,7 +142,7 @@ struct Ker
             __syncthreads();
             v = 0.0;
             isnan_ = 0;
-#pragma unroll
+#pragma unroll 2
             for (int w = 0; w < W; w++)
             {
                 double x = g_red[w];
@@ -226,6 +249,13 @@ struct Ker
         if (tid == 0 && bytes)
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
     }
+    // L1 prefetch of n doubles starting at p (one 128-byte line per thread and round): issued at the top of a stage so
+    // that the dependent phases below (each a short global-load -> shared -> barrier chain) hit L1 instead of paying an
+    // L2 / HBM round trip each
+    __device__ __forceinline__ void pf1(const double *p, int n) const
+    {
+        for (int i = tid * 16; i < n; i += NT * 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + i));
+    }
     // sum_c a[c*sa] * b[c*sb] on shared memory operands, 4 independent chains
     __device__ __forceinline__ double dot(const double *a, int sa, const double *b, int sb, int len)
     {
@@ -266,9 +296,11 @@ struct Ker
         for (int k = 0; k <= N; k++)
         {
             const StageDesc &s = CX.SD[k];
-            const int n = s.n, nu = s.nu, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1;
+            auto body = [&](auto dd) {
+            const int n = dd.n(s), nu = dd.nu(s), nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = dd.nx1(s);
             const int *idxb = CX.ipool + s.idx_off, *rev = idxb + nb;
             const double *qk = CX.qp;
+            pf1(qk + s.q_stage, (int) (s.q_stage_bytes >> 3));
             // ---- vectors of this stage (optionally moved along the step) to shared memory
             {
                 double *gu = vux(pset, s);
@@ -471,6 +503,9 @@ struct Ker
             sync();
             for (int j = tid; j < nx1; j += NT) pim[j] = pi[j];      // pi_k is "pi_{k-1}" of the next stage
             sync();
+            };
+            if (SNX > 0 && k >= 1 && k <= N - 2) body(SMid{});
+            else body(RDims{});
         }
         nrm[0] = rmax_nan(m0, f0);
         nrm[1] = rmax_nan(m1, f1);
@@ -552,10 +587,13 @@ struct Ker
         for (int k = N; k >= 0; k--)
         {
             const StageDesc &s = CX.SD[k];
-            const int n = s.n, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1, nu1 = s.nu1, n1 = s.n1;
+            auto body = [&](auto dd) {
+            const int n = dd.n(s), nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = dd.nx1(s), nu1 = dd.nu1(s), n1 = dd.n1(s);
             const int *idxb = CX.ipool + s.idx_off;
             const int ldal = ev(n + 1), ldm = ev(n + 1);
             const int kc = k < N ? nx1 : 0;
+            pf1(CX.qp + s.q_RSQ, n * n);
+            pf1(CX.wk + s.w_vec, (int) (s.w_vec_bytes >> 3) / 3);      // step / residual vectors (first third of the vector part)
             // ---- stage inputs: [A; b'] into SAL_ (asynchronous), constraint quantities
             if (k < N)
             {
@@ -830,6 +868,9 @@ struct Ker
             }
             ldm_prev = ldm;
             sync();
+            };
+            if (SNX > 0 && k >= 1 && k <= N - 2) body(SMid{});
+            else body(RDims{});
         }
     }
 
@@ -849,10 +890,13 @@ struct Ker
         for (int k = N; k >= 0; k--)
         {
             const StageDesc &s = CX.SD[k];
-            const int n = s.n, nu = s.nu, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1, nu1 = s.nu1, n1 = s.n1;
+            auto body = [&](auto dd) {
+            const int n = dd.n(s), nu = dd.nu(s), nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = dd.nx1(s), nu1 = dd.nu1(s), n1 = dd.n1(s);
             const int *idxb = CX.ipool + s.idx_off;
             const int nsolve = k == 0 ? n : nu;
             const double *Lg = CX.wk + s.w_L, *Li = CX.wk + s.w_Linv;
+            pf1(CX.qp + s.q_BAt, n * nx1);
+            pf1(Lg, n * nsolve);
             if (k > 0)
             {
                 const StageDesc &sp = CX.SD[k - 1];
@@ -953,6 +997,9 @@ struct Ker
                 for (int j = tid; j < s.nx; j += NT) xprev[j] = v[nu + j];
             }
             sync();
+            };
+            if (SNX > 0 && k >= 1 && k <= N - 2) body(SMid{});
+            else body(RDims{});
         }
     }
 
@@ -979,11 +1026,16 @@ struct Ker
         for (int k = 0; k <= N; k++)
         {
             const StageDesc &s = CX.SD[k];
-            const int n = s.n, nu = s.nu, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1, nu1 = s.nu1, n1 = s.n1;
+            auto body = [&](auto dd) {
+            const int n = dd.n(s), nu = dd.nu(s), nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = dd.nx1(s), nu1 = dd.nu1(s), n1 = dd.n1(s);
             const int *idxb = CX.ipool + s.idx_off, *rev = idxb + nb;
             const int nsolve = k == 0 ? n : nu;
             const double *Lg = CX.wk + s.w_L, *Li = CX.wk + s.w_Linv;
             const double *Ag = CX.qp + s.q_BAt, *Cg = CX.qp + s.q_DCt;
+            pf1(Lg, n * nsolve);
+            pf1(Ag, n * nx1);
+            if (k < N) pf1(CX.wk + CX.SD[k + 1].w_L + n1 * nu1, n1 * nx1);
+            if (do_lin) pf1(CX.qp + s.q_RSQ, n * n);
             {
                 const double *src = after_fact ? CX.wk + s.w_lrow : vux(dst, s);
                 for (int i = tid; i < nsolve; i += NT) v[i] = -src[i];
@@ -1191,6 +1243,9 @@ struct Ker
                 }
             }
             sync();
+            };
+            if (SNX > 0 && k >= 1 && k <= N - 2) body(SMid{});
+            else body(RDims{});
         }
         if (do_lin)
         {
@@ -1630,8 +1685,11 @@ struct Ker
     }
 };
 
-template <int W>
-__global__ void __launch_bounds__(32 * W) cuipm_solve_kernel(const LaunchArgs a)
+#ifndef CUIPM_MINB
+#define CUIPM_MINB 16
+#endif
+template <int W, int SNX, int SNU>
+__global__ void __launch_bounds__(32 * W, (W == 1 ? CUIPM_MINB : (W == 2 ? 8 : 4))) cuipm_solve_kernel(const LaunchArgs a)
 {
     if (threadIdx.x == 0)
     {
@@ -1640,7 +1698,7 @@ __global__ void __launch_bounds__(32 * W) cuipm_solve_kernel(const LaunchArgs a)
         CX.ipool = a.ipool;
         CX.o = a.o;
     }
-    Ker<W> K;
+    Ker<W, SNX, SNU> K;
     for (int q = blockIdx.x; q < a.nbatch; q += gridDim.x)
     {
         if (threadIdx.x == 0)
@@ -1661,23 +1719,32 @@ size_t smem_bytes(const ProbDesc &P) { return sizeof(double) * (size_t) P.sm_tot
 
 int max_warps() { return 4; }
 
+template <int W, int SNX, int SNU>
+static cudaError_t launch_one(const LaunchArgs &a, size_t smem, cudaStream_t stream)
+{
+    cudaError_t err = cudaFuncSetAttribute(cuipm_solve_kernel<W, SNX, SNU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (err != cudaSuccess) return err;
+    cuipm_solve_kernel<W, SNX, SNU><<<a.nbatch, 32 * W, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+// (nx, nu) pairs with a compile-time specialisation of the interior stages (BASELINE.json configs 1-4); any other
+// shape runs the generic path
 int launch_solve(const LaunchArgs &a, int warps, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t) stream_;
     const size_t smem = smem_bytes(a.P);
-    const int grid = a.nbatch;
-    cudaError_t err;
-#define CUIPM_LAUNCH(WW)                                                                                           \
-    do {                                                                                                           \
-        err = cudaFuncSetAttribute(cuipm_solve_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
-        if (err != cudaSuccess) return (int) err;                                                                  \
-        cuipm_solve_kernel<WW><<<grid, 32 * WW, smem, stream>>>(a);                                                \
-    } while (0)
-    if (warps <= 1) CUIPM_LAUNCH(1);
-    else if (warps == 2) CUIPM_LAUNCH(2);
-    else CUIPM_LAUNCH(4);
-#undef CUIPM_LAUNCH
-    return (int) cudaGetLastError();
+    if (warps <= 1)
+    {
+        const int nx = a.P.mid_nx, nu = a.P.mid_nu;
+        if (nx == 21 && nu == 3) return (int) launch_one<1, 21, 3>(a, smem, stream);
+        if (nx == 8 && nu == 3) return (int) launch_one<1, 8, 3>(a, smem, stream);
+        if (nx == 4 && nu == 1) return (int) launch_one<1, 4, 1>(a, smem, stream);
+        if (nx == 12 && nu == 4) return (int) launch_one<1, 12, 4>(a, smem, stream);
+        return (int) launch_one<1, 0, 0>(a, smem, stream);
+    }
+    if (warps == 2) return (int) launch_one<2, 0, 0>(a, smem, stream);
+    return (int) launch_one<4, 0, 0>(a, smem, stream);
 }
 
 }  // namespace cuipm
