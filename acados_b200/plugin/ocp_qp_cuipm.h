@@ -1,0 +1,72 @@
+/*
+ * ocp_qp_cuipm.h -- acados `qp_solver` plugin backed by the cuipm CUDA library (include/cuipm.h).
+ *
+ * Drop-in for acados/ocp_qp/ocp_qp_hpipm.{c,h}: same vtable (acados/ocp_qp/ocp_qp_common.h:60-79), same option
+ * field names, same memory_get fields, same status mapping.  Inside libacados this file would live at
+ * acados/ocp_qp/ocp_qp_cuipm.h and be registered as PARTIAL_CONDENSING_CUIPM.
+ */
+#ifndef ACADOS_OCP_QP_OCP_QP_CUIPM_H_
+#define ACADOS_OCP_QP_OCP_QP_CUIPM_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#include "acados/ocp_qp/ocp_qp_common.h"
+#include "acados/utils/types.h"
+
+#include "cuipm.h"
+
+typedef struct ocp_qp_cuipm_opts_
+{
+    cuipm_opts c;       /* solver options (HPIPM field names, see cuipm_opts_set) */
+    int print_level;
+    int device;         /* CUDA device ordinal (default 0) */
+} ocp_qp_cuipm_opts;
+
+typedef struct ocp_qp_cuipm_memory_
+{
+    cuipm_solver *solver;       /* device resources; created lazily on the first evaluate, freed in terminate */
+    int max_batch;              /* capacity of `solver` */
+    int N;
+    int *dims_i;                /* nx,nu,nb,ng,ns copies: 5*(N+1) ints */
+    int *idx_pool;              /* idxb / idxs_rev copies the solver was created with */
+    int **idxb_p, **idxs_rev_p; /* per-stage pointers into idx_pool */
+    int idx_pool_len;
+    double *qp_rec, *sol_rec;   /* host staging records for the single-QP path (pinned lazily is not possible in raw memory) */
+    double *stat;               /* (stat_max+1) x CUIPM_STAT_M table of the last solve (HPIPM's layout: row per iteration) */
+    cuipm_info info;
+    double time_qp_solver_call;
+    int iter;
+    int status;                 /* HPIPM status code of the last solve */
+} ocp_qp_cuipm_memory;
+
+acados_size_t ocp_qp_cuipm_opts_calculate_size(void *config, void *dims);
+void *ocp_qp_cuipm_opts_assign(void *config, void *dims, void *raw_memory);
+void ocp_qp_cuipm_opts_initialize_default(void *config, void *dims, void *opts_);
+void ocp_qp_cuipm_opts_update(void *config, void *dims, void *opts_);
+void ocp_qp_cuipm_opts_set(void *config_, void *opts_, const char *field, void *value);
+void ocp_qp_cuipm_opts_get(void *config_, void *opts_, const char *field, void *value);
+acados_size_t ocp_qp_cuipm_memory_calculate_size(void *config, void *dims, void *opts_);
+void *ocp_qp_cuipm_memory_assign(void *config, void *dims, void *opts_, void *raw_memory);
+void ocp_qp_cuipm_memory_get(void *config_, void *mem_, const char *field, void *value);
+acados_size_t ocp_qp_cuipm_workspace_calculate_size(void *config, void *dims, void *opts_);
+int ocp_qp_cuipm(void *config, void *qp_in, void *qp_out, void *opts_, void *mem_, void *work_);
+void ocp_qp_cuipm_memory_reset(void *config_, void *qp_in_, void *qp_out_, void *opts_, void *mem_, void *work_);
+void ocp_qp_cuipm_solver_get(void *config_, void *qp_in_, void *qp_out_, void *opts_, void *mem_, const char *field, int stage,
+                             void *value, int size1, int size2);
+void ocp_qp_cuipm_eval_forw_sens(void *config_, void *qp_in, void *seed, void *qp_out, void *opts_, void *mem_, void *work_);
+void ocp_qp_cuipm_eval_adj_sens(void *config_, void *qp_in, void *seed, void *qp_out, void *opts_, void *mem_, void *work_);
+void ocp_qp_cuipm_terminate(void *config_, void *mem_, void *work_);
+void ocp_qp_cuipm_config_initialize_default(void *config);
+
+/* Batched entry the reference lacks: n structurally identical QPs in, n solutions out, one
+ * kernel launch.  `mem` must come from memory_assign of this plugin; status_out[i] receives acados return codes.
+ * Replaces the OpenMP loop over capsules of the generated batch solver (c_templates_tera/acados_solver.in.c:3223-3243)
+ * at the QP level.  Returns the worst acados status. */
+int ocp_qp_cuipm_batch_solve(void *config, int n, ocp_qp_in **qp_in, ocp_qp_out **qp_out, void *opts_, void *mem_, int *status_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

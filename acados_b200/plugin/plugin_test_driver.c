@@ -1,0 +1,216 @@
+/*
+ * plugin_test_driver.c -- TEST DRIVER (our code): runs the reference's ocp_qp_xcond_solver with its own HPIPM plugin
+ * and with the cuipm plugin swapped into the same slot, on the reference's mass-spring problem class
+ * (examples/c/no_interface_examples/mass_spring_model/mass_spring_qp.c: nx=8, nu=3, N=15, nb=11, x0 as stage-0
+ * equality boxes eliminated by the partial condensing module), for N2 in {N, 5, 3} as test/ocp_qp/test_qpsolvers.cpp
+ * does, plus the batched entry, the Riccati getters and the memory_get fields.  Exit code 0 = all checks passed.
+ *
+ * The swap `ocp_qp_cuipm_config_initialize_default(config->qp_solver)` is exactly what a
+ * `case PARTIAL_CONDENSING_CUIPM:` in ocp_qp_xcond_solver_config_initialize_from_plan would do.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "acados/ocp_qp/ocp_qp_common.h"
+#include "acados/ocp_qp/ocp_qp_xcond_solver.h"
+#include "acados_c/ocp_qp_interface.h"
+#include "blasfeo/include/blasfeo_d_aux.h"
+#include "hpipm/include/hpipm_d_ocp_qp.h"
+
+#include "ocp_qp_cuipm.h"
+
+#define NX 8
+#define NU 3
+#define NN 15
+
+static void mass_spring(double Ts, double *A, double *B)
+{   /* exp of the augmented matrix [[Ac, Bc], [0, 0]] * Ts by a Taylor series (norm ~ 1.5) */
+    enum { M = NX + NU };
+    double Mx[M * M], T[M * M], E[M * M], T2[M * M];
+    int pp = NX / 2;
+    memset(Mx, 0, sizeof(Mx));
+    for (int i = 0; i < pp; i++)
+    {
+        Mx[i + M * (pp + i)] = Ts;                 /* p' = v */
+        Mx[(pp + i) + M * i] = -2 * Ts;            /* v' = T p + u */
+        if (i > 0) Mx[(pp + i) + M * (i - 1)] = Ts;
+        if (i < pp - 1) Mx[(pp + i) + M * (i + 1)] = Ts;
+    }
+    for (int i = 0; i < NU; i++) Mx[(pp + i) + M * (NX + i)] = Ts;
+    memset(E, 0, sizeof(E)); memset(T, 0, sizeof(T));
+    for (int i = 0; i < M; i++) E[i + M * i] = T[i + M * i] = 1.0;
+    for (int it = 1; it < 30; it++)
+    {
+        memset(T2, 0, sizeof(T2));
+        for (int j = 0; j < M; j++) for (int k = 0; k < M; k++) for (int i = 0; i < M; i++) T2[i + M * j] += T[i + M * k] * Mx[k + M * j] / it;
+        memcpy(T, T2, sizeof(T));
+        for (int i = 0; i < M * M; i++) E[i] += T[i];
+    }
+    for (int j = 0; j < NX; j++) for (int i = 0; i < NX; i++) A[i + NX * j] = E[i + M * j];
+    for (int j = 0; j < NU; j++) for (int i = 0; i < NX; i++) B[i + NX * j] = E[i + M * (NX + j)];
+}
+
+typedef struct { ocp_qp_xcond_solver_config *config; ocp_qp_xcond_solver_dims *dims; void *opts; ocp_qp_solver *solver; } chain;
+
+static chain make_chain(int use_cuipm, int N2)
+{
+    chain c;
+    ocp_qp_solver_plan_t plan; plan.qp_solver = PARTIAL_CONDENSING_HPIPM;
+    c.config = ocp_qp_xcond_solver_config_create(plan);
+    if (use_cuipm) ocp_qp_cuipm_config_initialize_default(c.config->qp_solver);
+    c.dims = ocp_qp_xcond_solver_dims_create(c.config, NN);
+    for (int k = 0; k <= NN; k++)
+    {
+        int nx = NX, nu = k < NN ? NU : 0, nbx = NX, nbu = nu, z = 0;
+        c.config->dims_set(c.config, c.dims, k, "nx", &nx);
+        c.config->dims_set(c.config, c.dims, k, "nu", &nu);
+        c.config->dims_set(c.config, c.dims, k, "nbx", &nbx);
+        c.config->dims_set(c.config, c.dims, k, "nbu", &nbu);
+        c.config->dims_set(c.config, c.dims, k, "ng", &z);
+        c.config->dims_set(c.config, c.dims, k, "ns", &z);
+    }
+    int nbxe0 = NX;
+    c.config->dims_set(c.config, c.dims, 0, "nbxe", &nbxe0);
+    c.opts = ocp_qp_xcond_solver_opts_create(c.config, c.dims);
+    ocp_qp_xcond_solver_opts_set(c.config, c.opts, "cond_N", &N2);
+    c.solver = ocp_qp_create(c.config, c.dims, c.opts);
+    return c;
+}
+
+static ocp_qp_in *make_qp(chain *c, const double *x0)
+{
+    double A[NX * NX], B[NX * NU], b[NX], Q[NX * NX], R[NU * NU], S[NU * NX], q[NX], r[NU];
+    mass_spring(0.5, A, B);
+    memset(Q, 0, sizeof(Q)); memset(R, 0, sizeof(R)); memset(S, 0, sizeof(S));
+    for (int i = 0; i < NX; i++) { Q[i + NX * i] = 1.0; q[i] = 0.1; b[i] = 0.1; }
+    for (int i = 0; i < NU; i++) { R[i + NU * i] = 2.0; r[i] = 0.2; }
+    ocp_qp_in *in = ocp_qp_in_create(c->dims->orig_dims);
+    int idxb[NU + NX], idxe[NX];
+    double lb[NU + NX], ub[NU + NX];
+    for (int k = 0; k <= NN; k++)
+    {
+        int nu = k < NN ? NU : 0;
+        if (k < NN) { d_ocp_qp_set_A(k, A, in); d_ocp_qp_set_B(k, B, in); d_ocp_qp_set_b(k, b, in); d_ocp_qp_set_R(k, R, in); d_ocp_qp_set_S(k, S, in); d_ocp_qp_set_r(k, r, in); }
+        d_ocp_qp_set_Q(k, Q, in); d_ocp_qp_set_q(k, q, in);
+        for (int i = 0; i < nu; i++) { idxb[i] = i; lb[i] = -0.5; ub[i] = 0.5; }
+        for (int i = 0; i < NX; i++)
+        {
+            idxb[nu + i] = nu + i;
+            lb[nu + i] = k == 0 ? x0[i] : -4.0;
+            ub[nu + i] = k == 0 ? x0[i] : 4.0;
+        }
+        d_ocp_qp_set_idxb(k, idxb, in); d_ocp_qp_set_lb(k, lb, in); d_ocp_qp_set_ub(k, ub, in);
+    }
+    for (int i = 0; i < NX; i++) idxe[i] = i;
+    d_ocp_qp_set_idxbxe(0, idxe, in);
+    return in;
+}
+
+static double diff_out(ocp_qp_dims *d, ocp_qp_out *a, ocp_qp_out *b, double *du)
+{
+    double m = 0.0; *du = 0.0;
+    for (int k = 0; k <= d->N; k++)
+    {
+        int n = d->nu[k] + d->nx[k], nc = 2 * (d->nb[k] + d->ng[k]);
+        for (int i = 0; i < n; i++)
+        {
+            double e = fabs(BLASFEO_DVECEL(a->ux + k, i) - BLASFEO_DVECEL(b->ux + k, i));
+            if (e > m) m = e;
+            if (i < d->nu[k] && e > *du) *du = e;
+        }
+        if (k < d->N) for (int i = 0; i < d->nx[k + 1]; i++) { double e = fabs(BLASFEO_DVECEL(a->pi + k, i) - BLASFEO_DVECEL(b->pi + k, i)); if (e > m) m = e; }
+        for (int i = 0; i < nc; i++)
+        {
+            double e = fabs(BLASFEO_DVECEL(a->lam + k, i) - BLASFEO_DVECEL(b->lam + k, i)); if (e > m) m = e;
+            e = fabs(BLASFEO_DVECEL(a->t + k, i) - BLASFEO_DVECEL(b->t + k, i)); if (e > m) m = e;
+        }
+    }
+    return m;
+}
+
+int main(void)
+{
+    int fails = 0;
+    double x0[NX] = {2.5, 2.5, 0, 0, 0, 0, 0, 0};
+    int N2s[3] = {NN, 5, 3};
+    for (int t = 0; t < 3; t++)
+    {
+        chain h = make_chain(0, N2s[t]), g = make_chain(1, N2s[t]);
+        ocp_qp_in *in_h = make_qp(&h, x0), *in_g = make_qp(&g, x0);
+        ocp_qp_out *out_h = ocp_qp_out_create(h.dims->orig_dims), *out_g = ocp_qp_out_create(g.dims->orig_dims);
+        int st_h = ocp_qp_solve(h.solver, in_h, out_h), st_g = ocp_qp_solve(g.solver, in_g, out_g);
+        /* reference acceptance test (test_qpsolvers.cpp:238-251): status 0 and residuals <= 1e-8 */
+        double res[4];
+        ocp_qp_inf_norm_residuals(g.dims->orig_dims, in_g, out_g, res);
+        double du, dall = diff_out(h.dims->orig_dims, out_h, out_g, &du);
+        int it_h, it_g;
+        h.config->qp_solver->memory_get(h.config->qp_solver, ((ocp_qp_xcond_solver_memory *) h.solver->mem)->solver_memory, "iter", &it_h);
+        g.config->qp_solver->memory_get(g.config->qp_solver, ((ocp_qp_xcond_solver_memory *) g.solver->mem)->solver_memory, "iter", &it_g);
+        double maxres = fmax(fmax(res[0], res[1]), fmax(res[2], res[3]));
+        int ok = st_h == 0 && st_g == 0 && it_h == it_g && du <= 1e-10 && dall <= 1e-6 && maxres <= 1e-8;
+        printf("N2=%2d: status hpipm %d cuipm %d  iters %d %d  |du| %.2e  |dsol| %.2e  max residual (cuipm) %.2e  %s\n", N2s[t], st_h, st_g,
+               it_h, it_g, du, dall, maxres, ok ? "OK" : "FAIL");
+        fails += !ok;
+        if (t == 0)
+        {
+            /* Riccati getters through the xcond solver (ocp_qp_xcond_solver.c:424) */
+            double Kh[NU * NX], Kg[NU * NX], Ph[NX * NX], Pg[NX * NX], e = 0.0;
+            h.config->solver_get(h.config, in_h, out_h, h.opts, h.solver->mem, "K", 2, Kh, NU, NX);
+            g.config->solver_get(g.config, in_g, out_g, g.opts, g.solver->mem, "K", 2, Kg, NU, NX);
+            h.config->solver_get(h.config, in_h, out_h, h.opts, h.solver->mem, "P", 2, Ph, NX, NX);
+            g.config->solver_get(g.config, in_g, out_g, g.opts, g.solver->mem, "P", 2, Pg, NX, NX);
+            for (int i = 0; i < NU * NX; i++) e = fmax(e, fabs(Kh[i] - Kg[i]));
+            for (int i = 0; i < NX * NX; i++) e = fmax(e, fabs(Ph[i] - Pg[i]));
+            printf("getters K,P at stage 2: max diff %.2e %s\n", e, e <= 1e-6 ? "OK" : "FAIL");
+            fails += !(e <= 1e-6);
+            double tq; int sm;
+            g.config->qp_solver->memory_get(g.config->qp_solver, ((ocp_qp_xcond_solver_memory *) g.solver->mem)->solver_memory, "time_qp_solver_call", &tq);
+            g.config->qp_solver->memory_get(g.config->qp_solver, ((ocp_qp_xcond_solver_memory *) g.solver->mem)->solver_memory, "stat_m", &sm);
+            fails += !(tq > 0 && sm == CUIPM_STAT_M);
+        }
+        g.config->terminate(g.config, g.solver->mem, g.solver->work);
+        h.config->terminate(h.config, h.solver->mem, h.solver->work);
+    }
+    {
+        /* batched entry at the plugin level on x0-eliminated QPs (the xcond module of each instance does the
+         * condensing on the host, as the reference's batch solver does per capsule) */
+        enum { NB = 6 };
+        chain c = make_chain(1, NN);
+        chain hs = make_chain(0, NN);
+        ocp_qp_xcond_solver_memory *xm = c.solver->mem;
+        ocp_qp_in *ins[NB], *cin[NB];
+        ocp_qp_out *cout[NB], *outs[NB], *ref[NB];
+        int status[NB];
+        double worst = 0.0;
+        for (int i = 0; i < NB; i++)
+        {
+            double x0i[NX];
+            for (int j = 0; j < NX; j++) x0i[j] = x0[j] + 0.3 * sin(1.0 + i + 2.0 * j);
+            ins[i] = make_qp(&c, x0i);
+            outs[i] = ocp_qp_out_create(c.dims->orig_dims);
+            ref[i] = ocp_qp_out_create(c.dims->orig_dims);
+            ocp_qp_solve(hs.solver, ins[i], ref[i]);
+            /* condense (x0 elimination) with the reference's module, keep a private copy of the reduced QP */
+            c.config->xcond->condensing(ins[i], xm->xcond_qp_in, ((ocp_qp_xcond_solver_opts *) c.opts)->xcond_opts, xm->xcond_memory, NULL);
+            cin[i] = ocp_qp_in_create(c.dims->xcond_dims);
+            d_ocp_qp_copy_all(xm->xcond_qp_in, cin[i]);
+            cout[i] = ocp_qp_out_create(c.dims->xcond_dims);
+        }
+        int rc = ocp_qp_cuipm_batch_solve(c.config->qp_solver, NB, cin, cout, ((ocp_qp_xcond_solver_opts *) c.opts)->qp_solver_opts, xm->solver_memory, status);
+        for (int i = 0; i < NB; i++)
+        {
+            /* compare u of the reduced solution with the reference's full solve */
+            for (int k = 0; k < NN; k++)
+                for (int j = 0; j < NU; j++)
+                    worst = fmax(worst, fabs(BLASFEO_DVECEL(cout[i]->ux + k, j) - BLASFEO_DVECEL(ref[i]->ux + k, j)));
+            fails += status[i] != 0;
+        }
+        printf("batch entry: %d QPs, rc %d, max |du| vs per-instance HPIPM %.2e %s\n", NB, rc, worst, (rc == 0 && worst <= 1e-10) ? "OK" : "FAIL");
+        fails += !(rc == 0 && worst <= 1e-10);
+        c.config->terminate(c.config, c.solver->mem, c.solver->work);
+    }
+    printf(fails ? "PLUGIN TEST FAILED (%d)\n" : "PLUGIN TEST PASSED\n", fails);
+    return fails != 0;
+}
