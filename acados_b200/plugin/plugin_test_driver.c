@@ -19,6 +19,9 @@
 #include "blasfeo/include/blasfeo_d_aux.h"
 #include "hpipm/include/hpipm_d_ocp_qp.h"
 
+#include "acados/ocp_qp/ocp_qp_hpipm.h"
+#include "hpipm/include/hpipm_d_ocp_qp_dim.h"
+
 #include "ocp_qp_cuipm.h"
 
 #define NX 8
@@ -133,6 +136,7 @@ static double diff_out(ocp_qp_dims *d, ocp_qp_out *a, ocp_qp_out *b, double *du)
 int main(void)
 {
     int fails = 0;
+    setvbuf(stdout, NULL, _IONBF, 0);
     double x0[NX] = {2.5, 2.5, 0, 0, 0, 0, 0, 0};
     int N2s[3] = {NN, 5, 3};
     for (int t = 0; t < 3; t++)
@@ -174,42 +178,69 @@ int main(void)
         h.config->terminate(h.config, h.solver->mem, h.solver->work);
     }
     {
-        /* batched entry at the plugin level on x0-eliminated QPs (the xcond module of each instance does the
-         * condensing on the host, as the reference's batch solver does per capsule) */
+        /* batched entry at the plugin level: QPs with x0 already eliminated (stage 0: nx = 0, b_0 = b + A x0), solved
+         * one by one with the reference's HPIPM plugin and in one launch with ocp_qp_cuipm_batch_solve */
         enum { NB = 6 };
-        chain c = make_chain(1, NN);
-        chain hs = make_chain(0, NN);
-        ocp_qp_xcond_solver_memory *xm = c.solver->mem;
-        ocp_qp_in *ins[NB], *cin[NB];
-        ocp_qp_out *cout[NB], *outs[NB], *ref[NB];
+        double A[NX * NX], B[NX * NU], Q[NX * NX], R[NU * NU], q[NX], r[NU], lb[NU + NX], ub[NU + NX];
+        int idxb[NU + NX];
+        mass_spring(0.5, A, B);
+        memset(Q, 0, sizeof(Q)); memset(R, 0, sizeof(R));
+        for (int i = 0; i < NX; i++) { Q[i + NX * i] = 1.0; q[i] = 0.1; }
+        for (int i = 0; i < NU; i++) { R[i + NU * i] = 2.0; r[i] = 0.2; }
+        ocp_qp_dims *dims = ocp_qp_dims_create(NN);
+        for (int k = 0; k <= NN; k++)
+        {
+            d_ocp_qp_dim_set_nx(k, k == 0 ? 0 : NX, dims);
+            d_ocp_qp_dim_set_nu(k, k < NN ? NU : 0, dims);
+            d_ocp_qp_dim_set_nbx(k, k == 0 ? 0 : NX, dims);
+            d_ocp_qp_dim_set_nbu(k, k < NN ? NU : 0, dims);
+        }
+        qp_solver_config cfg_h, cfg_g;
+        ocp_qp_hpipm_config_initialize_default(&cfg_h);
+        ocp_qp_cuipm_config_initialize_default(&cfg_g);
+        void *oh = cfg_h.opts_assign(&cfg_h, dims, calloc(1, cfg_h.opts_calculate_size(&cfg_h, dims)));
+        void *og = cfg_g.opts_assign(&cfg_g, dims, calloc(1, cfg_g.opts_calculate_size(&cfg_g, dims)));
+        cfg_h.opts_initialize_default(&cfg_h, dims, oh); cfg_g.opts_initialize_default(&cfg_g, dims, og);
+        void *mh = cfg_h.memory_assign(&cfg_h, dims, oh, calloc(1, cfg_h.memory_calculate_size(&cfg_h, dims, oh)));
+        void *mg = cfg_g.memory_assign(&cfg_g, dims, og, calloc(1, cfg_g.memory_calculate_size(&cfg_g, dims, og)));
+        ocp_qp_in *ins[NB];
+        ocp_qp_out *outs[NB], *ref[NB];
         int status[NB];
         double worst = 0.0;
         for (int i = 0; i < NB; i++)
         {
-            double x0i[NX];
-            for (int j = 0; j < NX; j++) x0i[j] = x0[j] + 0.3 * sin(1.0 + i + 2.0 * j);
-            ins[i] = make_qp(&c, x0i);
-            outs[i] = ocp_qp_out_create(c.dims->orig_dims);
-            ref[i] = ocp_qp_out_create(c.dims->orig_dims);
-            ocp_qp_solve(hs.solver, ins[i], ref[i]);
-            /* condense (x0 elimination) with the reference's module, keep a private copy of the reduced QP */
-            c.config->xcond->condensing(ins[i], xm->xcond_qp_in, ((ocp_qp_xcond_solver_opts *) c.opts)->xcond_opts, xm->xcond_memory, NULL);
-            cin[i] = ocp_qp_in_create(c.dims->xcond_dims);
-            d_ocp_qp_copy_all(xm->xcond_qp_in, cin[i]);
-            cout[i] = ocp_qp_out_create(c.dims->xcond_dims);
+            double x0i[NX], b0[NX], bb[NX];
+            for (int j = 0; j < NX; j++) { x0i[j] = x0[j] + 0.3 * sin(1.0 + i + 2.0 * j); bb[j] = 0.1; }
+            for (int j = 0; j < NX; j++) { b0[j] = 0.1; for (int c = 0; c < NX; c++) b0[j] += A[j + NX * c] * x0i[c]; }
+            ins[i] = ocp_qp_in_create(dims);
+            for (int k = 0; k <= NN; k++)
+            {
+                int nu = k < NN ? NU : 0, nx = k == 0 ? 0 : NX;
+                if (k < NN)
+                {
+                    if (k > 0) d_ocp_qp_set_A(k, A, ins[i]);
+                    d_ocp_qp_set_B(k, B, ins[i]); d_ocp_qp_set_b(k, k == 0 ? b0 : bb, ins[i]);
+                    d_ocp_qp_set_R(k, R, ins[i]); d_ocp_qp_set_r(k, r, ins[i]);
+                }
+                if (k > 0) { d_ocp_qp_set_Q(k, Q, ins[i]); d_ocp_qp_set_q(k, q, ins[i]); }
+                for (int j = 0; j < nu; j++) { idxb[j] = j; lb[j] = -0.5; ub[j] = 0.5; }
+                for (int j = 0; j < nx; j++) { idxb[nu + j] = nu + j; lb[nu + j] = -4.0; ub[nu + j] = 4.0; }
+                d_ocp_qp_set_idxb(k, idxb, ins[i]); d_ocp_qp_set_lb(k, lb, ins[i]); d_ocp_qp_set_ub(k, ub, ins[i]);
+            }
+            outs[i] = ocp_qp_out_create(dims);
+            ref[i] = ocp_qp_out_create(dims);
+            cfg_h.evaluate(&cfg_h, ins[i], ref[i], oh, mh, NULL);
         }
-        int rc = ocp_qp_cuipm_batch_solve(c.config->qp_solver, NB, cin, cout, ((ocp_qp_xcond_solver_opts *) c.opts)->qp_solver_opts, xm->solver_memory, status);
+        int rc = ocp_qp_cuipm_batch_solve(&cfg_g, NB, ins, outs, og, mg, status);
         for (int i = 0; i < NB; i++)
         {
-            /* compare u of the reduced solution with the reference's full solve */
-            for (int k = 0; k < NN; k++)
-                for (int j = 0; j < NU; j++)
-                    worst = fmax(worst, fabs(BLASFEO_DVECEL(cout[i]->ux + k, j) - BLASFEO_DVECEL(ref[i]->ux + k, j)));
-            fails += status[i] != 0;
+            double du, dall = diff_out(dims, ref[i], outs[i], &du);
+            worst = fmax(worst, du);
+            fails += status[i] != 0 || dall > 1e-6;
         }
-        printf("batch entry: %d QPs, rc %d, max |du| vs per-instance HPIPM %.2e %s\n", NB, rc, worst, (rc == 0 && worst <= 1e-10) ? "OK" : "FAIL");
+        printf("batch entry: %d QPs, rc %d, max |du| vs per-instance HPIPM plugin %.2e %s\n", NB, rc, worst, (rc == 0 && worst <= 1e-10) ? "OK" : "FAIL");
         fails += !(rc == 0 && worst <= 1e-10);
-        c.config->terminate(c.config, c.solver->mem, c.solver->work);
+        cfg_g.terminate(&cfg_g, mg, NULL);
     }
     printf(fails ? "PLUGIN TEST FAILED (%d)\n" : "PLUGIN TEST PASSED\n", fails);
     return fails != 0;

@@ -274,10 +274,19 @@ def main():
                     "algorithmic_bytes_per_qp": ab["B_min"], "mean_ipm_iterations": iters_mean,
                     "stream_model": {"bytes_per_qp": ab["B_stream_iter"] * iters_mean, "achieved_gbs": stream_gbs, "frac": stream_gbs / hbm_peak},
                     "fp64": {"achieved_tflops": tflops, "nominal_peak_tflops": 40.0, "frac": tflops / 40.0}}
-        cpu = None
+        cpu, parity = None, None
         if not args.no_cpu:
             try:
-                cpu, _, _ = cpu_reference(b, opts, args.cpu_sample or nb)
+                nsamp = args.cpu_sample or nb
+                cpu, rsol, rinfo = cpu_reference(b, opts, nsamp)
+                # parity of the CUDA solutions of the same instances against the reference (untimed)
+                gsol = h_sol.numpy()[:nsamp]
+                du = np.max(np.abs(b.layout.u_traj(gsol) - b.layout.u_traj(rsol)), axis=1)
+                parity = {"against": cpu["kind"], "instances": int(nsamp), "max_abs_du": float(du.max()),
+                          "frac_du_le_1e-10": float((du <= 1e-10).mean()),
+                          "iter_equal_frac": float((hinfo["iter"][:nsamp] == rinfo["iter"]).mean()),
+                          "status_equal_frac": float((hinfo["status"][:nsamp] == rinfo["status"]).mean()),
+                          "iter_mean_reference": float(rinfo["iter"].mean())}
             except Exception as e:  # noqa: BLE001
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -286,7 +295,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(b.qp.nbytes) * world,
                         "d2h_bytes_per_step": int(h_sol.numel() * 8 + h_info.numel()) * world, "ms_per_step": e2e_ms / steps},
                 "gpu_launches": steps * solver.last_launch_count,
-                "roofline": roofline, "cpu_baseline": cpu,
+                "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
                 "solver": {"status_hist": np.bincount(hinfo["status"], minlength=5).tolist(), "iter_mean": iters_mean,
                            "iter_max": int(info["iter"].max()), "lq_count": int(info["lq_count"].sum())}}
         print(json.dumps(line))
