@@ -6,6 +6,7 @@
 // handed raw host memory, which cannot hold device allocations -- SURVEY.md section 8(b)).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -31,6 +32,9 @@ struct cuipm_solver
     size_t stat_cap = 0;
     cuipm_info *d_info = nullptr;
     cudaStream_t stream = nullptr;
+    static constexpr int kPipe = 4;          // chunks of the host entry: copy of chunk c+1 overlaps the solve of chunk c
+    cudaStream_t pipe[kPipe] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_done[kPipe] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int last_launches = 0;
     float last_ms = 0.f;
@@ -171,6 +175,11 @@ extern "C" cuipm_solver *cuipm_create(const cuipm_shape *shape, int max_batch, i
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(); }
     cudaEventCreate(&s->ev0);
     cudaEventCreate(&s->ev1);
+    for (int i = 0; i < cuipm_solver::kPipe; i++)
+    {
+        cudaStreamCreateWithFlags(&s->pipe[i], cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&s->pipe_done[i], cudaEventDisableTiming);
+    }
     cudaMemsetAsync(s->d_work, 0, sizeof(double) * s->P.work_stride * max_batch, s->stream);
     cudaMemsetAsync(s->d_sol, 0, sizeof(double) * s->P.sol_stride * max_batch, s->stream);
     cudaStreamSynchronize(s->stream);
@@ -188,6 +197,11 @@ extern "C" void cuipm_destroy(cuipm_solver *s)
     cudaFree(s->d_stat); cudaFree(s->d_info);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    for (int i = 0; i < cuipm_solver::kPipe; i++)
+    {
+        if (s->pipe[i]) { cudaStreamSynchronize(s->pipe[i]); cudaStreamDestroy(s->pipe[i]); }
+        if (s->pipe_done[i]) cudaEventDestroy(s->pipe_done[i]);
+    }
     if (s->stream) cudaStreamDestroy(s->stream);
     cuipm_layout_destroy(s->layout);
     delete s;
@@ -263,14 +277,39 @@ extern "C" int cuipm_solve_host(cuipm_solver *s, int nbatch, const double *qp, d
         CK(cudaMalloc(&s->d_stat, sizeof(double) * stat_n));
         s->stat_cap = stat_n;
     }
-    CK(cudaMemcpyAsync(s->d_qp, qp, sizeof(double) * s->P.qp_stride * nbatch, cudaMemcpyHostToDevice, s->stream));
-    if (opts->warm_start >= 1)
-        CK(cudaMemcpyAsync(s->d_sol, sol, sizeof(double) * s->P.sol_stride * nbatch, cudaMemcpyHostToDevice, s->stream));
-    rc = cuipm_solve_device(s, nbatch, s->d_qp, s->d_sol, s->d_info, stat ? s->d_stat : nullptr, opts, 0);
-    if (rc != CUIPM_OK) return rc;
-    CK(cudaMemcpyAsync(sol, s->d_sol, sizeof(double) * s->P.sol_stride * nbatch, cudaMemcpyDeviceToHost, s->stream));
-    CK(cudaMemcpyAsync(info, s->d_info, sizeof(cuipm_info) * nbatch, cudaMemcpyDeviceToHost, s->stream));
-    if (stat) CK(cudaMemcpyAsync(stat, s->d_stat, sizeof(double) * stat_n, cudaMemcpyDeviceToHost, s->stream));
+    // Chunked pipeline: chunk c is copied in, solved and copied out on its own stream, so the H2D copy of the next chunk
+    // (the batch is ~0.4 MB per QP) overlaps the solve of the previous ones; kernels of different chunks share the SMs.
+    const int nchunk = nbatch >= 512 ? cuipm_solver::kPipe : 1;
+    const int per = (nbatch + nchunk - 1) / nchunk;
+    CK(cudaEventRecord(s->ev0, s->stream));
+    for (int c = 0; c < nchunk; c++)
+    {
+        const int lo = c * per, n = std::min(per, nbatch - lo);
+        if (n <= 0) break;
+        cudaStream_t st = s->pipe[c];
+        CK(cudaStreamWaitEvent(st, s->ev0, 0));
+        const size_t qo = s->P.qp_stride * (size_t) lo, so = s->P.sol_stride * (size_t) lo;
+        CK(cudaMemcpyAsync(s->d_qp + qo, qp + qo, sizeof(double) * s->P.qp_stride * n, cudaMemcpyHostToDevice, st));
+        if (opts->warm_start >= 1)
+            CK(cudaMemcpyAsync(s->d_sol + so, sol + so, sizeof(double) * s->P.sol_stride * n, cudaMemcpyHostToDevice, st));
+        LaunchArgs a;
+        a.P = s->P; a.sd = s->d_sd; a.ipool = s->d_ipool; a.qp = s->d_qp + qo; a.sol = s->d_sol + so;
+        a.work = s->d_work + s->P.work_stride * (size_t) lo; a.info = s->d_info + lo;
+        a.stat = stat ? s->d_stat + (size_t) lo * CUIPM_STAT_M * (opts->stat_max + 1) : nullptr;
+        a.o = *opts; a.nbatch = n;
+        int e = launch_solve(a, s->warps, (void *) st);
+        if (e != 0) { set_error(std::string("kernel launch: ") + cudaGetErrorString((cudaError_t) e)); return CUIPM_ERR_CUDA; }
+        CK(cudaMemcpyAsync(sol + so, s->d_sol + so, sizeof(double) * s->P.sol_stride * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(info + lo, s->d_info + lo, sizeof(cuipm_info) * n, cudaMemcpyDeviceToHost, st));
+        if (stat)
+            CK(cudaMemcpyAsync(stat + (size_t) lo * CUIPM_STAT_M * (opts->stat_max + 1), a.stat,
+                               sizeof(double) * (size_t) n * CUIPM_STAT_M * (opts->stat_max + 1), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(s->pipe_done[c], st));
+        CK(cudaStreamWaitEvent(s->stream, s->pipe_done[c], 0));
+    }
+    s->last_launches = nchunk;
+    s->last_opts = *opts;
+    CK(cudaEventRecord(s->ev1, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1);
     return CUIPM_OK;

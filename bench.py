@@ -223,6 +223,7 @@ def main():
     with torch.cuda.stream(stream):
         ev1.record()
     barrier()
+    launches_per_step = solver.last_launch_count
     clocks = sampler.stop()
     dev_ms = ev0.elapsed_time(ev1)
     # per-launch duration of the solve kernel (events recorded around each launch by the solver itself)
@@ -294,7 +295,7 @@ def main():
                 "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(b.qp.nbytes) * world,
                         "d2h_bytes_per_step": int(h_sol.numel() * 8 + h_info.numel()) * world, "ms_per_step": e2e_ms / steps},
-                "gpu_launches": steps * solver.last_launch_count,
+                "gpu_launches": steps * launches_per_step,
                 "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
                 "solver": {"status_hist": np.bincount(hinfo["status"], minlength=5).tolist(), "iter_mean": iters_mean,
                            "iter_max": int(info["iter"].max()), "lq_count": int(info["lq_count"].sum())}}
