@@ -107,17 +107,23 @@ def cpu_reference(batch_obj, opts, nqp: int, threads: int = 0):
     from acados_b200.problems import Batch
     from oracle import oracle_binding as ob
     sub = Batch(batch_obj.shape, batch_obj.layout, np.ascontiguousarray(batch_obj.qp[:nqp]), batch_obj.name)
+    if threads <= 0:   # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1: do not rely on the OpenMP default)
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     if ob.have_ref():
         ob.ref_solve(Batch(sub.shape, sub.layout, sub.qp[:min(nqp, 64)].copy()), opts, nthreads=threads)  # warm-up
         sol, info, tm = ob.ref_solve(sub, opts, nthreads=threads)
-        kind, secs, cores = "reference", tm["wall_s"], tm["threads"]
+        # time inside the reference's own evaluate() only (max over threads): its inputs are already in its own
+        # panel-major structs, the conversion from cuipm records done by the harness is not charged to the reference
+        kind, secs, cores, wall = "reference", tm["solve_s"], tm["threads"], tm["wall_s"]
     else:   # oracle port (only when oracle/_ref could not be built)
         t0 = time.perf_counter()
         sol, info = ob.oracle_solve(sub, opts, nthreads=threads)
         secs, kind, cores = time.perf_counter() - t0, "port", threads or os.cpu_count()
+        wall = secs
     return {"value": nqp / secs, "unit": UNIT, "cores": int(cores), "kind": kind,
-            "sample": f"{nqp} QPs of the workload, one solver object per OpenMP thread, wall clock incl. packing into the "
-                      f"reference's panel-major structs; mean IPM iterations {float(info['iter'].mean()):.2f}"}, sol, info
+            "sample": f"{nqp} QPs of the workload, one solver object per OpenMP thread (the structure of the reference's batch "
+                      f"solver), time inside ocp_qp_hpipm() only, max over threads; mean IPM iterations {float(info['iter'].mean()):.2f}",
+            "value_incl_struct_packing": nqp / wall}, sol, info
 
 
 def main():
@@ -149,7 +155,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        sample = args.cpu_sample or min(args.batch, 1024)
+        sample = args.cpu_sample or args.batch
         b = workload(sample, seed=1234)
         times = []
         base = None
