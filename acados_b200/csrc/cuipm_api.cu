@@ -126,7 +126,7 @@ static int build_desc(cuipm_solver *s, const cuipm_shape *sh)
     // rows incl. the gradient row, 16-byte aligned column starts); both <= nmax+2
     P.sm_M = e((P.nmax + 2) * P.nmax + 8);                       // factor of the stage being eliminated (rows incl. gradient row)
     P.sm_A = 0;                                                  // (matrices of the substitution / residual sweeps are streamed from global memory)
-    P.sm_AL = e((P.nmax + 2) * (P.nxmax + P.ngmax) + 8);         // [A; b'] -> A L_xx in place (+ general-constraint columns)
+    P.sm_AL = e(std::max((P.nmax + 2) * (P.nxmax + P.ngmax), e(P.nmax) + e(P.nxmax) + 4 * e(P.ncmax)) + 8);   // [A; b'] -> A L_xx in place (+ general-constraint columns); staging area of the substitution sweeps
     P.sm_C = P.ngmax > 0 ? 2 * e((P.nmax + 2) * P.ngmax) + 8 : 0;
     {
         const int nvs = e(P.nvsmax), nx = e(P.nxmax), nc = e(P.ncmax), nbg = e(P.nbgmax), n = e(P.nmax + 1), ns2 = e(2 * P.nsmax);

@@ -887,6 +887,7 @@ struct Ker
         double *v = SV_, *gam = v + ev(CX.P.nvsmax), *Gam = gam + ev(CX.P.ncmax), *tmp0 = Gam + ev(CX.P.ncmax);
         double *tmp1 = tmp0 + ev(CX.P.nbgmax), *Zi = tmp1 + ev(CX.P.nbgmax), *ds = Zi + ev(2 * CX.P.nsmax);
         double *xprev = ds + ev(2 * CX.P.nsmax), *tmpx = xprev + ev(CX.P.nxmax), *tmpl = tmpx + ev(CX.P.nxmax);
+        double *Ls = SM_, *Lis = SAL_, *pbs = Lis + ev(CX.P.nmax);   // staged from global memory at the top of each stage
         for (int k = N; k >= 0; k--)
         {
             const StageDesc &s = CX.SD[k];
@@ -930,6 +931,13 @@ struct Ker
                     const double *z_ = CX.wk + s.w_Zsi;
                     for (int j = tid; j < 2 * ns; j += NT) Zi[j] = z_[j];
                 }
+                for (int e = tid; e < n * nsolve; e += NT) Ls[e] = Lg[e];
+                for (int j = tid; j < nsolve; j += NT) Lis[j] = Li[j];
+                if (k < N && use_Pb)
+                {
+                    const double *pb = CX.wk + s.w_Pb;
+                    for (int j = tid; j < nx1; j += NT) pbs[j] = pb[j];
+                }
             }
             sync();
             if (ns > 0)
@@ -952,8 +960,7 @@ struct Ker
             {
                 if (use_Pb)
                 {
-                    const double *pb = CX.wk + s.w_Pb;
-                    for (int j = tid; j < nx1; j += NT) tmpx[j] = xprev[j] + pb[j];
+                    for (int j = tid; j < nx1; j += NT) tmpx[j] = xprev[j] + pbs[j];
                 }
                 else
                 {   // P b = Lxx (Lxx' b) from the factor of stage k+1 in global memory
@@ -982,14 +989,14 @@ struct Ker
                 for (int j = 0; j < nsolve; j++)
                 {
                     double part = 0.0;
-                    for (int c = tid; c < j; c += 32) part += Lg[j + n * c] * v[c];
+                    for (int c = tid; c < j; c += 32) part += Ls[j + n * c] * v[c];
                     part = wsum(part);
-                    if (tid == 0) v[j] = (v[j] - part) * Li[j];
+                    if (tid == 0) v[j] = (v[j] - part) * Lis[j];
                     __syncwarp();
                 }
             }
             sync();
-            for (int i = nsolve + tid; i < n; i += NT) v[i] -= gdot<false>(Lg + i, n, v, nsolve);
+            for (int i = nsolve + tid; i < n; i += NT) v[i] -= dot(Ls + i, n, v, 1, nsolve);
             sync();
             {
                 double *o_ = vux(dst, s);
@@ -1020,6 +1027,11 @@ struct Ker
         double *pim = pik + ev(CX.P.nxmax), *Gam = pim + ev(CX.P.nxmax), *dt = Gam + ev(CX.P.ncmax), *lam = dt + ev(CX.P.ncmax);
         double *dlm = lam + ev(CX.P.ncmax), *Zi = dlm + ev(CX.P.ncmax), *ds = Zi + ev(2 * CX.P.nsmax), *g_ = ds + ev(2 * CX.P.nsmax);
         double *tmp0 = g_ + ev(CX.P.nvsmax);
+        // staging areas borrowed from the factorisation buffers (idle during this sweep): the first nsolve columns of L_k
+        // and the per-stage vectors, all fetched in ONE burst at the top of the stage instead of one exposed global
+        // round trip per dependent phase
+        double *Ls = SM_, *Lis = SAL_, *bs = Lis + ev(CX.P.nmax), *ts = bs + ev(CX.P.nxmax), *rds = ts + ev(CX.P.ncmax);
+        double *rms = rds + ev(CX.P.ncmax), *mks = rms + ev(CX.P.ncmax);
         double alpha = 1.0;
         double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
         int f0 = 0, f1 = 0, f2 = 0, f3 = 0;
@@ -1058,6 +1070,21 @@ struct Ker
                 const double *z_ = CX.wk + s.w_Zsi, *d_ = vux(dst, s) + n;
                 for (int j = tid; j < 2 * ns; j += NT) { Zi[j] = z_[j]; ds[j] = d_[j]; }
             }
+            {
+                for (int e = tid; e < n * nsolve; e += NT) Ls[e] = Lg[e];
+                for (int j = tid; j < nsolve; j += NT) Lis[j] = Li[j];
+                const double *b_ = rb(rhs, s);
+                for (int j = tid; j < nx1; j += NT) bs[j] = b_[j];
+                const double *gl = CX.sol + s.sol.lam, *gt = CX.sol + s.sol.t, *grd = rd(rhs, s), *grm = rm(rhs, s), *gm = CX.qp + s.q_dmask;
+                for (int i = tid; i < nc; i += NT)
+                {
+                    lam[i] = gl[i];
+                    ts[i] = gt[i];
+                    rds[i] = grd[i];
+                    rms[i] = grm[i];
+                    mks[i] = CX.mask_constr ? __ldg(gm + i) : 1.0;
+                }
+            }
             sync();
             // TRSV_LTN(_MN): back substitution with the transposed factor on the first nsolve unknowns
             if (tid < 32)
@@ -1065,9 +1092,9 @@ struct Ker
                 for (int j = nsolve - 1; j >= 0; j--)
                 {
                     double part = 0.0;
-                    for (int i = j + 1 + tid; i < n; i += 32) part += Lg[i + n * j] * v[i];
+                    for (int i = j + 1 + tid; i < n; i += 32) part += Ls[i + n * j] * v[i];
                     part = wsum(part);
-                    if (tid == 0) v[j] = (v[j] - part) * Li[j];
+                    if (tid == 0) v[j] = (v[j] - part) * Lis[j];
                     __syncwarp();
                 }
             }
@@ -1079,11 +1106,10 @@ struct Ker
             if (k < N)
             {
                 const double *L1 = CX.wk + CX.SD[k + 1].w_L + nu1 + n1 * nu1;      // Lxx of stage k+1: L1[i + n1*j]
-                const double *b_ = rb(rhs, s);
                 double *ob = rb(1, s);
                 for (int j = tid; j < nx1; j += NT)
                 {
-                    const double acc = gdot<true>(Ag + n * j, 1, v, n), bv = b_[j];
+                    const double acc = gdot<true>(Ag + n * j, 1, v, n), bv = bs[j];
                     const double xj = bv + acc;
                     x1[j] = xj;
                     if (do_lin)
@@ -1113,12 +1139,10 @@ struct Ker
             }
             // ---- constraint part of the step at this stage
             {
-                const double *gl = CX.sol + s.sol.lam, *gt = CX.sol + s.sol.t;
                 const double t_min_inv = CX.o.t_min > 0 ? 1.0 / CX.o.t_min : 1e30;
                 for (int i = tid; i < nc; i += NT)
                 {
-                    const double l = gl[i], tt = gt[i];
-                    lam[i] = l;
+                    const double l = lam[i], tt = ts[i];
                     Gam[i] = (ns > 0 && CX.o.t_lam_min == 1) ? (tt < CX.o.t_min ? t_min_inv : 1.0 / tt) * (l < CX.o.lam_min ? CX.o.lam_min : l)
                                                           : (1.0 / tt) * l;
                 }
@@ -1151,15 +1175,14 @@ struct Ker
                     for (int j = tid; j < 2 * ns; j += NT) o_[j] = ds[j];
                 }
                 sync();
-                const double *grd = rd(rhs, s), *grm = rm(rhs, s), *gm = CX.qp + s.q_dmask;
                 double *odl = vlam(dst, s), *odt = vt(dst, s), *ld_ = rd(1, s), *lm_ = rm(1, s);
                 for (int i = tid; i < nc; i += NT)
                 {
-                    const double l = lam[i], tt = gt[i], ti = 1.0 / tt, rdi = grd[i], rmi = grm[i];
+                    const double l = lam[i], tt = ts[i], ti = 1.0 / tt, rdi = rds[i], rmi = rms[i];
                     const double dtr = dt[i];
                     double dl = -ti * (rmi + (l * dtr) - (l * rdi));
                     double dti = dtr - rdi;
-                    const double mk = CX.mask_constr ? __ldg(gm + i) : 1.0;
+                    const double mk = mks[i];
                     if (CX.mask_constr && mask_out)
                     {
                         dl *= mk;
