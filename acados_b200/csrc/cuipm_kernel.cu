@@ -243,6 +243,12 @@ struct Ker
         for (; j < n; j++) s0 += __ldg(H + (j <= i ? i + n * j : j + n * i)) * x[j];
         return (s0 + s1) + (s2 + s3);
     }
+    // 8-byte asynchronous global -> shared copy (LDGSTS): no register staging, completion via cp.async.wait_group
+    __device__ __forceinline__ void cpa8(double *sdst, const double *gsrc) const
+    {
+        const unsigned sa = (unsigned) __cvta_generic_to_shared(sdst);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc));
+    }
     // L2 prefetch of a 16-byte-multiple chunk (TMA bulk prefetch), issued by one thread
     __device__ __forceinline__ void prefetch_l2(const double *p, unsigned bytes)
     {
@@ -597,25 +603,15 @@ struct Ker
             // ---- stage inputs: [A; b'] into SAL_ (asynchronous), constraint quantities
             if (k < N)
             {
-                // [A; b'] into SAL_: thread r copies row r (coalesced across threads, 8 loads in flight)
+                // [A; b'] into SAL_ with cp.async (LDGSTS): thread r copies row r (coalesced across threads); the copies are
+                // all in flight while the constraint quantities below are computed and are waited for just before the TRMM
                 const double *Ag = CX.qp + s.q_BAt, *b_ = rb(0, s);
                 for (int r = tid; r <= n; r += NT)
                 {
                     if (r < n)
-                    {
-                        int c = 0;
-#pragma unroll 2
-                        for (; c + 3 < nx1; c += 4)
-                        {
-                            const double a0 = __ldg(Ag + r + n * c), a1 = __ldg(Ag + r + n * (c + 1));
-                            const double a2 = __ldg(Ag + r + n * (c + 2)), a3 = __ldg(Ag + r + n * (c + 3));
-                            SAL_[r + ldal * c] = a0; SAL_[r + ldal * (c + 1)] = a1;
-                            SAL_[r + ldal * (c + 2)] = a2; SAL_[r + ldal * (c + 3)] = a3;
-                        }
-                        for (; c < nx1; c++) SAL_[r + ldal * c] = __ldg(Ag + r + n * c);
-                    }
+                        for (int c = 0; c < nx1; c++) cpa8(SAL_ + r + ldal * c, Ag + r + n * c);
                     else
-                        for (int c = 0; c < nx1; c++) SAL_[n + ldal * c] = b_[c];
+                        for (int c = 0; c < nx1; c++) cpa8(SAL_ + n + ldal * c, b_ + c);
                 }
             }
             if (k > 0)
@@ -678,6 +674,7 @@ struct Ker
                     dadd[ix] += tmp0[i];
                     rowv[ix] += tmp1[i];
                 }
+            asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
             sync();
             if (k < N)
             {
