@@ -153,11 +153,6 @@ struct Ker
         }
         return isnan_ ? NAN : v;
     }
-    __device__ __forceinline__ void cp(double *dst, const double *src, int n)
-    {
-        for (int i = tid; i < n; i += NT) dst[i] = src[i];
-    }
-
     // ---- addressing -------------------------------------------------------------------------------
     // vector sets: 0 = current iterate (solution record), 1 = step, 2 = iterative-refinement step
     __device__ __forceinline__ double *vux(int set, const StageDesc &s) const
@@ -181,25 +176,6 @@ struct Ker
     __device__ __forceinline__ double *rb(int set, const StageDesc &s) const { return CX.wk + (set == 0 ? s.res.b : s.ires.b); }
     __device__ __forceinline__ double *rd(int set, const StageDesc &s) const { return CX.wk + (set == 0 ? s.res.d : s.ires.d); }
     __device__ __forceinline__ double *rm(int set, const StageDesc &s) const { return CX.wk + (set == 0 ? s.res.m : s.ires.m); }
-
-    // iterate over the lower triangle (i >= j, i < n) plus the extra row i == n of an (n+1) x n array,
-    // perfectly balanced: column p is paired with column n-1-p (n+3 entries per pair).
-    template <class F>
-    __device__ __forceinline__ void for_lower_plus_row(int n, F f)
-    {
-        const int np = (n + 1) >> 1, rows = n + 3, tot = np * rows;
-        for (int e = tid; e < tot; e += NT)
-        {
-            int p = e / rows, r = e - p * rows;
-            int len0 = n - p + 1;
-            if (r < len0) f(p + r, p);
-            else
-            {
-                int q = n - 1 - p;
-                if (q != p) f(q + (r - len0), q);
-            }
-        }
-    }
 
     // ---- global-memory access ---------------------------------------------------------------------
     // QP records are read-only for the whole launch (ld.global.nc); work / solution records are written by this
@@ -1307,37 +1283,6 @@ struct Ker
         return rsum(acc) * CX.nc_mask_inv;
     }
 
-    // res_m updates of one IPM iteration (x_core_qp_ipm_aux.c:672-781):
-    // mode 0: bkp <- res_m; res_m <- bkp - tau_min      (affine direction)
-    // mode 1: res_m <- bkp + dt*dlam - sigma_mu         (centring + second-order correction)
-    // mode 2: res_m <- bkp - sigma_mu                   (pure centring)
-    __device__ __noinline__ void res_m_pass(int mode, double sigma_mu)
-    {
-        for (int k = 0; k <= CX.P.N; k++)
-        {
-            const StageDesc s = CX.SD[k];
-            double *m = rm(0, s), *bk = CX.wk + s.w_rmb;
-            const double *dl = CX.wk + s.step.lam, *dt = CX.wk + s.step.t, *gm = CX.qp + s.q_dmask;
-            for (int i = tid; i < s.nc; i += NT)
-            {
-                double r;
-                if (mode == 0)
-                {
-                    const double b = m[i];
-                    bk[i] = b;
-                    r = b - CX.o.tau_min;
-                }
-                else if (mode == 1)
-                    r = bk[i] + dt[i] * dl[i] - sigma_mu;
-                else
-                    r = bk[i] - sigma_mu;
-                if (CX.mask_constr) r *= gm[i];
-                m[i] = r;
-            }
-        }
-        sync();
-    }
-
     // step <- step + itref
     __device__ __noinline__ void add_itref()
     {
@@ -1353,36 +1298,6 @@ struct Ker
             for (int i = tid; i < s.nc; i += NT) a[i] += b[i];
             a = CX.wk + s.step.t; b = CX.wk + s.itref.t;
             for (int i = tid; i < s.nc; i += NT) a[i] += b[i];
-        }
-        sync();
-    }
-
-    // UPDATE_VAR_QP (x_core_qp_ipm_aux.c:472-582) + lam masking (x_ocp_qp_ipm.c:2672-2676)
-    __device__ __noinline__ void update_var(double alpha)
-    {
-        if (alpha < 1.0) alpha = alpha * ((1.0 - alpha) * 0.99 + alpha * 0.9999999);
-        for (int k = 0; k <= CX.P.N; k++)
-        {
-            const StageDesc s = CX.SD[k];
-            double *a = CX.sol + s.sol.ux;
-            const double *b = CX.wk + s.step.ux;
-            for (int i = tid; i < s.n + 2 * s.ns; i += NT) a[i] += alpha * b[i];
-            a = CX.sol + s.sol.pi; b = CX.wk + s.step.pi;
-            for (int i = tid; i < s.nx1; i += NT) a[i] += alpha * b[i];
-            double *l = CX.sol + s.sol.lam, *t = CX.sol + s.sol.t;
-            const double *dl = CX.wk + s.step.lam, *dt = CX.wk + s.step.t, *gm = CX.qp + s.q_dmask;
-            for (int i = tid; i < s.nc; i += NT)
-            {
-                double ln = l[i] + alpha * dl[i], tn = t[i] + alpha * dt[i];
-                if (CX.o.t_lam_min == 2)
-                {
-                    ln = ln <= CX.o.lam_min ? CX.o.lam_min : ln;
-                    tn = tn <= CX.o.t_min ? CX.o.t_min : tn;
-                }
-                if (CX.mask_constr) ln *= gm[i];
-                l[i] = ln;
-                t[i] = tn;
-            }
         }
         sync();
     }
@@ -1549,8 +1464,8 @@ struct Ker
             for (int k = 0; k <= N; k++)
             {
                 const StageDesc s = CX.SD[k];
-                cp(CX.sol + s.sol.ux, CX.wk + s.step.ux, s.n + 2 * s.ns);
-                cp(CX.sol + s.sol.pi, CX.wk + s.step.pi, s.nx1);
+                for (int i = tid; i < s.n + 2 * s.ns; i += NT) (CX.sol + s.sol.ux)[i] = (CX.wk + s.step.ux)[i];
+                for (int i = tid; i < s.nx1; i += NT) (CX.sol + s.sol.pi)[i] = (CX.wk + s.step.pi)[i];
             }
             sync();
             res_pass(0, 0, -1, 0, 0, 0.0, mu, obj, gap, res_max, dmy);
@@ -1685,24 +1600,6 @@ struct Ker
         }
     }
 
-    // || res_m - tau_min * d_mask ||_inf  (x_ocp_qp_ipm.c:3012-3014)
-    __device__ __noinline__ double res_m_tau_norm()
-    {
-        double m = 0.0;
-        int f = 0;
-        for (int k = 0; k <= CX.P.N; k++)
-        {
-            const StageDesc s = CX.SD[k];
-            const double *r = rm(0, s), *gm = CX.qp + s.q_dmask;
-            for (int i = tid; i < s.nc; i += NT)
-            {
-                const double a = fabs(r[i] - CX.o.tau_min * gm[i]);
-                m = fmax(m, a);
-                f |= (a != a);
-            }
-        }
-        return rmax_nan(m, f);
-    }
 };
 
 #ifndef CUIPM_MINB
