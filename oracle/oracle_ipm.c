@@ -18,8 +18,9 @@
  * golden fixtures in tests/golden/.
  *
  * Not restated (the product rejects these option values as well): abs_form=1, split_step=1,
- * var_init_scheme=0, non-zero m (acados "tau_min" relaxation), LQ refactorisation (lq_fact: the accuracy
- * test is evaluated and counted in info.lq_count, the Cholesky result is kept).
+ * var_init_scheme=0, non-zero m (acados "tau_min" relaxation).  info.lq_count counts the LQ refactorisations
+ * (OCP_QP_FACT_LQ_SOLVE_KKT_STEP) of a solve; the Hessian factor the reference caches per solve (use_hess_fact) is
+ * recomputed at each of them.
  */
 #include "oracle_ipm.h"
 
@@ -107,6 +108,7 @@ typedef struct
     double **res_m_bkp;
     double **L, **Linv, **lrow, **Pb, **Gamma, **gamma, **t_inv, **Zs_inv;
     double *AL;                   /* (nvmax+1) x (nxmax + ngmax) scratch */
+    double *lq;                   /* nvmax x (2 nvmax + ngmax + nxmax) scratch of the LQ refactorisation */
     double *tmp0, *tmp1, *tmp2, *tmp3, *tmpx, *tmpl; /* nb+ng / nx scratch */
     int mask_constr;
     double nc_mask_inv;
@@ -189,11 +191,13 @@ static work *work_create(const cuipm_shape *sh)
     w->AL = bump(&p, (size_t) (nvmax + 1) * (nxmax + ngmax + 1));
     w->tmp0 = bump(&p, nbgmax); w->tmp1 = bump(&p, nbgmax); w->tmp2 = bump(&p, nbgmax); w->tmp3 = bump(&p, nbgmax);
     w->tmpx = bump(&p, nvmax + 1); w->tmpl = bump(&p, nvmax + 1);
+    w->lq = (double *) calloc((size_t) nvmax * (2 * nvmax + ngmax + nxmax) + 2, sizeof(double));
     return w;
 }
 
 static void work_destroy(work *w)
 {
+    free(w->lq);
     free(w->arena);
     free(w);
 }
@@ -708,6 +712,149 @@ static void fact_solve_kkt_step(work *w, const rset *rhs, vset *step, const cuip
     finish_step(w, rhs, step, 1);
 }
 
+/* Householder LQ with non-negative diagonal of the n x m column-major matrix X (ld n), in place: on exit the lower
+ * triangle of the first n columns holds L with X X' = L L'.  Reflector formulas of BLASFEO's positive-diagonal
+ * kernels (kernel/generic/kernel_dgeqrf_4_lib4.c:4743-4771: beta = +sqrt(sigma + alpha^2), the pivot is left alone
+ * when the rest of the row is zero), unblocked. */
+static void gelqf_pd(int n, int m, double *X)
+{
+    for (int i = 0; i < n; i++)
+    {
+        double sigma = 0.0;
+        for (int j = i + 1; j < m; j++) sigma += X[i + n * j] * X[i + n * j];
+        if (sigma == 0.0) continue;
+        double alpha = X[i + n * i];
+        double beta = sqrt(sigma + alpha * alpha);
+        double tmp = alpha <= 0 ? alpha - beta : -sigma / (alpha + beta);
+        double tau = 2 * tmp * tmp / (sigma + tmp * tmp);
+        tmp = 1.0 / tmp;
+        X[i + n * i] = beta;
+        for (int j = i + 1; j < m; j++) X[i + n * j] *= tmp;
+        for (int r = i + 1; r < n; r++)
+        {
+            double ww = X[r + n * i];
+            for (int j = i + 1; j < m; j++) ww += X[r + n * j] * X[i + n * j];
+            ww = -ww * tau;
+            X[r + n * i] += ww;
+            for (int j = i + 1; j < m; j++) X[r + n * j] += ww * X[i + n * j];
+        }
+    }
+}
+
+/* OCP_QP_FACT_LQ_SOLVE_KKT_STEP (x_ocp_qp_kkt.c:1201-1541): L_k from an LQ factorisation of
+ * [chol(RSQ_k + reg I) | sqrt(Gamma_b) on idxb | DCt sqrt(Gamma_g) | BAt L_{k+1,xx}] instead of the Cholesky
+ * factorisation of the accumulated Gram matrix; the gradient goes through plain substitutions. */
+static void fact_lq_solve_kkt_step(work *w, const rset *rhs, vset *step, const cuipm_opts *o)
+{
+    int N = w->N;
+    compute_Gamma_gamma(w, rhs, 1, o->t_lam_min, o->lam_min, o->t_min);
+    for (int k = N; k >= 0; k--)
+    {
+        int nu0 = w->nu[k], n = w->nv[k], nb0 = w->nb[k], ng0 = w->ng[k], nbg = nb0 + ng0;
+        int nx1 = k < N ? w->nx[k + 1] : 0;
+        int m = 2 * n + ng0 + nx1;
+        double *X = w->lq, *v = step->ux[k];
+        memset(X, 0, sizeof(double) * (size_t) n * m);
+        for (int i = 0; i < n; i++) v[i] = rhs->g[k][i];
+        if (k < N)
+        {
+            int nu1 = w->nu[k + 1], n1 = w->nv[k + 1];
+            const double *A = w->BAt[k], *L1 = w->L[k + 1];
+            double *AL = X + (size_t) n * (2 * n + ng0);
+            for (int j = 0; j < nx1; j++)
+                for (int i = 0; i < n; i++)
+                {
+                    double acc = 0.0;
+                    for (int c = j; c < nx1; c++) acc += A[i + n * c] * L1[(nu1 + c) + n1 * (nu1 + j)];
+                    AL[i + n * j] = acc;
+                }
+            for (int j = 0; j < nx1; j++)
+            {
+                double acc = 0.0;
+                for (int i = j; i < nx1; i++) acc += L1[(nu1 + i) + n1 * (nu1 + j)] * rhs->b[k][i];
+                w->tmpl[j] = acc;
+            }
+            for (int i = nx1 - 1; i >= 0; i--)
+            {
+                double acc = 0.0;
+                for (int j = 0; j <= i; j++) acc += L1[(nu1 + i) + n1 * (nu1 + j)] * w->tmpl[j];
+                w->Pb[k][i] = acc;
+            }
+            for (int j = 0; j < nx1; j++) w->tmpx[j] = step->ux[k + 1][nu1 + j] + w->Pb[k][j];
+            for (int j = 0; j < nx1; j++)
+                for (int i = 0; i < n; i++) v[i] += A[i + n * j] * w->tmpx[j];
+        }
+        if (w->ns[k] > 0)
+            cond_slacks(w, k, 1, rhs, step, o->reg_prim);
+        else
+            for (int i = 0; i < nbg; i++)
+            {
+                w->tmp0[i] = w->Gamma[k][i] + w->Gamma[k][nbg + i];
+                w->tmp1[i] = w->gamma[k][i] - w->gamma[k][nbg + i];
+            }
+        for (int i = 0; i < nb0; i++)
+        {
+            int ix = w->idxb[k][i];
+            double t = w->tmp0[i] >= 0.0 ? w->tmp0[i] : 0.0;
+            t = sqrt(t);
+            X[ix + n * (n + ix)] = t > 0.0 ? t : 0.0;
+            v[ix] += w->tmp1[i];
+        }
+        for (int g = 0; g < ng0; g++)
+        {
+            const double *C = w->DCt[k] + (size_t) n * g;
+            double t = w->tmp0[nb0 + g] >= 0.0 ? w->tmp0[nb0 + g] : 0.0;
+            t = sqrt(t);
+            for (int i = 0; i < n; i++)
+            {
+                X[i + n * (2 * n + g)] = C[i] * t;
+                v[i] += C[i] * w->tmp1[nb0 + g];
+            }
+        }
+        /* Lh = chol(tril(RSQ) + reg I) (the reference caches it per solve: use_hess_fact) */
+        {
+            const double *H = w->RSQ[k];
+            for (int j = 0; j < n; j++)
+            {
+                for (int i = j; i < n; i++) X[i + n * j] = H[i + n * j];
+                X[j + n * j] += o->reg_prim;
+            }
+            for (int j = 0; j < n; j++) w->tmpl[j] = 0.0;
+            potrf_row(n, X, w->Linv[k], w->tmpl);
+        }
+        gelqf_pd(n, m, X);
+        double *L = w->L[k], *Li = w->Linv[k];
+        for (int j = 0; j < n; j++)
+        {
+            for (int i = 0; i < j; i++) L[i + n * j] = 0.0;
+            for (int i = j; i < n; i++) L[i + n * j] = X[i + n * j];
+            Li[j] = 1.0 / L[j + n * j];
+        }
+        int nsolve = k == 0 ? n : nu0;
+        for (int j = 0; j < nsolve; j++)
+        {
+            double a = v[j];
+            for (int c = 0; c < j; c++) a -= L[j + n * c] * v[c];
+            v[j] = a * Li[j];
+        }
+        for (int i = nsolve; i < n; i++)
+        {
+            double a = v[i];
+            for (int c = 0; c < nsolve; c++) a -= L[i + n * c] * v[c];
+            v[i] = a;
+        }
+    }
+    for (int k = 0; k <= N; k++)
+    {
+        if (k < N)
+            for (int j = 0; j < w->nx[k + 1]; j++) step->pi[k][j] = step->ux[k + 1][w->nu[k + 1] + j];
+        int nneg = k == 0 ? w->nv[k] : w->nu[k];
+        for (int i = 0; i < nneg; i++) step->ux[k][i] = -step->ux[k][i];
+    }
+    forward_sweep(w, rhs, step, 1);
+    finish_step(w, rhs, step, 1);
+}
+
 /* OCP_QP_SOLVE_KKT_STEP, square-root algorithm (x_ocp_qp_kkt.c:1582-1727) */
 static void solve_kkt_step(work *w, const rset *rhs, vset *step, int use_Pb, int mask_out)
 {
@@ -950,7 +1097,7 @@ static void solve_one(work *w, const cuipm_opts *o, cuipm_info *info, double *st
     int N = w->N;
     const int SM = CUIPM_STAT_M;
     double res_max[4] = {0, 0, 0, 0}, mu = 0, obj = 0, gap = 0;
-    int lq_count = 0;
+    int lq_count = 0, force_lq = 0;
     if (stat) memset(stat, 0, sizeof(double) * SM * (size_t) (o->stat_max + 1));
 
     /* constraint masks (x_ocp_qp_ipm.c:2774-2806) */
@@ -1036,14 +1183,31 @@ static void solve_one(work *w, const cuipm_opts *o, cuipm_info *info, double *st
                 w->res.m[k][i] = w->res_m_bkp[k][i] - o->tau_min;
             }
         mask_res_m(w);
-        fact_solve_kkt_step(w, &w->res, &w->step, o);
-        if (o->lq_fact == 1)
+        /* factorisation: Cholesky, with a switch to LQ for the rest of the solve once the linear-system residual of
+         * a Cholesky step is too large (x_ocp_qp_ipm.c:2246-2346) */
+        if (o->lq_fact == 0 || (o->lq_fact == 1 && !force_lq))
         {
-            res_body(w, 1, &w->step, &w->res, &w->sol, &w->res_itref, 0, 0, 0);
-            res_inf_norm(w, &w->res_itref, nrm);
-            if ((nrm[0] == 0.0 && isnan(w->res_itref.g[0][0])) || nrm[0] > 1e-5 || nrm[1] > 1e-5 || nrm[2] > 1e-5
-                || nrm[3] > 1e-5)
-                lq_count++;   /* the reference would refactorise with LQ here (x_ocp_qp_ipm.c:2299-2330) */
+            fact_solve_kkt_step(w, &w->res, &w->step, o);
+            if (st) st[13] = 0;
+            if (o->lq_fact == 1)
+            {
+                res_body(w, 1, &w->step, &w->res, &w->sol, &w->res_itref, 0, 0, 0);
+                res_inf_norm(w, &w->res_itref, nrm);
+                if ((nrm[0] == 0.0 && isnan(w->res_itref.g[0][0])) || nrm[0] > 1e-5 || nrm[1] > 1e-5 || nrm[2] > 1e-5
+                    || nrm[3] > 1e-5)
+                {
+                    fact_lq_solve_kkt_step(w, &w->res, &w->step, o);
+                    force_lq = 1;
+                    lq_count++;
+                    if (st) st[13] = 1;
+                }
+            }
+        }
+        else
+        {
+            fact_lq_solve_kkt_step(w, &w->res, &w->step, o);
+            lq_count++;
+            if (st) st[13] = 1;
         }
         alpha = compute_alpha(w, &w->step);
         if (st) { st[0] = alpha; st[1] = alpha; }
@@ -1123,7 +1287,7 @@ fill:
 static int opts_supported(const cuipm_opts *o)
 {
     return o->abs_form == 0 && o->split_step == 0 && o->comp_dual_sol_eq == 1 && o->comp_res_exit == 1
-           && o->var_init_scheme == 1 && o->m_relax == 0.0 && o->itref_pred_max == 0 && o->lq_fact != 2;
+           && o->var_init_scheme == 1 && o->m_relax == 0.0 && o->itref_pred_max == 0;
 }
 
 int oracle_solve(const cuipm_shape *shape, int nbatch, const double *qp, double *sol, cuipm_info *info, double *stat,
