@@ -119,6 +119,8 @@ static int build_desc(cuipm_solver *s, const cuipm_shape *sh)
         uni = uni && sh->nx[N] == sh->nx[1];
         if (uni) { P.mid_nx = sh->nx[1]; P.mid_nu = sh->nu[1]; }
     }
+    P.w_lq = (unsigned) w;
+    w += ev2u((size_t) P.nmax * (P.nbgmax + P.nxmax));
     if (w >= (size_t) 1 << 32 || l->qp_stride >= (size_t) 1 << 32) { set_error("QP record too large for 32-bit offsets"); return CUIPM_ERR_TOO_LARGE; }
     P.qp_stride = l->qp_stride; P.sol_stride = l->sol_stride; P.work_stride = w;
     auto e = [](int n) { return (n + 1) & ~1; };

@@ -35,7 +35,7 @@ struct ProbDesc
     int nmax, nxmax, ngmax, nsmax, nbgmax, ncmax, nvsmax;  // maxima over stages (nvs = n + 2 ns)
     int nct;                                               // total constraint count
     int mid_nx, mid_nu;                                    // (nx, nu) shared by stages 1..N-1 and nx of stage N, or 0,0 if not uniform
-    int pad_;
+    unsigned w_lq;                                         // work record: nmax x (nbgmax + nxmax) scratch of the LQ refactorisation
     size_t qp_stride, sol_stride, work_stride;
     // shared-memory carve (doubles)
     int sm_M, sm_A, sm_AL, sm_C, sm_V;

@@ -848,6 +848,234 @@ struct Ker
     }
 
     // ---------------------------------------------------------------------------------------------
+    // backward sweep of the LQ refactorisation (OCP_QP_FACT_LQ_SOLVE_KKT_STEP, x_ocp_qp_kkt.c:1201-1475), the
+    // fallback of lq_fact = 1 when a Cholesky step leaves a large linear-system residual, and the only
+    // factorisation of lq_fact = 2:   L_k L_k' = Lh Lh' + W W',   Lh = chol(RSQ_k + reg I),
+    //   W = [ sqrt(Gamma_b) on the idxb rows | DCt sqrt(Gamma_g) | BAt L_{k+1,xx} ]
+    // computed with Householder reflectors from the right on [Lh | W] (non-negative diagonal, the formulas of BLASFEO's
+    // GELQF_PD kernels) instead of a Cholesky factorisation of the accumulated sum.  The gradient is not carried as an
+    // extra row: it goes through the substitutions of the solve-only sweep, whose results (backward quantities in step
+    // set 1, Pb, Zs_inv) this sweep leaves behind, so that forward_pass(after_fact = 0) completes the step.
+    // Cold path: generic dimensions only, Lh / L in SM_ (ld even(n+1)), W in a per-QP scratch of the work record
+    // (column-major, ld n; thread r owns row r), reflector in SAL_.
+    // ---------------------------------------------------------------------------------------------
+    __device__ __noinline__ void fact_lq_backward()
+    {
+        const int N = CX.P.N;
+        double *v = SV_, *gam = v + ev(CX.P.nvsmax), *Gam = gam + ev(CX.P.ncmax), *tmp0 = Gam + ev(CX.P.ncmax);
+        double *tmp1 = tmp0 + ev(CX.P.nbgmax), *Zi = tmp1 + ev(CX.P.nbgmax), *ds = Zi + ev(2 * CX.P.nsmax);
+        double *xprev = ds + ev(2 * CX.P.nsmax), *tmpx = xprev + ev(CX.P.nxmax), *tmpl = tmpx + ev(CX.P.nxmax);
+        double *hv = SAL_, *Lis = SAL_ + ev(CX.P.nbgmax + CX.P.nxmax);
+        double *Wg = CX.wk + CX.P.w_lq;
+        for (int k = N; k >= 0; k--)
+        {
+            const StageDesc &s = CX.SD[k];
+            const int n = s.n, nu = s.nu, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1, nu1 = s.nu1, n1 = s.n1;
+            const int *idxb = CX.ipool + s.idx_off;
+            const int ldm = ev(n + 1), mw = nb + ng + nx1, nsolve = k == 0 ? n : nu;
+            const double *Ag = CX.qp + s.q_BAt, *Cg = CX.qp + s.q_DCt, *Hg = CX.qp + s.q_RSQ;
+            // ---- Gamma, gamma, gradient, Lh <- tril(RSQ) + reg I
+            {
+                const double *gl = CX.sol + s.sol.lam, *gt = CX.sol + s.sol.t, *grd = rd(0, s), *grm = rm(0, s);
+                const double t_min_inv = CX.o.t_min > 0 ? 1.0 / CX.o.t_min : 1e30;
+                for (int i = tid; i < nc; i += NT)
+                {
+                    const double l = gl[i], tt = gt[i], ti = 1.0 / tt;
+                    Gam[i] = CX.o.t_lam_min == 1 ? (tt < CX.o.t_min ? t_min_inv : ti) * (l < CX.o.lam_min ? CX.o.lam_min : l) : ti * l;
+                    gam[i] = ti * (grm[i] - l * grd[i]);
+                }
+                const double *g_ = rg(0, s);
+                for (int i = tid; i < n; i += NT) v[i] = g_[i];
+                for (int r = tid; r < n; r += NT)
+                    for (int j = 0; j < n; j++) SM_[r + ldm * j] = r >= j ? __ldg(Hg + r + n * j) + (r == j ? CX.o.reg_prim : 0.0) : 0.0;
+                for (int r = tid; r < n; r += NT)
+                    for (int j = 0; j < nb; j++) Wg[r + n * j] = 0.0;
+            }
+            sync();
+            if (ns > 0)
+            {
+                cond_slacks(s, 1, Gam, gam, rg(0, s) + n, Zi, ds, tmp0, tmp1);
+                sync();
+                for (int j = tid; j < 2 * ns; j += NT)
+                {
+                    (CX.wk + s.w_Zsi)[j] = Zi[j];
+                    (CX.wk + s.step.ux + n)[j] = ds[j];
+                }
+            }
+            else
+            {
+                for (int i = tid; i < nbg; i += NT)
+                {
+                    tmp0[i] = Gam[i] + Gam[nbg + i];
+                    tmp1[i] = gam[i] - gam[nbg + i];
+                }
+                sync();
+            }
+            // ---- W: box columns (one per bound; of bounds on the same variable the reference keeps the last one only,
+            // it writes the entry instead of adding to it, :1281-1288), general-constraint columns, A Lxx columns
+            if (!s.dup_idxb)
+                for (int i = tid; i < nb; i += NT)
+                {
+                    const int ix = idxb[i];
+                    const double g0 = tmp0[i] >= 0.0 ? tmp0[i] : 0.0;
+                    Wg[ix + n * i] = sqrt(g0);
+                    v[ix] += tmp1[i];
+                }
+            else if (tid == 0)
+                for (int i = 0; i < nb; i++)
+                {
+                    const int ix = idxb[i];
+                    int last = 1;
+                    for (int j = i + 1; j < nb; j++) last &= idxb[j] != ix;
+                    const double g0 = tmp0[i] >= 0.0 ? tmp0[i] : 0.0;
+                    if (last) Wg[ix + n * i] = sqrt(g0);
+                    v[ix] += tmp1[i];
+                }
+            for (int g = tid; g < ng; g += NT)
+            {
+                const double g0 = tmp0[nb + g] >= 0.0 ? tmp0[nb + g] : 0.0;
+                hv[g] = sqrt(g0);
+            }
+            sync();
+            for (int r = tid; r < n; r += NT)
+            {
+                double acc = 0.0;
+                for (int g = 0; g < ng; g++)
+                {
+                    const double c = __ldg(Cg + r + n * g);
+                    Wg[r + n * (nb + g)] = c * hv[g];
+                    acc += c * tmp1[nb + g];
+                }
+                v[r] += acc;
+            }
+            if (k < N)
+            {
+                const double *L1 = CX.wk + CX.SD[k + 1].w_L + nu1 + n1 * nu1, *b_ = rb(0, s);   // Lxx of stage k+1 (global)
+                for (int r = tid; r < n; r += NT)
+                    for (int j = 0; j < nx1; j++)
+                    {
+                        double acc = 0.0;
+                        for (int c = j; c < nx1; c++) acc += __ldg(Ag + r + n * c) * L1[c + n1 * j];
+                        Wg[r + n * (nbg + j)] = acc;
+                    }
+                // Pb = Lxx (Lxx' b)
+                for (int j = tid; j < nx1; j += NT) tmpx[j] = b_[j];
+                sync();
+                for (int j = tid; j < nx1; j += NT) tmpl[j] = gdot<false>(L1 + j + n1 * j, 1, tmpx + j, nx1 - j);
+                sync();
+                double *Pb = CX.wk + s.w_Pb;
+                for (int i = tid; i < nx1; i += NT)
+                {
+                    const double pb = gdot<false>(L1 + i, n1, tmpl, i + 1);
+                    Pb[i] = pb;
+                    tmpx[i] = pb + xprev[i];
+                }
+                sync();
+                for (int i = tid; i < n; i += NT) v[i] += gdot<true>(Ag + i, n, tmpx, nx1);
+            }
+            sync();
+            // ---- Lh = chol(SM_) in place (right-looking; pivot rule blasfeo_ref/x_lapack_ref.c:84-91)
+            for (int j = 0; j < n; j++)
+            {
+                const double d = SM_[j + ldm * j];
+                const double inv = d > 0.0 ? 1.0 / sqrt(d) : 0.0;
+                sync();
+                for (int r = j + tid; r < n; r += NT) SM_[r + ldm * j] = r == j ? d * inv : SM_[r + ldm * j] * inv;
+                sync();
+                for (int r = j + 1 + tid; r < n; r += NT)
+                {
+                    const double a = SM_[r + ldm * j];
+                    for (int c = j + 1; c <= r; c++) SM_[r + ldm * c] -= a * SM_[c + ldm * j];
+                }
+                sync();
+            }
+            // ---- Householder reflectors from the right, row by row
+            for (int i = 0; i < n; i++)
+            {
+                double part = 0.0;
+                for (int j = tid; j < mw; j += NT)
+                {
+                    const double x = Wg[i + n * j];
+                    hv[j] = x;
+                    part += x * x;
+                }
+                const double sigma = rsum(part);
+                sync();
+                if (sigma == 0.0) continue;
+                const double alpha = SM_[i + ldm * i];
+                const double beta = sqrt(sigma + alpha * alpha);
+                double tmp = alpha <= 0.0 ? alpha - beta : -sigma / (alpha + beta);
+                const double tau = 2.0 * tmp * tmp / (sigma + tmp * tmp);
+                tmp = 1.0 / tmp;
+                for (int j = tid; j < mw; j += NT) hv[j] *= tmp;
+                sync();
+                if (tid == 0) SM_[i + ldm * i] = beta;
+                for (int r = i + 1 + tid; r < n; r += NT)
+                {
+                    double ww = SM_[r + ldm * i];
+                    for (int j = 0; j < mw; j++) ww += Wg[r + n * j] * hv[j];
+                    ww = -ww * tau;
+                    SM_[r + ldm * i] += ww;
+                    for (int j = 0; j < mw; j++) Wg[r + n * j] += ww * hv[j];
+                }
+                sync();
+            }
+            // ---- keep the factor; Linv = 1 / diag
+            {
+                double *Lg = CX.wk + s.w_L, *li = CX.wk + s.w_Linv;
+                for (int r = tid; r < n; r += NT)
+                    for (int j = 0; j < n; j++) Lg[r + n * j] = r >= j ? SM_[r + ldm * j] : 0.0;
+                for (int j = tid; j < n; j += NT)
+                {
+                    const double inv = 1.0 / SM_[j + ldm * j];
+                    li[j] = inv;
+                    Lis[j] = inv;
+                }
+            }
+            sync();
+            // ---- gradient: TRSV_LNN(_MN) on the first nsolve columns, as in the solve-only sweep
+            if (tid < 32)
+            {
+                for (int j = 0; j < nsolve; j++)
+                {
+                    double part = 0.0;
+                    for (int c = tid; c < j; c += 32) part += SM_[j + ldm * c] * v[c];
+                    part = wsum(part);
+                    if (tid == 0) v[j] = (v[j] - part) * Lis[j];
+                    __syncwarp();
+                }
+            }
+            sync();
+            for (int i = nsolve + tid; i < n; i += NT) v[i] -= dot(SM_ + i, ldm, v, 1, nsolve);
+            sync();
+            {
+                double *o_ = vux(1, s);
+                for (int i = tid; i < n; i += NT) o_[i] = v[i];
+                for (int j = tid; j < s.nx; j += NT) xprev[j] = v[nu + j];
+            }
+            // ---- gradient row of the factor for the Riccati getters (p_k = Lxx lrow_x): lrow_x = Lxx^{-1} v_x
+            sync();
+            if (tid < 32)
+            {
+                for (int j = nsolve; j < n; j++)
+                {
+                    double part = 0.0;
+                    for (int c = nsolve + tid; c < j; c += 32) part += SM_[j + ldm * c] * v[c];
+                    part = wsum(part);
+                    if (tid == 0) v[j] = (v[j] - part) * Lis[j];
+                    __syncwarp();
+                }
+            }
+            sync();
+            {
+                double *lr = CX.wk + s.w_lrow;
+                for (int j = tid; j < n; j += NT) lr[j] = v[j];
+            }
+            sync();
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------
     // backward substitution with an existing factorisation (OCP_QP_SOLVE_KKT_STEP, x_ocp_qp_kkt.c:1582-1680)
     // rhs residual set `rhs`, result (backward quantities) into step set `dst`.
     // rm_mode fuses the complementarity right-hand side update of the corrector into this sweep
@@ -1425,7 +1653,7 @@ struct Ker
         const int N = CX.P.N;
         const int SM = CUIPM_STAT_M;
         double res_max[4] = {0, 0, 0, 0}, mu = 0.0, obj = 0.0, gap = 0.0;
-        int lq_count = 0, status, iter = 0;
+        int lq_count = 0, force_lq = 0, status, iter = 0;
         if (stat)
             for (int i = tid; i < SM * (CX.o.stat_max + 1); i += NT) stat[i] = 0.0;
 #ifdef CUIPM_PROFILE
@@ -1508,16 +1736,31 @@ struct Ker
                 double nrm[4] = {0, 0, 0, 0}, dmy;
                 PROF_T0();
                 // affine direction: res_m already holds lam*t - tau_min (written by the residual sweep)
-                fact_backward();
-                PROF_ADD(2);
-                alpha = forward_pass(0, 1, 1, 1, CX.o.lq_fact == 1, nrm);
-                PROF_ADD(3);
-                if (CX.o.lq_fact == 1)
+                // Cholesky, with a switch to LQ for the rest of the solve once a Cholesky step leaves a large residual in the
+                // linear system (x_ocp_qp_ipm.c:2246-2346)
+                int used_lq = 0;
+                if (CX.o.lq_fact == 0 || (CX.o.lq_fact == 1 && !force_lq))
                 {
-                    const double g00 = (CX.wk + CX.SD[0].ires.g)[0];
-                    if ((nrm[0] == 0.0 && g00 != g00) || nrm[0] > 1e-5 || nrm[1] > 1e-5 || nrm[2] > 1e-5 || nrm[3] > 1e-5)
-                        lq_count++;
+                    fact_backward();
+                    PROF_ADD(2);
+                    alpha = forward_pass(0, 1, 1, 1, CX.o.lq_fact == 1, nrm);
+                    PROF_ADD(3);
+                    if (CX.o.lq_fact == 1)
+                    {
+                        const double g00 = (CX.wk + CX.SD[0].ires.g)[0];
+                        if ((nrm[0] == 0.0 && g00 != g00) || nrm[0] > 1e-5 || nrm[1] > 1e-5 || nrm[2] > 1e-5 || nrm[3] > 1e-5)
+                            force_lq = used_lq = 1;
+                    }
                 }
+                else
+                    used_lq = 1;
+                if (used_lq)
+                {
+                    fact_lq_backward();
+                    alpha = forward_pass(0, 1, 0, 1, 0, nrm);
+                    lq_count++;
+                }
+                if (st && tid == 0) st[13] = used_lq;
                 if (st && tid == 0) { st[0] = alpha; st[1] = alpha; }
                 int itref1 = 0;
                 if (CX.o.pred_corr == 1)

@@ -41,14 +41,51 @@ def test_cuda_matches_oracle(built, name, warps):
     osol, oinfo, ostat = ob.oracle_solve(b, o, want_stat=True)
     assert np.array_equal(info["iter"], oinfo["iter"]), (info["iter"], oinfo["iter"])
     assert np.array_equal(info["status"], oinfo["status"])
-    assert np.array_equal(info["lq_count"] > 0, oinfo["lq_count"] > 0)
+    # the switch to the LQ refactorisation is triggered by round-off (see test_oracle_vs_reference): +-1 iteration
+    assert np.max(np.abs(info["lq_count"] - oinfo["lq_count"])) <= 1
     du = np.max(np.abs(b.layout.u_traj(sol) - b.layout.u_traj(osol)))
     assert du <= _tol_default(name), du
     assert np.max(np.abs(sol - osol)) <= 1e-6 * max(1.0, np.max(np.abs(osol)))
     for q in range(b.nbatch):
         it = info["iter"][q]
-        assert np.allclose(stat[q, :it + 1, :13], ostat[q, :it + 1, :13], rtol=1e-4, atol=1e-6)
+        same = info["lq_count"][q] == oinfo["lq_count"][q]
+        assert np.allclose(stat[q, :it + 1, :13], ostat[q, :it + 1, :13], rtol=1e-4, atol=1e-6 if same else 1e-5)
+        if same:
+            assert np.array_equal(stat[q, :it + 1, 13], ostat[q, :it + 1, 13])
     assert np.allclose(info["obj"], oinfo["obj"], rtol=1e-9, atol=1e-9)
+
+
+def _lq_compare(b, o, warps):
+    from oracle import oracle_binding as ob
+    sol, info, stat = _solve(b, o, warps, want_stat=True)
+    osol, oinfo, ostat = ob.oracle_solve(b, o, want_stat=True)
+    assert np.array_equal(info["iter"], oinfo["iter"]), (info["iter"], oinfo["iter"])
+    assert np.array_equal(info["status"], oinfo["status"])
+    assert np.max(np.abs(info["lq_count"] - oinfo["lq_count"])) <= (1 if o.lq_fact == 1 else 0), (info["lq_count"], oinfo["lq_count"])
+    du = np.max(np.abs(b.layout.u_traj(sol) - b.layout.u_traj(osol)).reshape(b.nbatch, -1), axis=1)
+    conv = oinfo["status"] == 0
+    return du, conv, oinfo
+
+
+@pytest.mark.parametrize("name", ["c1_mass_spring", "c2_chain_mass", "rand_general", "rand_soft", "rand_masked", "rand_x0_free", "c5_sized"])
+@pytest.mark.parametrize("warps", [1, 4])
+def test_cuda_lq_every_iteration(built, name, warps):
+    """lq_fact = 2 (HPIPM ROBUST mode): every factorisation goes through the LQ sweep."""
+    b = CASES[name]()
+    du, conv, oinfo = _lq_compare(b, default_opts(lq_fact=2), warps)
+    assert conv.all() and (oinfo["lq_count"] == oinfo["iter"]).all()
+    assert du.max() <= _tol_default(name), du
+
+
+@pytest.mark.parametrize("name", ["infeasible_box", "infeasible_general", "infeasible_soft"])
+def test_cuda_lq_fallback(built, name):
+    """Near-singular instances on which the Cholesky step fails the accuracy test and the solver refactorises with LQ
+    (lq_fact = 1, the acados default): same trajectory as the oracle (pinned against the reference on these cases)."""
+    from test_oracle_vs_reference import LQ_CASES
+    b = LQ_CASES[name]()
+    du, conv, oinfo = _lq_compare(b, default_opts(lq_fact=1), 1)
+    assert (oinfo["lq_count"] > 0).sum() >= 8
+    assert du[conv].max(initial=0.0) <= 1e-9 and du.max() <= 1e-7, du
 
 
 @pytest.mark.parametrize("name", [n for n in CASES if n not in ("rand_infeasible", "c2_chain_hard")])
