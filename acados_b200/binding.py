@@ -14,7 +14,7 @@ import numpy as np
 from .problems import Batch, Layout, Shape
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libcuipm.so")
+LIB_PATH = os.environ.get("CUIPM_LIB") or os.path.join(_HERE, "csrc", "libcuipm.so")
 
 STAT_M = 20
 STATUS_NAMES = {0: "SUCCESS", 1: "MAX_ITER", 2: "MIN_STEP", 3: "NAN_SOL", 4: "INCONS_EQ"}
@@ -86,6 +86,10 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.cuipm_last_launch_count.restype = ip
     lib.cuipm_last_kernel_ms.argtypes = [vp]
     lib.cuipm_last_kernel_ms.restype = C.c_float
+    lib.cuipm_sens_host.argtypes = [vp, ip, vp, vp, ip, C.POINTER(CuipmOpts)]
+    lib.cuipm_sens_host.restype = ip
+    lib.cuipm_sens_device.argtypes = [vp, ip, vp, vp, vp, ip, C.POINTER(CuipmOpts), ip]
+    lib.cuipm_sens_device.restype = ip
     lib.cuipm_set_tuning.argtypes = [vp, C.c_char_p, ip]
     lib.cuipm_set_tuning.restype = ip
     _lib = lib
@@ -173,6 +177,22 @@ class CuipmSolver:
                      d_stat: int = 0):
         self._check(self.lib.cuipm_solve_device(self.handle, nbatch, d_qp, d_sol, d_info, d_stat or None,
                                                 C.byref(opts), 1 if sync else 0))
+
+    def sens(self, seed: np.ndarray, opts: Optional[CuipmOpts] = None, adjoint: bool = False) -> np.ndarray:
+        """Forward / adjoint solution sensitivities for one seed per QP of the preceding ``solve`` (records in the
+        solution layout: (seed_g, seed_b, seed_d, seed_m) in the (ux, pi, lam, t) slots)."""
+        opts = opts or default_opts()
+        seed = np.ascontiguousarray(seed, dtype=np.float64)
+        assert seed.ndim == 2 and seed.shape[1] == self.layout.sol_stride
+        out = np.zeros_like(seed)
+        self._check(self.lib.cuipm_sens_host(self.handle, seed.shape[0], seed.ctypes.data, out.ctypes.data,
+                                             1 if adjoint else 0, C.byref(opts)))
+        return out
+
+    def sens_device(self, nbatch: int, d_qp: int, d_seed: int, d_sens: int, opts: CuipmOpts, adjoint: bool = False,
+                    sync: bool = True):
+        self._check(self.lib.cuipm_sens_device(self.handle, nbatch, d_qp, d_seed, d_sens, 1 if adjoint else 0,
+                                               C.byref(opts), 1 if sync else 0))
 
     def set_tuning(self, key: str, value: int):
         self._check(self.lib.cuipm_set_tuning(self.handle, key.encode(), value))

@@ -28,7 +28,7 @@ struct cuipm_solver
     std::vector<StageDesc> sd_host;
     StageDesc *d_sd = nullptr;
     int *d_ipool = nullptr;
-    double *d_qp = nullptr, *d_sol = nullptr, *d_work = nullptr, *d_stat = nullptr;
+    double *d_qp = nullptr, *d_sol = nullptr, *d_work = nullptr, *d_stat = nullptr, *d_seed = nullptr, *d_sens = nullptr;
     size_t stat_cap = 0;
     cuipm_info *d_info = nullptr;
     cudaStream_t stream = nullptr;
@@ -121,6 +121,8 @@ static int build_desc(cuipm_solver *s, const cuipm_shape *sh)
     }
     P.w_lq = (unsigned) w;
     w += ev2u((size_t) P.nmax * (P.nbgmax + P.nxmax));
+    P.w_bkp = (unsigned) w;
+    w += ev2u(l->sol_stride);
     if (w >= (size_t) 1 << 32 || l->qp_stride >= (size_t) 1 << 32) { set_error("QP record too large for 32-bit offsets"); return CUIPM_ERR_TOO_LARGE; }
     P.qp_stride = l->qp_stride; P.sol_stride = l->sol_stride; P.work_stride = w;
     auto e = [](int n) { return (n + 1) & ~1; };
@@ -196,7 +198,7 @@ extern "C" void cuipm_destroy(cuipm_solver *s)
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->d_sd); cudaFree(s->d_ipool); cudaFree(s->d_qp); cudaFree(s->d_sol); cudaFree(s->d_work);
-    cudaFree(s->d_stat); cudaFree(s->d_info);
+    cudaFree(s->d_stat); cudaFree(s->d_info); cudaFree(s->d_seed); cudaFree(s->d_sens);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     for (int i = 0; i < cuipm_solver::kPipe; i++)
@@ -244,7 +246,7 @@ extern "C" int cuipm_solve_device(cuipm_solver *s, int nbatch, const double *d_q
     if (nbatch == 0) return CUIPM_OK;
     LaunchArgs a;
     a.P = s->P; a.sd = s->d_sd; a.ipool = s->d_ipool; a.qp = d_qp; a.sol = d_sol; a.work = s->d_work; a.info = d_info;
-    a.stat = d_stat; a.o = *opts; a.nbatch = nbatch;
+    a.stat = d_stat; a.o = *opts; a.nbatch = nbatch; a.seed = nullptr; a.sens = nullptr; a.adjoint = 0;
     s->last_opts = *opts;
     CK(cudaEventRecord(s->ev0, s->stream));
     int e = launch_solve(a, s->warps, (void *) s->stream);
@@ -298,7 +300,7 @@ extern "C" int cuipm_solve_host(cuipm_solver *s, int nbatch, const double *qp, d
         a.P = s->P; a.sd = s->d_sd; a.ipool = s->d_ipool; a.qp = s->d_qp + qo; a.sol = s->d_sol + so;
         a.work = s->d_work + s->P.work_stride * (size_t) lo; a.info = s->d_info + lo;
         a.stat = stat ? s->d_stat + (size_t) lo * CUIPM_STAT_M * (opts->stat_max + 1) : nullptr;
-        a.o = *opts; a.nbatch = n;
+        a.o = *opts; a.nbatch = n; a.seed = nullptr; a.sens = nullptr; a.adjoint = 0;
         int e = launch_solve(a, s->warps, (void *) st);
         if (e != 0) { set_error(std::string("kernel launch: ") + cudaGetErrorString((cudaError_t) e)); return CUIPM_ERR_CUDA; }
         CK(cudaMemcpyAsync(sol + so, s->d_sol + so, sizeof(double) * s->P.sol_stride * n, cudaMemcpyDeviceToHost, st));
@@ -312,6 +314,61 @@ extern "C" int cuipm_solve_host(cuipm_solver *s, int nbatch, const double *qp, d
     s->last_launches = nchunk;
     s->last_opts = *opts;
     CK(cudaEventRecord(s->ev1, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1);
+    return CUIPM_OK;
+}
+
+// Solution sensitivities (reference: d_ocp_qp_ipm_sens_frw / _adj, external/hpipm/ocp_qp/x_ocp_qp_ipm.c:3285-3444, behind
+// ocp_qp_hpipm_eval_forw_sens / _adj_sens, acados/ocp_qp/ocp_qp_hpipm.c:481-506): one substitution per QP with the
+// factorisation of the last IPM iteration of the preceding solve, which is still in the solver's work records.
+extern "C" int cuipm_sens_device(cuipm_solver *s, int nbatch, const double *d_qp, const double *d_seed, double *d_sens, int adjoint,
+                                 const cuipm_opts *opts, int sync)
+{
+    if (!s || nbatch < 0 || nbatch > s->max_batch || !d_qp || !d_seed || !d_sens || !opts)
+    {
+        set_error("cuipm_sens_device: bad arguments (nbatch must be <= max_batch)");
+        return CUIPM_ERR_INVALID;
+    }
+    int rc = opts_check(opts);
+    if (rc != CUIPM_OK) return rc;
+    CK(cudaSetDevice(s->device));
+    s->last_launches = 0;
+    if (nbatch == 0) return CUIPM_OK;
+    LaunchArgs a;
+    a.P = s->P; a.sd = s->d_sd; a.ipool = s->d_ipool; a.qp = d_qp; a.sol = nullptr; a.work = s->d_work; a.info = nullptr;
+    a.stat = nullptr; a.o = *opts; a.nbatch = nbatch; a.seed = d_seed; a.sens = d_sens; a.adjoint = adjoint != 0;
+    CK(cudaEventRecord(s->ev0, s->stream));
+    int e = launch_sens(a, s->warps, (void *) s->stream);
+    if (e != 0) { set_error(std::string("kernel launch: ") + cudaGetErrorString((cudaError_t) e)); return CUIPM_ERR_CUDA; }
+    s->last_launches = 1;
+    CK(cudaEventRecord(s->ev1, s->stream));
+    if (sync)
+    {
+        CK(cudaStreamSynchronize(s->stream));
+        cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1);
+    }
+    return CUIPM_OK;
+}
+
+extern "C" int cuipm_sens_host(cuipm_solver *s, int nbatch, const double *seed, double *sens, int adjoint, const cuipm_opts *opts)
+{
+    if (!s || nbatch < 0 || nbatch > s->max_batch || !seed || !sens || !opts)
+    {
+        set_error("cuipm_sens_host: bad arguments (nbatch must be <= max_batch)");
+        return CUIPM_ERR_INVALID;
+    }
+    CK(cudaSetDevice(s->device));
+    if (nbatch == 0) return CUIPM_OK;
+    const size_t bytes = sizeof(double) * s->P.sol_stride * (size_t) s->max_batch;
+    if (!s->d_seed) CK(cudaMalloc(&s->d_seed, bytes));
+    if (!s->d_sens) CK(cudaMalloc(&s->d_sens, bytes));
+    const size_t n = sizeof(double) * s->P.sol_stride * (size_t) nbatch;
+    CK(cudaMemcpyAsync(s->d_seed, seed, n, cudaMemcpyHostToDevice, s->stream));
+    // the QP records of the preceding cuipm_solve_host are still resident in the solver's own device buffer
+    int rc = cuipm_sens_device(s, nbatch, s->d_qp, s->d_seed, s->d_sens, adjoint, opts, 0);
+    if (rc != CUIPM_OK) return rc;
+    CK(cudaMemcpyAsync(sens, s->d_sens, n, cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1);
     return CUIPM_OK;

@@ -36,6 +36,8 @@ struct ProbDesc
     int nct;                                               // total constraint count
     int mid_nx, mid_nu;                                    // (nx, nu) shared by stages 1..N-1 and nx of stage N, or 0,0 if not uniform
     unsigned w_lq;                                         // work record: nmax x (nbgmax + nxmax) scratch of the LQ refactorisation
+    unsigned w_bkp;                                        // work record: lam, t of the iterate of the last factorisation, in a record of the solution layout
+    int pad_;
     size_t qp_stride, sol_stride, work_stride;
     // shared-memory carve (doubles)
     int sm_M, sm_A, sm_AL, sm_C, sm_V;
@@ -54,10 +56,16 @@ struct LaunchArgs
     double *stat;      // may be null
     cuipm_opts o;
     int nbatch;
+    // sensitivity launch only: right-hand side and result records (solution layout), forward / adjoint
+    const double *seed;
+    double *sens;
+    int adjoint;
 };
 
 // launches the solve kernel with `warps` warps per QP on `stream`; returns cudaError_t as int
 int launch_solve(const LaunchArgs &a, int warps, void *stream);
+// launches the sensitivity kernel (one substitution with the factorisation the last solve left in the work records)
+int launch_sens(const LaunchArgs &a, int warps, void *stream);
 // dynamic shared memory (bytes) the kernel needs for P
 size_t smem_bytes(const ProbDesc &P);
 // largest warps-per-QP value compiled

@@ -318,6 +318,10 @@ struct Ker
                     const double mk = CX.mask_constr ? __ldg(gm + i) : 1.0;
                     if (update)
                     {
+                        // iterate of the factorisation just used (UPDATE_VAR_QP backups, x_core_qp_ipm_aux.c:534-575): the point the
+                        // sensitivities are evaluated at
+                        (CX.wk + CX.P.w_bkp + s.sol.lam)[i] = l;
+                        (CX.wk + CX.P.w_bkp + s.sol.t)[i] = tt;
                         l += alpha_u * dl[i];
                         tt += alpha_u * dtt[i];
                         if (CX.o.t_lam_min == 2)
@@ -1646,6 +1650,46 @@ struct Ker
     }
 
     // ---------------------------------------------------------------------------------------------
+    // solution sensitivities (OCP_QP_IPM_SENS_FRW / _ADJ, x_ocp_qp_ipm.c:3285-3444): OCP_QP_SOLVE_KKT_STEP with the seed as
+    // right-hand side, at the iterate of the last factorisation (CX.sol points at the backup record), Pb recomputed.
+    // ---------------------------------------------------------------------------------------------
+    __device__ __noinline__ void sens(const double *seed, double *out, int adjoint)
+    {
+        const int N = CX.P.N;
+        for (int k = 0; k <= N; k++)
+        {
+            const StageDesc s = CX.SD[k];
+            double *g_ = rg(0, s), *b_ = rb(0, s), *d_ = rd(0, s), *m_ = rm(0, s);
+            const double *tb = CX.sol + s.sol.t;
+            for (int i = tid; i < s.n + 2 * s.ns; i += NT) g_[i] = seed[s.sol.ux + i];
+            for (int i = tid; i < s.nx1; i += NT) b_[i] = seed[s.sol.pi + i];
+            for (int i = tid; i < s.nc; i += NT)
+            {
+                d_[i] = seed[s.sol.lam + i];
+                m_[i] = adjoint ? seed[s.sol.t + i] * tb[i] : seed[s.sol.t + i];
+            }
+        }
+        sync();
+        double dmy4[4];
+        solve_backward(0, 1, 0, 0, 0.0);
+        forward_pass(0, 1, 0, 0, 0, dmy4);
+        for (int k = 0; k <= N; k++)
+        {
+            const StageDesc s = CX.SD[k];
+            const double *tb = CX.sol + s.sol.t;
+            for (int i = tid; i < s.n + 2 * s.ns; i += NT) out[s.sol.ux + i] = (CX.wk + s.step.ux)[i];
+            for (int i = tid; i < s.nx1; i += NT) out[s.sol.pi + i] = (CX.wk + s.step.pi)[i];
+            for (int i = tid; i < s.nc; i += NT)
+            {
+                out[s.sol.lam + i] = (CX.wk + s.step.lam)[i];
+                const double dt = (CX.wk + s.step.t)[i];
+                out[s.sol.t + i] = adjoint ? dt * (1.0 / tb[i]) : dt;
+            }
+        }
+        sync();
+    }
+
+    // ---------------------------------------------------------------------------------------------
     // driver (OCP_QP_IPM_SOLVE x_ocp_qp_ipm.c:2684-3120 + OCP_QP_IPM_DELTA_STEP :2208-2682)
     // ---------------------------------------------------------------------------------------------
     __device__ __noinline__ void solve(cuipm_info *info, double *stat)
@@ -1873,6 +1917,33 @@ __global__ void __launch_bounds__(32 * W, (W == 1 ? CUIPM_MINB : (W == 2 ? 8 : 4
     }
 }
 
+template <int W>
+__global__ void __launch_bounds__(32 * W, (W == 1 ? CUIPM_MINB : (W == 2 ? 8 : 4))) cuipm_sens_kernel(const LaunchArgs a)
+{
+    if (threadIdx.x == 0)
+    {
+        CX.P = a.P;
+        CX.SD = a.sd;
+        CX.ipool = a.ipool;
+        CX.o = a.o;
+        CX.mask_constr = 0;      // the reference's sensitivity substitution does not mask
+        CX.nc_mask_inv = 0.0;
+    }
+    Ker<W, 0, 0> K;
+    for (int q = blockIdx.x; q < a.nbatch; q += gridDim.x)
+    {
+        if (threadIdx.x == 0)
+        {
+            CX.qp = a.qp + (size_t) q * a.P.qp_stride;
+            CX.wk = a.work + (size_t) q * a.P.work_stride;
+            CX.sol = CX.wk + a.P.w_bkp;      // lam, t of the iterate the factorisation belongs to
+        }
+        K.sync();
+        K.sens(a.seed + (size_t) q * a.P.sol_stride, a.sens + (size_t) q * a.P.sol_stride, a.adjoint);
+        K.sync();
+    }
+}
+
 }  // namespace
 
 size_t smem_bytes(const ProbDesc &P) { return sizeof(double) * (size_t) P.sm_total; }
@@ -1905,6 +1976,24 @@ int launch_solve(const LaunchArgs &a, int warps, void *stream_)
     }
     if (warps == 2) return (int) launch_one<2, 0, 0>(a, smem, stream);
     return (int) launch_one<4, 0, 0>(a, smem, stream);
+}
+
+template <int W>
+static cudaError_t launch_sens_one(const LaunchArgs &a, size_t smem, cudaStream_t stream)
+{
+    cudaError_t err = cudaFuncSetAttribute(cuipm_sens_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (err != cudaSuccess) return err;
+    cuipm_sens_kernel<W><<<a.nbatch, 32 * W, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+int launch_sens(const LaunchArgs &a, int warps, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t) stream_;
+    const size_t smem = smem_bytes(a.P);
+    if (warps <= 1) return (int) launch_sens_one<1>(a, smem, stream);
+    if (warps == 2) return (int) launch_sens_one<2>(a, smem, stream);
+    return (int) launch_sens_one<4>(a, smem, stream);
 }
 
 }  // namespace cuipm

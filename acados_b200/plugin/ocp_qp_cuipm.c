@@ -17,6 +17,7 @@
 
 #include "blasfeo/include/blasfeo_d_aux.h"
 #include "hpipm/include/hpipm_d_ocp_qp.h"
+#include "hpipm/include/hpipm_d_ocp_qp_seed.h"
 #include "hpipm/include/hpipm_d_ocp_qp_sol.h"
 
 #include "acados/utils/mem.h"
@@ -104,7 +105,7 @@ acados_size_t ocp_qp_cuipm_memory_calculate_size(void *config_, void *dims_, voi
     acados_size_t size = sizeof(ocp_qp_cuipm_memory);
     size += 5 * (dims->N + 1) * sizeof(int) + idx_pool_len(dims) * sizeof(int) + 8;
     size += 2 * (dims->N + 1) * sizeof(int *);
-    size += (l->qp_stride + l->sol_stride) * sizeof(double);
+    size += (l->qp_stride + 3 * l->sol_stride) * sizeof(double);
     size += (acados_size_t) (opts->c.stat_max + 1) * CUIPM_STAT_M * sizeof(double);
     size += 3 * 8;
     cuipm_layout_destroy(l);
@@ -133,6 +134,8 @@ void *ocp_qp_cuipm_memory_assign(void *config_, void *dims_, void *opts_, void *
     cuipm_layout *l = cuipm_layout_create(&sh);
     mem->qp_rec = (double *) c_ptr; c_ptr += l->qp_stride * sizeof(double);
     mem->sol_rec = (double *) c_ptr; c_ptr += l->sol_stride * sizeof(double);
+    mem->seed_rec = (double *) c_ptr; c_ptr += l->sol_stride * sizeof(double);
+    mem->sens_rec = (double *) c_ptr; c_ptr += l->sol_stride * sizeof(double);
     mem->stat = (double *) c_ptr; c_ptr += (acados_size_t) (opts->c.stat_max + 1) * CUIPM_STAT_M * sizeof(double);
     cuipm_layout_destroy(l);
     mem->solver = NULL;
@@ -400,16 +403,48 @@ void ocp_qp_cuipm_solver_get(void *config_, void *qp_in_, void *qp_out_, void *o
         printf("\nocp_qp_cuipm_solver_get: %s\n", mem->solver ? cuipm_last_error() : "no factorisation available (call evaluate first)");
 }
 
+/* Solution sensitivities with the factorisation of the last evaluate() on this memory (reference:
+ * ocp_qp_hpipm_eval_forw_sens / _adj_sens, ocp_qp_hpipm.c:481-506 -> d_ocp_qp_ipm_sens_frw / _adj).  The QP of that
+ * evaluate() is still resident on the device; only the seed travels. */
+static void eval_sens(void *qp_in_, void *seed_, void *qp_out_, void *opts_, void *mem_, int adjoint)
+{
+    ocp_qp_in *qp_in = qp_in_;
+    ocp_qp_seed *seed = seed_;
+    ocp_qp_out *sens = qp_out_;
+    ocp_qp_cuipm_opts *opts = opts_;
+    ocp_qp_cuipm_memory *mem = mem_;
+    if (mem->solver == NULL)
+    {
+        printf("\nerror: ocp_qp_cuipm_eval_%s_sens: no factorisation available, call evaluate first\n", adjoint ? "adj" : "forw");
+        exit(1);
+    }
+    const ocp_qp_dims *d = qp_in->dim;
+    const cuipm_layout *l = cuipm_get_layout(mem->solver);
+    for (int k = 0; k <= d->N; k++)
+    {
+        int nc = 2 * (d->nb[k] + d->ng[k] + d->ns[k]);
+        blasfeo_unpack_dvec(d->nu[k] + d->nx[k] + 2 * d->ns[k], seed->seed_g + k, 0, mem->seed_rec + l->off_ux[k], 1);
+        if (k < d->N) blasfeo_unpack_dvec(d->nx[k + 1], seed->seed_b + k, 0, mem->seed_rec + l->off_pi[k], 1);
+        blasfeo_unpack_dvec(nc, seed->seed_d + k, 0, mem->seed_rec + l->off_lam[k], 1);
+        blasfeo_unpack_dvec(nc, seed->seed_m + k, 0, mem->seed_rec + l->off_t[k], 1);
+    }
+    int rc = cuipm_sens_host(mem->solver, 1, mem->seed_rec, mem->sens_rec, adjoint, &opts->c);
+    if (rc != CUIPM_OK)
+    {
+        printf("\nerror: ocp_qp_cuipm_eval_%s_sens: %s\n", adjoint ? "adj" : "forw", cuipm_last_error());
+        exit(1);
+    }
+    unpack_sol(mem->sens_rec, d, l, sens);
+}
+
 void ocp_qp_cuipm_eval_forw_sens(void *config_, void *qp_in, void *seed, void *qp_out, void *opts_, void *mem_, void *work_)
 {
-    printf("\nerror: ocp_qp_cuipm_eval_forw_sens: not implemented (SURVEY.md section 8(f), rank 2)\n");
-    exit(1);
+    eval_sens(qp_in, seed, qp_out, opts_, mem_, 0);
 }
 
 void ocp_qp_cuipm_eval_adj_sens(void *config_, void *qp_in, void *seed, void *qp_out, void *opts_, void *mem_, void *work_)
 {
-    printf("\nerror: ocp_qp_cuipm_eval_adj_sens: not implemented (SURVEY.md section 8(f), rank 2)\n");
-    exit(1);
+    eval_sens(qp_in, seed, qp_out, opts_, mem_, 1);
 }
 
 void ocp_qp_cuipm_terminate(void *config_, void *mem_, void *work_)

@@ -34,6 +34,7 @@ typedef struct ocp_qp_cuipm_memory_
     int **idxb_p, **idxs_rev_p; /* per-stage pointers into idx_pool */
     int idx_pool_len;
     double *qp_rec, *sol_rec;   /* host staging records for the single-QP path (pinned lazily is not possible in raw memory) */
+    double *seed_rec, *sens_rec; /* staging records of eval_forw_sens / eval_adj_sens (solution layout) */
     double *stat;               /* (stat_max+1) x CUIPM_STAT_M table of the last solve (HPIPM's layout: row per iteration) */
     cuipm_info info;
     double time_qp_solver_call;

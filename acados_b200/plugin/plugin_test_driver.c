@@ -169,6 +169,41 @@ int main(void)
             for (int i = 0; i < NX * NX; i++) e = fmax(e, fabs(Ph[i] - Pg[i]));
             printf("getters K,P at stage 2: max diff %.2e %s\n", e, e <= 1e-6 ? "OK" : "FAIL");
             fails += !(e <= 1e-6);
+            /* solution sensitivities through the xcond solver (ocp_qp_xcond_solver.c:672-726): same seed, both plugins */
+            for (int adj = 0; adj < 2; adj++)
+            {
+                ocp_qp_dims *od = h.dims->orig_dims;
+                void *sm_h = calloc(1, ocp_qp_seed_calculate_size(od) + 64), *sm_g = calloc(1, ocp_qp_seed_calculate_size(od) + 64);
+                ocp_qp_seed *sd_h = ocp_qp_seed_assign(od, sm_h), *sd_g = ocp_qp_seed_assign(od, sm_g);
+                ocp_qp_out *se_h = ocp_qp_out_create(od), *se_g = ocp_qp_out_create(od);
+                for (int k = 0; k <= od->N; k++)
+                {
+                    int n = od->nu[k] + od->nx[k], nc = 2 * (od->nb[k] + od->ng[k]);
+                    for (int i = 0; i < n; i++) { double v = sin(1.0 + i + 3.0 * k); BLASFEO_DVECEL(sd_h->seed_g + k, i) = v; BLASFEO_DVECEL(sd_g->seed_g + k, i) = v; }
+                    if (k < od->N) for (int i = 0; i < od->nx[k + 1]; i++) { double v = 0.1 * cos(2.0 + i + k); BLASFEO_DVECEL(sd_h->seed_b + k, i) = v; BLASFEO_DVECEL(sd_g->seed_b + k, i) = v; }
+                    for (int i = 0; i < nc; i++) { BLASFEO_DVECEL(sd_h->seed_d + k, i) = 0.0; BLASFEO_DVECEL(sd_g->seed_d + k, i) = 0.0; BLASFEO_DVECEL(sd_h->seed_m + k, i) = 0.0; BLASFEO_DVECEL(sd_g->seed_m + k, i) = 0.0; }
+                }
+                if (adj)
+                {
+                    h.config->eval_adj_sens(h.config, h.dims, in_h, sd_h, se_h, h.opts, h.solver->mem, h.solver->work);
+                    g.config->eval_adj_sens(g.config, g.dims, in_g, sd_g, se_g, g.opts, g.solver->mem, g.solver->work);
+                }
+                else
+                {
+                    h.config->eval_forw_sens(h.config, h.dims, in_h, sd_h, se_h, h.opts, h.solver->mem, h.solver->work);
+                    g.config->eval_forw_sens(g.config, g.dims, in_g, sd_g, se_g, g.opts, g.solver->mem, g.solver->work);
+                }
+                double es = 0.0, sc = 0.0;
+                for (int k = 0; k <= od->N; k++)
+                    for (int i = 0; i < od->nu[k] + od->nx[k]; i++)
+                    {
+                        es = fmax(es, fabs(BLASFEO_DVECEL(se_h->ux + k, i) - BLASFEO_DVECEL(se_g->ux + k, i)));
+                        sc = fmax(sc, fabs(BLASFEO_DVECEL(se_h->ux + k, i)));
+                    }
+                printf("%s sensitivities (dux): max diff %.2e of %.2e %s\n", adj ? "adjoint" : "forward", es, sc, es <= 1e-6 * sc && sc > 0 ? "OK" : "FAIL");
+                fails += !(es <= 1e-6 * sc && sc > 0);
+                ocp_qp_out_free(se_h); ocp_qp_out_free(se_g); free(sm_h); free(sm_g);
+            }
             double tq; int sm;
             g.config->qp_solver->memory_get(g.config->qp_solver, ((ocp_qp_xcond_solver_memory *) g.solver->mem)->solver_memory, "time_qp_solver_call", &tq);
             g.config->qp_solver->memory_get(g.config->qp_solver, ((ocp_qp_xcond_solver_memory *) g.solver->mem)->solver_memory, "stat_m", &sm);

@@ -186,6 +186,17 @@ double *cuipm_device_sol_buffer(cuipm_solver *s);      /* max_batch * sol_stride
 cuipm_info *cuipm_device_info_buffer(cuipm_solver *s); /* max_batch */
 void *cuipm_stream(cuipm_solver *s);                   /* cudaStream_t */
 
+/* Solution sensitivities with the factorisation of the last IPM iteration of the preceding solve on this solver
+ * (reference: d_ocp_qp_ipm_sens_frw / d_ocp_qp_ipm_sens_adj, external/hpipm/ocp_qp/x_ocp_qp_ipm.c:3285-3444, reached through
+ * ocp_qp_hpipm_eval_forw_sens / ocp_qp_hpipm_eval_adj_sens, acados/ocp_qp/ocp_qp_hpipm.c:481-506).
+ * seed, sens: nbatch records in the SOLUTION layout -- (seed_g, seed_b, seed_d, seed_m) in the (ux, pi, lam, t) slots of
+ * the seed, the sensitivities of (ux, pi, lam, t) in sens.  One substitution per QP, no refactorisation.  The host
+ * variant uses the QP records the preceding cuipm_solve_host left in the solver's device buffer; the device variant is
+ * handed the same d_qp as the preceding cuipm_solve_device. */
+int cuipm_sens_host(cuipm_solver *s, int nbatch, const double *seed, double *sens, int adjoint, const cuipm_opts *opts);
+int cuipm_sens_device(cuipm_solver *s, int nbatch, const double *d_qp, const double *d_seed, double *d_sens, int adjoint,
+                      const cuipm_opts *opts, int sync);
+
 /* Riccati quantities of the last factorisation (reference: ocp_qp_hpipm_solver_get, ocp_qp_hpipm.c:417-478).
  * field in {"P","p","K","k","Lr"}; copies column-major data of QP `iqp`, stage `stage` into `value`. */
 int cuipm_get_ric(cuipm_solver *s, int iqp, const char *field, int stage, double *value, int size1, int size2);

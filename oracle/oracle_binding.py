@@ -85,3 +85,31 @@ def ref_solve(batch: Batch, opts: CuipmOpts, sol0=None, want_stat=False, nthread
     timing = {"solve_s": ts.value, "wall_s": tw.value,
               "threads": nthreads if nthreads > 0 else int(lib.ref_num_procs())}
     return (sol, info, stat, timing) if want_stat else (sol, info, timing)
+
+
+def _solve_sens(lib, fn, batch, opts, seed, adjoint, nthreads, sol0):
+    nb = batch.nbatch
+    sol = batch.layout.new_sol(nb) if sol0 is None else np.ascontiguousarray(sol0).copy()
+    info = np.zeros(nb, dtype=INFO_DTYPE)
+    seed = np.ascontiguousarray(seed, dtype=np.float64)
+    assert seed.shape == sol.shape
+    sens = np.zeros_like(sol)
+    fn.restype = C.c_int
+    rc = fn(C.byref(batch.shape.as_ctypes()), C.c_int(nb), C.c_void_p(batch.qp.ctypes.data), C.c_void_p(sol.ctypes.data),
+            C.c_void_p(info.ctypes.data), C.byref(opts), C.c_int(nthreads), C.c_void_p(seed.ctypes.data),
+            C.c_void_p(sens.ctypes.data), C.c_int(1 if adjoint else 0))
+    if rc != 0:
+        raise RuntimeError(f"solve_sens failed ({rc})")
+    return sol, info, sens
+
+
+def oracle_solve_sens(batch: Batch, opts: CuipmOpts, seed, adjoint=False, nthreads=0, sol0=None):
+    """Solve, then one forward / adjoint solution-sensitivity evaluation per QP; seed and the returned sens are records
+    in the solution layout with (seed_g, seed_b, seed_d, seed_m) in the (ux, pi, lam, t) slots."""
+    lib = _load(ORACLE_LIB)
+    return _solve_sens(lib, lib.oracle_solve_sens, batch, opts, seed, adjoint, nthreads, sol0)
+
+
+def ref_solve_sens(batch: Batch, opts: CuipmOpts, seed, adjoint=False, nthreads=1, sol0=None):
+    lib = _load(REF_LIB)
+    return _solve_sens(lib, lib.ref_solve_sens, batch, opts, seed, adjoint, nthreads, sol0)

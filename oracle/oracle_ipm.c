@@ -106,6 +106,7 @@ typedef struct
     vset sol, step, itref;
     rset res, res_itref;
     double **res_m_bkp;
+    double **lam_bkp, **t_bkp;     /* iterate of the last factorisation (UPDATE_VAR backups, x_core_qp_ipm_aux.c:534-575) */
     double **L, **Linv, **lrow, **Pb, **Gamma, **gamma, **t_inv, **Zs_inv;
     double *AL;                   /* (nvmax+1) x (nxmax + ngmax) scratch */
     double *lq;                   /* nvmax x (2 nvmax + ngmax + nxmax) scratch of the LQ refactorisation */
@@ -147,7 +148,7 @@ static work *work_create(const cuipm_shape *sh)
         if (sh->ng[k] > ngmax) ngmax = sh->ng[k];
         if (sh->nb[k] + sh->ng[k] > nbgmax) nbgmax = sh->nb[k] + sh->ng[k];
     }
-    size_t bytes = sizeof(double) * (4 * nvt + 4 * net + 16 * nct + nLt + (size_t) (nvmax + 1) * (nxmax + ngmax + 2)
+    size_t bytes = sizeof(double) * (4 * nvt + 4 * net + 18 * nct + nLt + (size_t) (nvmax + 1) * (nxmax + ngmax + 2)
                                      + 4 * (size_t) (nbgmax + 2) + 2 * (size_t) (nvmax + 2) + 64)
                    + sizeof(double *) * 64 * (size_t) (N + 2) + sizeof(int) * 2 * (size_t) (N + 2);
     work *w = (work *) calloc(1, sizeof(work));
@@ -161,7 +162,7 @@ static work *work_create(const cuipm_shape *sh)
                       (double ***) &w->z, &w->sol.ux, &w->sol.pi, &w->sol.lam, &w->sol.t, &w->step.ux, &w->step.pi,
                       &w->step.lam, &w->step.t, &w->itref.ux, &w->itref.pi, &w->itref.lam, &w->itref.t, &w->res.g,
                       &w->res.b, &w->res.d, &w->res.m, &w->res_itref.g, &w->res_itref.b, &w->res_itref.d,
-                      &w->res_itref.m, &w->res_m_bkp, &w->L, &w->Linv, &w->lrow, &w->Pb, &w->Gamma, &w->gamma,
+                      &w->res_itref.m, &w->res_m_bkp, &w->lam_bkp, &w->t_bkp, &w->L, &w->Linv, &w->lrow, &w->Pb, &w->Gamma, &w->gamma,
                       &w->t_inv, &w->Zs_inv};
     for (unsigned i = 0; i < sizeof(pp) / sizeof(pp[0]); i++) *pp[i] = bumpp(&p, np);
     w->nv = (int *) p; p += sizeof(int) * (np + (np & 1));
@@ -183,6 +184,7 @@ static work *work_create(const cuipm_shape *sh)
         w->res.d[k] = bump(&p, nc); w->res.m[k] = bump(&p, nc);
         w->res_itref.d[k] = bump(&p, nc); w->res_itref.m[k] = bump(&p, nc);
         w->res_m_bkp[k] = bump(&p, nc);
+        w->lam_bkp[k] = bump(&p, nc); w->t_bkp[k] = bump(&p, nc);
         w->Gamma[k] = bump(&p, nc); w->gamma[k] = bump(&p, nc); w->t_inv[k] = bump(&p, nc);
         w->Zs_inv[k] = bump(&p, 2 * sh->ns[k]);
         w->L[k] = bump(&p, (size_t) n * n); w->Linv[k] = bump(&p, n); w->lrow[k] = bump(&p, n);
@@ -974,6 +976,8 @@ static void update_var(work *w, double alpha, const cuipm_opts *o)
         for (int i = 0; i < nx1; i++) w->sol.pi[k][i] += alpha * w->step.pi[k][i];
         for (int i = 0; i < nc; i++)
         {
+            w->lam_bkp[k][i] = w->sol.lam[k][i];
+            w->t_bkp[k][i] = w->sol.t[k][i];
             double l = w->sol.lam[k][i] + alpha * w->step.lam[k][i];
             double t = w->sol.t[k][i] + alpha * w->step.t[k][i];
             if (o->t_lam_min == 2)
@@ -1309,6 +1313,65 @@ int oracle_solve(const cuipm_shape *shape, int nbatch, const double *qp, double 
             work_bind(w, l, qp + (size_t) q * l->qp_stride, sol + (size_t) q * l->sol_stride);
             solve_one(w, opts, info + q, stat ? stat + (size_t) q * CUIPM_STAT_M * (opts->stat_max + 1) : 0);
         }
+        work_destroy(w);
+    }
+    oracle_layout_destroy(l);
+    return CUIPM_OK;
+}
+
+/* OCP_QP_IPM_SENS_FRW / _ADJ (x_ocp_qp_ipm.c:3285-3444): one substitution with the factorisation of the last IPM
+ * iteration, at the iterate that factorisation was computed at (the UPDATE_VAR backups), the seed being the right-hand
+ * side.  seed / sens use the solution-record layout: (seed_g, seed_b, seed_d, seed_m) in the (ux, pi, lam, t) slots. */
+static void sens_one(work *w, const cuipm_layout *l, const double *seed, double *sens, int adjoint, double *scratch)
+{
+    int N = w->N;
+    rset rhs;
+    vset out;
+    double **pp = (double **) calloc(8 * (size_t) (N + 1), sizeof(double *));
+    rhs.g = pp; rhs.b = pp + (N + 1); rhs.d = pp + 2 * (N + 1); rhs.m = pp + 3 * (N + 1);
+    out.ux = pp + 4 * (N + 1); out.pi = pp + 5 * (N + 1); out.lam = pp + 6 * (N + 1); out.t = pp + 7 * (N + 1);
+    memcpy(scratch, seed, sizeof(double) * l->sol_stride);
+    for (int k = 0; k <= N; k++)
+    {
+        rhs.g[k] = scratch + l->off_ux[k]; rhs.b[k] = scratch + l->off_pi[k];
+        rhs.d[k] = scratch + l->off_lam[k]; rhs.m[k] = scratch + l->off_t[k];
+        out.ux[k] = sens + l->off_ux[k]; out.pi[k] = sens + l->off_pi[k];
+        out.lam[k] = sens + l->off_lam[k]; out.t[k] = sens + l->off_t[k];
+        if (adjoint)
+            for (int i = 0; i < w->nc[k]; i++) rhs.m[k][i] *= w->t_bkp[k][i];
+    }
+    double **lam_cur = w->sol.lam, **t_cur = w->sol.t;
+    w->sol.lam = w->lam_bkp; w->sol.t = w->t_bkp;
+    solve_kkt_step(w, &rhs, &out, 0, 0);
+    w->sol.lam = lam_cur; w->sol.t = t_cur;
+    if (adjoint)
+        for (int k = 0; k <= N; k++)
+            for (int i = 0; i < w->nc[k]; i++) out.t[k][i] *= w->t_inv[k][i];
+    free(pp);
+}
+
+int oracle_solve_sens(const cuipm_shape *shape, int nbatch, const double *qp, double *sol, cuipm_info *info,
+                      const cuipm_opts *opts, int nthreads, const double *seed, double *sens, int adjoint)
+{
+    if (!opts_supported(opts)) return CUIPM_ERR_INVALID;
+    cuipm_layout *l = oracle_layout_create(shape);
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+#pragma omp parallel num_threads(nthreads)
+    {
+        work *w = work_create(shape);
+        double *scratch = (double *) calloc(l->sol_stride + 2, sizeof(double));
+#pragma omp for schedule(dynamic, 4)
+        for (int q = 0; q < nbatch; q++)
+        {
+            work_bind(w, l, qp + (size_t) q * l->qp_stride, sol + (size_t) q * l->sol_stride);
+            solve_one(w, opts, info + q, 0);
+            sens_one(w, l, seed + (size_t) q * l->sol_stride, sens + (size_t) q * l->sol_stride, adjoint, scratch);
+        }
+        free(scratch);
         work_destroy(w);
     }
     oracle_layout_destroy(l);

@@ -24,6 +24,12 @@ void oracle_layout_destroy(cuipm_layout *l);
 int oracle_solve(const cuipm_shape *shape, int nbatch, const double *qp, double *sol, cuipm_info *info,
                  double *stat, const cuipm_opts *opts, int nthreads);
 
+/* oracle_solve followed by the solution sensitivities for one seed per QP (restates d_ocp_qp_ipm_sens_frw / _adj,
+ * external/hpipm/ocp_qp/x_ocp_qp_ipm.c:3285-3444).  seed and sens are records in the solution layout:
+ * (seed_g, seed_b, seed_d, seed_m) in the (ux, pi, lam, t) slots. */
+int oracle_solve_sens(const cuipm_shape *shape, int nbatch, const double *qp, double *sol, cuipm_info *info,
+                      const cuipm_opts *opts, int nthreads, const double *seed, double *sens, int adjoint);
+
 /* KKT residuals of a given primal-dual point (restates OCP_QP_RES_COMPUTE + INF_NORM,
  * external/hpipm/ocp_qp/x_ocp_qp_res.c:345-531,689-727): res_max[4], mu, obj, dual_gap per QP. */
 int oracle_residuals(const cuipm_shape *shape, int nbatch, const double *qp, const double *sol,

@@ -27,6 +27,7 @@
 #include "hpipm/include/hpipm_d_ocp_qp.h"
 #include "hpipm/include/hpipm_d_ocp_qp_dim.h"
 #include "hpipm/include/hpipm_d_ocp_qp_ipm.h"
+#include "hpipm/include/hpipm_d_ocp_qp_seed.h"
 #include "hpipm/include/hpipm_d_ocp_qp_sol.h"
 
 #include "../include/cuipm.h"
@@ -234,6 +235,63 @@ int ref_solve(const cuipm_shape *sh, int nbatch, const double *qp, double *sol, 
     }
     if (wall_seconds) *wall_seconds = now_s() - w0;
     if (solve_seconds) *solve_seconds = tmax;
+    oracle_layout_destroy(l);
+    return 0;
+}
+
+/* Solve, then evaluate the reference's solution sensitivities (config->eval_forw_sens / eval_adj_sens, i.e.
+ * d_ocp_qp_ipm_sens_frw / _adj) for one seed per QP.  seed / sens: records in the solution layout, (seed_g, seed_b,
+ * seed_d, seed_m) in the (ux, pi, lam, t) slots. */
+int ref_solve_sens(const cuipm_shape *sh, int nbatch, const double *qp, double *sol, cuipm_info *info, const cuipm_opts *co,
+                   int nthreads, const double *seed, double *sens, int adjoint)
+{
+    cuipm_layout *l = oracle_layout_create(sh);
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+#pragma omp parallel num_threads(nthreads)
+    {
+        ref_obj *o = obj_create(sh, co);
+        ocp_qp_out *sout = ocp_qp_out_create(o->dims);
+        void *seed_mem = calloc(1, ocp_qp_seed_calculate_size(o->dims) + 64);
+        ocp_qp_seed *sd = ocp_qp_seed_assign(o->dims, seed_mem);
+#pragma omp for schedule(dynamic, 4)
+        for (int q = 0; q < nbatch; q++)
+        {
+            load_qp(o, sh, l, qp + (size_t) q * l->qp_stride);
+            if (co->warm_start >= 1) load_sol(o, sh, l, sol + (size_t) q * l->sol_stride);
+            o->config->evaluate(o->config, o->in, o->out, o->opts, o->mem, o->work_mem);
+            store_sol(o, sh, l, sol + (size_t) q * l->sol_stride);
+            if (info)
+            {
+                int st, it;
+                o->config->memory_get(o->config, o->mem, "status", &st);
+                o->config->memory_get(o->config, o->mem, "iter", &it);
+                memset(info + q, 0, sizeof(cuipm_info));
+                info[q].status = st; info[q].iter = it;
+            }
+            const double *sq = seed + (size_t) q * l->sol_stride;
+            for (int k = 0; k <= sh->N; k++)
+            {
+                int n = sh->nu[k] + sh->nx[k], nc = 2 * (sh->nb[k] + sh->ng[k] + sh->ns[k]);
+                blasfeo_pack_dvec(n + 2 * sh->ns[k], (double *) sq + l->off_ux[k], 1, sd->seed_g + k, 0);
+                if (k < sh->N) blasfeo_pack_dvec(sh->nx[k + 1], (double *) sq + l->off_pi[k], 1, sd->seed_b + k, 0);
+                blasfeo_pack_dvec(nc, (double *) sq + l->off_lam[k], 1, sd->seed_d + k, 0);
+                blasfeo_pack_dvec(nc, (double *) sq + l->off_t[k], 1, sd->seed_m + k, 0);
+            }
+            if (adjoint) o->config->eval_adj_sens(o->config, o->in, sd, sout, o->opts, o->mem, o->work_mem);
+            else o->config->eval_forw_sens(o->config, o->in, sd, sout, o->opts, o->mem, o->work_mem);
+            ocp_qp_out *keep = o->out;
+            o->out = sout;
+            store_sol(o, sh, l, sens + (size_t) q * l->sol_stride);
+            o->out = keep;
+        }
+        free(seed_mem);
+        ocp_qp_out_free(sout);
+        obj_free(o);
+    }
     oracle_layout_destroy(l);
     return 0;
 }
