@@ -19,6 +19,12 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-I" + os.path.join(ROOT, "include"), "-I" + HERE]
 if os.environ.get("CUIPM_PROFILE"):
     FLAGS.append("-DCUIPM_PROFILE")   # per-pass cycle counters into the last row of the stat table (development)
+# development variants: CUIPM_DEFS="-DX=1 -DY" adds defines, CUIPM_VARIANT=name builds csrc/variants/libcuipm_<name>.so
+# (load it with CUIPM_LIB=<path>, see binding.py) next to the product library
+FLAGS += os.environ.get("CUIPM_DEFS", "").split()
+VARIANT = os.environ.get("CUIPM_VARIANT", "")
+if VARIANT:
+    OUT = os.path.join(HERE, "variants", f"libcuipm_{VARIANT}.so")
 
 
 def _newer(target: str, deps) -> bool:
@@ -29,8 +35,9 @@ def _newer(target: str, deps) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    bdir = os.path.join(HERE, "build")
+    bdir = os.path.join(HERE, "build", VARIANT) if VARIANT else os.path.join(HERE, "build")
     os.makedirs(bdir, exist_ok=True)
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
     hdrs = [h if os.path.isabs(h) else os.path.join(HERE, h) for h in HEADERS]
     objs = []
     procs = []

@@ -236,7 +236,9 @@ struct Ker
     // L2 / HBM round trip each
     __device__ __forceinline__ void pf1(const double *p, int n) const
     {
+#ifndef CUIPM_NO_PF1
         for (int i = tid * 16; i < n; i += NT * 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + i));
+#endif
     }
     // sum_c a[c*sa] * b[c*sb] on shared memory operands, 4 independent chains
     __device__ __forceinline__ double dot(const double *a, int sa, const double *b, int sb, int len)
