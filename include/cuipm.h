@@ -133,7 +133,7 @@ typedef struct cuipm_info {
     double mu;             /* duality measure at exit */
     double obj;            /* objective value at exit */
     double dual_gap;
-    int lq_count;          /* iterations in which the Cholesky accuracy test (x_ocp_qp_ipm.c:2299-2310) failed */
+    int lq_count;          /* iterations factorised with the LQ refactorisation (stat column 13; x_ocp_qp_ipm.c:2299-2346) */
     int reserved;
 } cuipm_info;
 
