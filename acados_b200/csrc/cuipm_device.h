@@ -27,7 +27,9 @@ struct StageDesc
     unsigned q_stage, q_stage_bytes;      // this stage's sub-record inside the QP record (16-byte multiple)
     unsigned w_fac, w_fac_bytes;          // factor part of the work record (L, Linv, lrow, Pb, Zs_inv)
     unsigned w_vec, w_vec_bytes;          // vector part of the work record
+    unsigned pad2_;                       // sizeof(StageDesc) is a multiple of 8: the kernel copies descriptors with 8-byte cp.async
 };
+static_assert(sizeof(StageDesc) % 8 == 0, "StageDesc must be a multiple of 8 bytes");
 
 struct ProbDesc
 {

@@ -37,6 +37,9 @@ struct Ctx
     cuipm_opts o;
     int mask_constr;
     double nc_mask_inv;
+    // descriptors of the stages around the one being processed, slot k & 3: the sweeps read their offsets and dimensions
+    // from here (LDS with immediate offsets) instead of chasing the global-memory table
+    StageDesc ring[4];
 #ifdef CUIPM_PROFILE
     long long prof[16];   // cycles per pass kind (thread 0): 0 res, 1 res_lin, 2 fact_backward, 3 forward, 4 solve_backward, 5 vector passes
 #endif
@@ -231,6 +234,28 @@ struct Ker
         if (tid == 0 && bytes)
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
     }
+    // stage descriptor k -> ring slot k & 3, asynchronously (LDGSTS); desc_wait() + a barrier make it visible
+    __device__ __forceinline__ void desc_fetch(int k)
+    {
+        constexpr int W8 = (int) (sizeof(StageDesc) / 8);
+        if (tid < W8) cpa8(reinterpret_cast<double *>(&CX.ring[k & 3]) + tid, reinterpret_cast<const double *>(CX.SD + k) + tid);
+    }
+    __device__ __forceinline__ void desc_wait() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+    // descriptors for a sweep that starts at stage k0 and moves by dir (+1 / -1): k0 and its successor now, the rest one
+    // stage ahead at the top of each stage (desc_next)
+    __device__ __forceinline__ void desc_begin(int k0, int dir)
+    {
+        sync();
+        desc_fetch(k0);
+        if (k0 + dir >= 0 && k0 + dir <= CX.P.N) desc_fetch(k0 + dir);
+        if (k0 - dir >= 0 && k0 - dir <= CX.P.N) desc_fetch(k0 - dir);
+        desc_wait();
+        sync();
+    }
+    __device__ __forceinline__ void desc_next(int k, int dir)
+    {
+        if (k + 2 * dir >= 0 && k + 2 * dir <= CX.P.N) desc_fetch(k + 2 * dir);
+    }
     // L1 prefetch of n doubles starting at p (one 128-byte line per thread and round): issued at the top of a stage so
     // that the dependent phases below (each a short global-load -> shared -> barrier chain) hit L1 instead of paying an
     // L2 / HBM round trip each
@@ -277,9 +302,11 @@ struct Ker
         double *lam = pim + ev(CX.P.nxmax), *lamr = lam + ev(CX.P.ncmax), *t = lamr + ev(CX.P.ncmax), *msk = t + ev(CX.P.ncmax);
         double *tmp0 = msk + ev(CX.P.ncmax), *tmp1 = tmp0 + ev(CX.P.nbgmax), *g_ = tmp1 + ev(CX.P.nbgmax);
         if (update && alpha_u < 1.0) alpha_u = alpha_u * ((1.0 - alpha_u) * 0.99 + alpha_u * 0.9999999);
+        desc_begin(0, 1);
         for (int k = 0; k <= N; k++)
         {
-            const StageDesc &s = CX.SD[k];
+            const StageDesc &s = CX.ring[k & 3];
+            desc_next(k, 1);
             auto body = [&](auto dd) {
             const int n = dd.n(s), nu = dd.nu(s), nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = dd.nx1(s);
             const int *idxb = CX.ipool + s.idx_off, *rev = idxb + nb;
@@ -298,7 +325,7 @@ struct Ker
             }
             if (k < N)
             {
-                const StageDesc &s1 = CX.SD[k + 1];
+                const StageDesc &s1 = CX.ring[(k + 1) & 3];
                 const double *gu1 = vux(pset, s1) + s1.nu, *du1 = CX.wk + s1.step.ux + s1.nu, *dp = CX.wk + s.step.pi;
                 double *gp = vpi(pset, s);
                 for (int j = tid; j < nx1; j += NT)
@@ -494,6 +521,8 @@ struct Ker
             };
             if (SNX > 0 && k >= 1 && k <= N - 2) body(SMid{});
             else body(RDims{});
+            desc_wait();
+            sync();
         }
         nrm[0] = rmax_nan(m0, f0);
         nrm[1] = rmax_nan(m1, f1);
@@ -572,9 +601,11 @@ struct Ker
         double *Zi = Linv + ev(CX.P.nmax), *ds = Zi + ev(2 * CX.P.nsmax), *D = ds + ev(2 * CX.P.nsmax);   // D: 4 x 4 diagonal block
         double *sCb = SC_ + ev((CX.P.nmax + 2) * CX.P.ngmax);
         int ldm_prev = 0;
+        desc_begin(N, -1);
         for (int k = N; k >= 0; k--)
         {
-            const StageDesc &s = CX.SD[k];
+            const StageDesc &s = CX.ring[k & 3];
+            desc_next(k, -1);
             auto body = [&](auto dd) {
             const int n = dd.n(s), nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = dd.nx1(s), nu1 = dd.nu1(s), n1 = dd.n1(s);
             const int *idxb = CX.ipool + s.idx_off;
@@ -598,7 +629,7 @@ struct Ker
             }
             if (k > 0)
             {
-                const StageDesc &sp = CX.SD[k - 1];
+                const StageDesc &sp = CX.ring[(k - 1) & 3];
                 prefetch_l2(CX.qp + sp.q_stage, sp.q_stage_bytes);
                 prefetch_l2(CX.wk + sp.w_vec, sp.w_vec_bytes);
             }
@@ -850,6 +881,8 @@ struct Ker
             };
             if (SNX > 0 && k >= 1 && k <= N - 2) body(SMid{});
             else body(RDims{});
+            desc_wait();
+            sync();
         }
     }
 
@@ -873,9 +906,11 @@ struct Ker
         double *xprev = ds + ev(2 * CX.P.nsmax), *tmpx = xprev + ev(CX.P.nxmax), *tmpl = tmpx + ev(CX.P.nxmax);
         double *hv = SAL_, *Lis = SAL_ + ev(CX.P.nbgmax + CX.P.nxmax);
         double *Wg = CX.wk + CX.P.w_lq;
+        desc_begin(N, -1);
         for (int k = N; k >= 0; k--)
         {
-            const StageDesc &s = CX.SD[k];
+            const StageDesc &s = CX.ring[k & 3];
+            desc_next(k, -1);
             const int n = s.n, nu = s.nu, nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = s.nx1, nu1 = s.nu1, n1 = s.n1;
             const int *idxb = CX.ipool + s.idx_off;
             const int ldm = ev(n + 1), mw = nb + ng + nx1, nsolve = k == 0 ? n : nu;
@@ -956,7 +991,7 @@ struct Ker
             }
             if (k < N)
             {
-                const double *L1 = CX.wk + CX.SD[k + 1].w_L + nu1 + n1 * nu1, *b_ = rb(0, s);   // Lxx of stage k+1 (global)
+                const double *L1 = CX.wk + CX.ring[(k + 1) & 3].w_L + nu1 + n1 * nu1, *b_ = rb(0, s);   // Lxx of stage k+1 (global)
                 for (int r = tid; r < n; r += NT)
                     for (int j = 0; j < nx1; j++)
                     {
@@ -1077,6 +1112,7 @@ struct Ker
                 double *lr = CX.wk + s.w_lrow;
                 for (int j = tid; j < n; j += NT) lr[j] = v[j];
             }
+            desc_wait();
             sync();
         }
     }
@@ -1095,9 +1131,11 @@ struct Ker
         double *tmp1 = tmp0 + ev(CX.P.nbgmax), *Zi = tmp1 + ev(CX.P.nbgmax), *ds = Zi + ev(2 * CX.P.nsmax);
         double *xprev = ds + ev(2 * CX.P.nsmax), *tmpx = xprev + ev(CX.P.nxmax), *tmpl = tmpx + ev(CX.P.nxmax);
         double *Ls = SM_, *Lis = SAL_, *pbs = Lis + ev(CX.P.nmax);   // staged from global memory at the top of each stage
+        desc_begin(N, -1);
         for (int k = N; k >= 0; k--)
         {
-            const StageDesc &s = CX.SD[k];
+            const StageDesc &s = CX.ring[k & 3];
+            desc_next(k, -1);
             auto body = [&](auto dd) {
             const int n = dd.n(s), nu = dd.nu(s), nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = dd.nx1(s), nu1 = dd.nu1(s), n1 = dd.n1(s);
             const int *idxb = CX.ipool + s.idx_off;
@@ -1107,7 +1145,7 @@ struct Ker
             pf1(Lg, n * nsolve);
             if (k > 0)
             {
-                const StageDesc &sp = CX.SD[k - 1];
+                const StageDesc &sp = CX.ring[(k - 1) & 3];
                 prefetch_l2(CX.qp + sp.q_BAt, (unsigned) (ev(sp.n * sp.nx1) * sizeof(double)));
                 prefetch_l2(CX.wk + sp.w_fac, sp.w_fac_bytes);
             }
@@ -1171,7 +1209,7 @@ struct Ker
                 }
                 else
                 {   // P b = Lxx (Lxx' b) from the factor of stage k+1 in global memory
-                    const double *L1 = CX.wk + CX.SD[k + 1].w_L + nu1 + n1 * nu1, *b_ = rb(rhs, s);
+                    const double *L1 = CX.wk + CX.ring[(k + 1) & 3].w_L + nu1 + n1 * nu1, *b_ = rb(rhs, s);
                     for (int j = tid; j < nx1; j += NT) tmpx[j] = b_[j];
                     sync();
                     for (int j = tid; j < nx1; j += NT) tmpl[j] = gdot<false>(L1 + j + n1 * j, 1, tmpx + j, nx1 - j);
@@ -1214,6 +1252,8 @@ struct Ker
             };
             if (SNX > 0 && k >= 1 && k <= N - 2) body(SMid{});
             else body(RDims{});
+            desc_wait();
+            sync();
         }
     }
 
@@ -1242,9 +1282,11 @@ struct Ker
         double alpha = 1.0;
         double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
         int f0 = 0, f1 = 0, f2 = 0, f3 = 0;
+        desc_begin(0, 1);
         for (int k = 0; k <= N; k++)
         {
-            const StageDesc &s = CX.SD[k];
+            const StageDesc &s = CX.ring[k & 3];
+            desc_next(k, 1);
             auto body = [&](auto dd) {
             const int n = dd.n(s), nu = dd.nu(s), nb = s.nb, ng = s.ng, ns = s.ns, nbg = s.nbg, nc = s.nc, nx1 = dd.nx1(s), nu1 = dd.nu1(s), n1 = dd.n1(s);
             const int *idxb = CX.ipool + s.idx_off, *rev = idxb + nb;
@@ -1253,7 +1295,7 @@ struct Ker
             const double *Ag = CX.qp + s.q_BAt, *Cg = CX.qp + s.q_DCt;
             pf1(Lg, n * nsolve);
             pf1(Ag, n * nx1);
-            if (k < N) pf1(CX.wk + CX.SD[k + 1].w_L + n1 * nu1, n1 * nx1);
+            if (k < N) pf1(CX.wk + CX.ring[(k + 1) & 3].w_L + n1 * nu1, n1 * nx1);
             if (do_lin) pf1(CX.qp + s.q_RSQ, n * n);
             {
                 const double *src = after_fact ? CX.wk + s.w_lrow : vux(dst, s);
@@ -1262,15 +1304,10 @@ struct Ker
             }
             if (k < N)
             {
-                const StageDesc &s1 = CX.SD[k + 1];
+                const StageDesc &s1 = CX.ring[(k + 1) & 3];
                 const double *ps = after_fact ? CX.wk + s1.w_lrow + nu1 : vux(dst, s1) + nu1;   // p part / backward value of x_{k+1}
                 for (int j = tid; j < nx1; j += NT) p1[j] = ps[j];
                 prefetch_l2(CX.qp + s1.q_stage, s1.q_stage_bytes);
-                if (k + 1 < N)
-                {
-                    const StageDesc &s2 = CX.SD[k + 2];
-                    prefetch_l2(CX.wk + s2.w_fac, s2.w_fac_bytes);
-                }
             }
             if (ns > 0)
             {
@@ -1312,7 +1349,7 @@ struct Ker
             }
             if (k < N)
             {
-                const double *L1 = CX.wk + CX.SD[k + 1].w_L + nu1 + n1 * nu1;      // Lxx of stage k+1: L1[i + n1*j]
+                const double *L1 = CX.wk + CX.ring[(k + 1) & 3].w_L + nu1 + n1 * nu1;      // Lxx of stage k+1: L1[i + n1*j]
                 double *ob = rb(1, s);
                 for (int j = tid; j < nx1; j += NT)
                 {
@@ -1476,6 +1513,9 @@ struct Ker
             };
             if (SNX > 0 && k >= 1 && k <= N - 2) body(SMid{});
             else body(RDims{});
+            desc_wait();
+            sync();
+            if (k + 2 <= N) prefetch_l2(CX.wk + CX.ring[(k + 2) & 3].w_fac, CX.ring[(k + 2) & 3].w_fac_bytes);   // factor needed by the next stage (its Lxx)
         }
         if (do_lin)
         {
