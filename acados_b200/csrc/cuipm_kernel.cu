@@ -234,6 +234,12 @@ struct Ker
         if (tid == 0 && bytes)
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
     }
+    // asynchronous copy of n doubles global -> shared (LDGSTS, no register staging: a register-staged copy loop stalls
+    // at its first store until the load returns, one exposed round trip per loop); completion: desc_wait() + barrier
+    __device__ __forceinline__ void cpv(double *sdst, const double *gsrc, int n) const
+    {
+        for (int i = tid; i < n; i += NT) cpa8(sdst + i, gsrc + i);
+    }
     // stage descriptor k -> ring slot k & 3, asynchronously (LDGSTS); desc_wait() + a barrier make it visible
     __device__ __forceinline__ void desc_fetch(int k)
     {
@@ -613,7 +619,9 @@ struct Ker
             const int kc = k < N ? nx1 : 0;
             pf1(CX.qp + s.q_RSQ, n * n);
             pf1(CX.wk + s.w_vec, (int) (s.w_vec_bytes >> 3) / 3);      // step / residual vectors (first third of the vector part)
-            // ---- stage inputs: [A; b'] into SAL_ (asynchronous), constraint quantities
+            // ---- stage inputs: gradient into rowv, [A; b'] into SAL_ (both asynchronous, two groups), constraint quantities
+            cpv(rowv, rg(0, s), n);
+            asm volatile("cp.async.commit_group;" ::: "memory");
             if (k < N)
             {
                 // [A; b'] into SAL_ with cp.async (LDGSTS): thread r copies row r (coalesced across threads); the copies are
@@ -646,12 +654,9 @@ struct Ker
                         Gam[i] = ti * l;
                     gam[i] = ti * (grm[i] - l * grd[i]);
                 }
-                const double *g_ = rg(0, s);
-                for (int i = tid; i < n; i += NT)
-                {
-                    dadd[i] = CX.o.reg_prim;
-                    rowv[i] = g_[i];
-                }
+                for (int i = tid; i < n; i += NT) dadd[i] = CX.o.reg_prim;
+                // the gradient copy (older group) must have landed; the [A; b'] copies may still be in flight
+                asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 1;" ::: "memory");
             }
             sync();
             if (ns > 0)
@@ -1150,8 +1155,13 @@ struct Ker
                 prefetch_l2(CX.wk + sp.w_fac, sp.w_fac_bytes);
             }
             {
-                const double *g_ = rg(rhs, s);
-                for (int i = tid; i < n; i += NT) v[i] = g_[i];
+                // pure copies first, as asynchronous global -> shared copies (all in flight at once) ...
+                cpv(v, rg(rhs, s), n);
+                if (ns > 0) cpv(Zi, CX.wk + s.w_Zsi, 2 * ns);
+                cpv(Ls, Lg, n * nsolve);
+                cpv(Lis, Li, nsolve);
+                if (k < N && use_Pb) cpv(pbs, CX.wk + s.w_Pb, nx1);
+                // ... then the constraint quantities through registers while those are in flight
                 const double *gl = CX.sol + s.sol.lam, *gt = CX.sol + s.sol.t, *grd = rd(rhs, s), *gm = CX.qp + s.q_dmask;
                 double *grm = rm(rhs, s);
                 const double *bk = CX.wk + s.w_rmb, *dl = CX.wk + s.step.lam, *dtt = CX.wk + s.step.t;
@@ -1171,18 +1181,7 @@ struct Ker
                     Gam[i] = (ns > 0 && CX.o.t_lam_min == 1) ? (tt < CX.o.t_min ? t_min_inv : ti) * (l < CX.o.lam_min ? CX.o.lam_min : l) : ti * l;
                     gam[i] = ti * (m - l * grd[i]);
                 }
-                if (ns > 0)
-                {
-                    const double *z_ = CX.wk + s.w_Zsi;
-                    for (int j = tid; j < 2 * ns; j += NT) Zi[j] = z_[j];
-                }
-                for (int e = tid; e < n * nsolve; e += NT) Ls[e] = Lg[e];
-                for (int j = tid; j < nsolve; j += NT) Lis[j] = Li[j];
-                if (k < N && use_Pb)
-                {
-                    const double *pb = CX.wk + s.w_Pb;
-                    for (int j = tid; j < nx1; j += NT) pbs[j] = pb[j];
-                }
+                desc_wait();
             }
             sync();
             if (ns > 0)

@@ -206,7 +206,9 @@ int cuipm_last_launch_count(const cuipm_solver *s);
 /* device time in milliseconds of the main kernel of the last cuipm_solve_* call with sync (CUDA events) */
 float cuipm_last_kernel_ms(const cuipm_solver *s);
 /* launch tuning without a reference counterpart: key "warps" = warps cooperating on one QP (1, 2 or 4; the default is
- * chosen from the stage dimensions).  Results do not depend on it beyond floating-point summation order. */
+ * chosen from the stage dimensions); key "pipe" = chunks (1..8, default 8) the host entry splits a batch into so that
+ * the copies of one chunk overlap the solve of the others.  Results do not depend on either beyond floating-point
+ * summation order. */
 int cuipm_set_tuning(cuipm_solver *s, const char *key, int value);
 
 #ifdef __cplusplus
