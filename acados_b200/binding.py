@@ -75,6 +75,10 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.cuipm_last_error.restype = C.c_char_p
     lib.cuipm_solve_host.argtypes = [vp, ip, vp, vp, vp, vp, C.POINTER(CuipmOpts)]
     lib.cuipm_solve_host.restype = ip
+    lib.cuipm_solve_host_async.argtypes = [vp, ip, vp, vp, vp, vp, C.POINTER(CuipmOpts)]
+    lib.cuipm_solve_host_async.restype = ip
+    lib.cuipm_wait.argtypes = [vp]
+    lib.cuipm_wait.restype = ip
     lib.cuipm_solve_device.argtypes = [vp, ip, vp, vp, vp, vp, C.POINTER(CuipmOpts), ip]
     lib.cuipm_solve_device.restype = ip
     for name in ("cuipm_device_qp_buffer", "cuipm_device_sol_buffer", "cuipm_device_info_buffer", "cuipm_stream"):
@@ -172,6 +176,13 @@ class CuipmSolver:
                                        stat.ctypes.data if want_stat else None, C.byref(opts))
         self._check(rc)
         return (sol, info, stat) if want_stat else (sol, info)
+
+    def solve_host_async(self, nbatch: int, h_qp: int, h_sol: int, h_info: int, opts: CuipmOpts, h_stat: int = 0):
+        """Enqueue a host-buffer solve (raw pointers to PINNED host memory) and return; ``wait()`` completes it."""
+        self._check(self.lib.cuipm_solve_host_async(self.handle, nbatch, h_qp, h_sol, h_info, h_stat or None, C.byref(opts)))
+
+    def wait(self):
+        self._check(self.lib.cuipm_wait(self.handle))
 
     def solve_device(self, nbatch: int, d_qp: int, d_sol: int, d_info: int, opts: CuipmOpts, sync: bool = True,
                      d_stat: int = 0):

@@ -38,6 +38,7 @@ struct cuipm_solver
     cudaEvent_t pipe_done[kPipe] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int last_launches = 0;
+    int pending = 0;                         // an asynchronous host solve has been enqueued and not waited for
     float last_ms = 0.f;
     cuipm_opts last_opts{};
 };
@@ -268,8 +269,11 @@ extern "C" int cuipm_solve_device(cuipm_solver *s, int nbatch, const double *d_q
     return CUIPM_OK;
 }
 
-extern "C" int cuipm_solve_host(cuipm_solver *s, int nbatch, const double *qp, double *sol, cuipm_info *info, double *stat,
-                                const cuipm_opts *opts)
+// Enqueues the whole host-buffer solve (copies in, kernels, copies out) on the solver's streams and returns; cuipm_wait
+// blocks until it has completed.  Two solver objects used alternately overlap the copies of one batch with the solve of
+// the previous one (what a streaming caller -- an RL sweep, the benchmark's end-to-end leg -- wants).
+extern "C" int cuipm_solve_host_async(cuipm_solver *s, int nbatch, const double *qp, double *sol, cuipm_info *info, double *stat,
+                                      const cuipm_opts *opts)
 {
     if (!s || nbatch < 0 || nbatch > s->max_batch || !qp || !sol || !info || !opts)
     {
@@ -279,6 +283,7 @@ extern "C" int cuipm_solve_host(cuipm_solver *s, int nbatch, const double *qp, d
     int rc = opts_check(opts);
     if (rc != CUIPM_OK) return rc;
     CK(cudaSetDevice(s->device));
+    s->pending = 0;
     if (nbatch == 0) return CUIPM_OK;
     const size_t stat_n = (size_t) nbatch * CUIPM_STAT_M * (opts->stat_max + 1);
     if (stat && s->stat_cap < stat_n)
@@ -321,9 +326,26 @@ extern "C" int cuipm_solve_host(cuipm_solver *s, int nbatch, const double *qp, d
     s->last_launches = nchunk;
     s->last_opts = *opts;
     CK(cudaEventRecord(s->ev1, s->stream));
-    CK(cudaStreamSynchronize(s->stream));
-    cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1);
+    s->pending = 1;
     return CUIPM_OK;
+}
+
+extern "C" int cuipm_wait(cuipm_solver *s)
+{
+    if (!s) { set_error("cuipm_wait: null solver"); return CUIPM_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    if (s->pending) cudaEventElapsedTime(&s->last_ms, s->ev0, s->ev1);
+    s->pending = 0;
+    return CUIPM_OK;
+}
+
+extern "C" int cuipm_solve_host(cuipm_solver *s, int nbatch, const double *qp, double *sol, cuipm_info *info, double *stat,
+                                const cuipm_opts *opts)
+{
+    int rc = cuipm_solve_host_async(s, nbatch, qp, sol, info, stat, opts);
+    if (rc != CUIPM_OK) return rc;
+    return cuipm_wait(s);
 }
 
 // Solution sensitivities (reference: d_ocp_qp_ipm_sens_frw / _adj, external/hpipm/ocp_qp/x_ocp_qp_ipm.c:3285-3444, behind

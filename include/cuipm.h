@@ -174,6 +174,14 @@ const char *cuipm_last_error(void);
  * Copies H2D, solves on the device, copies D2H, synchronises.  Returns enum cuipm_error. */
 int cuipm_solve_host(cuipm_solver *s, int nbatch, const double *qp, double *sol, cuipm_info *info,
                      double *stat, const cuipm_opts *opts);
+/* The same, split: cuipm_solve_host_async enqueues the copies and the kernels on the solver's own streams and returns,
+ * cuipm_wait blocks until that work has completed (the host buffers must stay valid until then; pinned memory is needed
+ * for the copies to overlap anything).  Two solver objects used alternately overlap the transfers of one batch with
+ * the solve of the previous one; the reference has no counterpart (its batch solve is a blocking OpenMP loop,
+ * c_templates_tera/acados_solver.in.c:3223-3243). */
+int cuipm_solve_host_async(cuipm_solver *s, int nbatch, const double *qp, double *sol, cuipm_info *info, double *stat,
+                           const cuipm_opts *opts);
+int cuipm_wait(cuipm_solver *s);
 
 /* Device-buffer entry: all pointers are device pointers on the solver's device; asynchronous on the
  * solver's stream unless `sync` != 0. */
