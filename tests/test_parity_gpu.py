@@ -242,3 +242,27 @@ def test_riccati_getters(built):
             Lr = s.get_ric(q, "Lr", k, (nu, nu))
             assert np.allclose(np.triu(Lr, 1), 0) and (np.diag(Lr) > 0).all()
     s.close()
+
+
+def test_async_host_entry_matches_blocking(built):
+    """cuipm_solve_host_async / cuipm_wait on two solver objects used alternately (the double buffering of bench.py's
+    end-to-end leg): bit-identical to the blocking entry, whatever is in flight on the other object."""
+    import torch
+    b = P.chain_mass(1024, seed=99)
+    o = default_opts()
+    ref_sol, ref_info = _solve(b, o)
+    solvers = [CuipmSolver(b.shape, b.nbatch) for _ in range(2)]
+    h_qp = torch.from_numpy(b.qp).pin_memory()
+    outs = [(torch.zeros((b.nbatch, b.layout.sol_stride), dtype=torch.float64).pin_memory(),
+             torch.zeros(b.nbatch * ref_info.dtype.itemsize, dtype=torch.uint8).pin_memory()) for _ in range(2)]
+    for i in range(5):
+        s, (hs, hi) = solvers[i % 2], outs[i % 2]
+        s.wait()
+        s.solve_host_async(b.nbatch, h_qp.data_ptr(), hs.data_ptr(), hi.data_ptr(), o)
+    for s in solvers:
+        s.wait()
+    for hs, hi in outs:
+        assert np.array_equal(hs.numpy(), ref_sol)
+        assert np.array_equal(np.frombuffer(hi.numpy().tobytes(), dtype=ref_info.dtype)["iter"], ref_info["iter"])
+    for s in solvers:
+        s.close()
