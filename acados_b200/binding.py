@@ -94,6 +94,16 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.cuipm_sens_host.restype = ip
     lib.cuipm_sens_device.argtypes = [vp, ip, vp, vp, vp, ip, C.POINTER(CuipmOpts), ip]
     lib.cuipm_sens_device.restype = ip
+    lib.cuipm_reducer_create.argtypes = [vp, ip, C.POINTER(C.c_int), ip]
+    lib.cuipm_reducer_create.restype = vp
+    lib.cuipm_reducer_destroy.argtypes = [vp]
+    for name in ("cuipm_reducer_reduced_shape", "cuipm_reducer_full_layout", "cuipm_reducer_reduced_layout"):
+        getattr(lib, name).argtypes = [vp]
+        getattr(lib, name).restype = vp
+    lib.cuipm_reduce_device.argtypes = [vp, ip, vp, vp, vp]
+    lib.cuipm_reduce_device.restype = ip
+    lib.cuipm_restore_device.argtypes = [vp, ip, vp, vp, vp, C.c_double, C.c_double, vp]
+    lib.cuipm_restore_device.restype = ip
     lib.cuipm_set_tuning.argtypes = [vp, C.c_char_p, ip]
     lib.cuipm_set_tuning.restype = ip
     _lib = lib
@@ -220,3 +230,49 @@ class CuipmSolver:
         out = np.zeros(shape2[::-1])  # column-major (size1 x size2)
         self._check(self.lib.cuipm_get_ric(self.handle, iqp, field.encode(), stage, out.ctypes.data, shape2[0], shape2[1]))
         return out.T
+
+
+class CuipmReducer:
+    """Stage-0 equality elimination / restore on the device (``cuipm_reducer_*``, include/cuipm.h): maps QP records of
+    the shape the user poses (x0 a stage-0 equality) to records of the reduced shape and solutions back."""
+
+    def __init__(self, full_shape: Shape, idxe0, device: int = 0):
+        self.lib = load_library()
+        self.full_shape = full_shape
+        self._cshape = full_shape.as_ctypes()
+        idx = (C.c_int * max(1, len(idxe0)))(*[int(i) for i in idxe0])
+        self.handle = self.lib.cuipm_reducer_create(C.byref(self._cshape), len(idxe0), idx, device)
+        if not self.handle:
+            raise RuntimeError("cuipm_reducer_create failed: " + self.lib.cuipm_last_error().decode())
+        N = full_shape.N
+
+        class _CS(C.Structure):
+            _fields_ = [("N", C.c_int)] + [(n, C.POINTER(C.c_int)) for n in ("nx", "nu", "nb", "ng", "ns")] + \
+                       [("idxb", C.POINTER(C.POINTER(C.c_int))), ("idxs_rev", C.POINTER(C.POINTER(C.c_int)))]
+        cs = C.cast(self.lib.cuipm_reducer_reduced_shape(self.handle), C.POINTER(_CS)).contents
+        g = lambda a: [int(a[k]) for k in range(N + 1)]
+        nx, nu, nb, ng, ns = g(cs.nx), g(cs.nu), g(cs.nb), g(cs.ng), g(cs.ns)
+        self.reduced_shape = Shape(N, nx, nu, nb, ng, ns, [[int(cs.idxb[k][i]) for i in range(nb[k])] for k in range(N + 1)],
+                                   [[int(cs.idxs_rev[k][i]) for i in range(nb[k] + ng[k])] for k in range(N + 1)])
+        self.full_layout, self.reduced_layout = Layout(full_shape), Layout(self.reduced_shape)
+
+    def reduce(self, nbatch: int, d_qp_full: int, d_qp_red: int, stream: int = 0):
+        rc = self.lib.cuipm_reduce_device(self.handle, nbatch, d_qp_full, d_qp_red, stream or None)
+        if rc != 0:
+            raise RuntimeError(self.lib.cuipm_last_error().decode())
+
+    def restore(self, nbatch: int, d_qp_full: int, d_sol_red: int, d_sol_full: int, lam_min: float, t_min: float, stream: int = 0):
+        rc = self.lib.cuipm_restore_device(self.handle, nbatch, d_qp_full, d_sol_red, d_sol_full, lam_min, t_min, stream or None)
+        if rc != 0:
+            raise RuntimeError(self.lib.cuipm_last_error().decode())
+
+    def close(self):
+        if self.handle:
+            self.lib.cuipm_reducer_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

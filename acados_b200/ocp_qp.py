@@ -227,7 +227,9 @@ class OcpQpOptions:
 class PackedBatch:
     """Records of a batch plus what is needed to restore the eliminated stage-0 states afterwards."""
 
-    def __init__(self, qps: Sequence[OcpQp]):
+    def __init__(self, qps: Sequence[OcpQp], eliminate: bool = True):
+        """eliminate=False keeps stage 0 as posed (records of the FULL shape, x0 still a pair of coinciding bounds): the
+        input format of the device-side elimination (binding.CuipmReducer)."""
         q0 = qps[0]
         for q in qps:
             q.make_consistent()
@@ -243,7 +245,7 @@ class PackedBatch:
             raise ValueError("idxe at stages > 0 is not supported (the reference eliminates stage-0 states only)")
         # stage 0: eliminated state components E (through their bounds), kept ones F
         nu0, nx0 = int(d.nu[0]), int(d.nx[0])
-        eb = np.asarray(q0.idxe[0], dtype=int)                      # positions in the bound list
+        eb = np.asarray(q0.idxe[0], dtype=int) if eliminate else np.zeros(0, dtype=int)   # positions in the bound list
         self.elim_b = eb
         self.E = np.asarray(q0.idxb[0], dtype=int)[eb] - nu0 if len(eb) else np.zeros(0, dtype=int)   # state indices
         self.F = np.setdiff1d(np.arange(nx0), self.E)
@@ -388,16 +390,30 @@ class PackedBatch:
 class OcpQpBatchSolver:
     """Solves a batch of structurally identical QPs in one launch of the CUDA path."""
 
-    def __init__(self, qps: Sequence[OcpQp], opts: Optional[OcpQpOptions] = None, device: int = 0):
+    def __init__(self, qps: Sequence[OcpQp], opts: Optional[OcpQpOptions] = None, device: int = 0, device_reduce: bool = True):
+        """device_reduce: run the stage-0 equality elimination and the restore on the GPU (cuipm_reduce_device /
+        cuipm_restore_device): the records travel as posed, the reduced records never exist on the host.  False keeps
+        both on the host (numpy)."""
         self.opts = opts or OcpQpOptions()
         self.opts.make_consistent(qps[0].N)
-        self.packed = PackedBatch(qps)
+        self.device, self.device_reduce = device, device_reduce
         self.c_opts = self.opts.to_cuipm()
-        self._solver = CuipmSolver(self.packed.shape, self.packed.nbatch, device)
+        self._reducer = None
+        self._load(qps)
+        self._solver = CuipmSolver(self.packed.shape if not device_reduce else self._reducer.reduced_shape, len(qps), device)
         self._sol = None
         self.info = None
         self.stat = None
         self.result = None
+
+    def _load(self, qps):
+        if self.device_reduce:
+            from .binding import CuipmReducer
+            self.packed = PackedBatch(qps, eliminate=False)
+            if self._reducer is None:
+                self._reducer = CuipmReducer(self.packed.shape, [int(i) for i in qps[0].idxe[0]], self.device)
+        else:
+            self.packed = PackedBatch(qps)
 
     @property
     def N(self) -> int:
@@ -405,13 +421,36 @@ class OcpQpBatchSolver:
 
     def update(self, qps: Sequence[OcpQp]):
         """New data, same structure (an SQP / RL sweep re-solving with updated linearisations)."""
-        self.packed = PackedBatch(qps)
+        self._load(qps)
 
     def solve(self) -> np.ndarray:
         """Returns the acados status per QP (0 success, 2 max iter, 3 min step, 1 NaN; ocp_qp_hpipm.c:398-404)."""
         warm = self._sol if (self.c_opts.warm_start >= 2 and self._sol is not None) else None
-        self._sol, self.info, self.stat = self._solver.solve(self.packed.qp, self.c_opts, sol0=warm, want_stat=True)
-        self.result = self.packed.unpack(self._sol, self.c_opts.lam_min, self.c_opts.t_min)
+        if not self.device_reduce:
+            self._sol, self.info, self.stat = self._solver.solve(self.packed.qp, self.c_opts, sol0=warm, want_stat=True)
+            self.result = self.packed.unpack(self._sol, self.c_opts.lam_min, self.c_opts.t_min)
+        else:
+            import torch   # device buffers and copies only
+            from .binding import INFO_DTYPE
+            nb, red, o = self.packed.nbatch, self._reducer, self.c_opts
+            dev = torch.device("cuda", self.device)
+            st = self._solver.lib.cuipm_stream(self._solver.handle)
+            d_full = torch.from_numpy(self.packed.qp).to(dev)
+            d_red = torch.empty((nb, red.reduced_layout.qp_stride), dtype=torch.float64, device=dev)
+            d_sol = torch.zeros((nb, red.reduced_layout.sol_stride), dtype=torch.float64, device=dev) if warm is None \
+                else torch.from_numpy(warm).to(dev)
+            d_info = torch.zeros(nb * INFO_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+            d_stat = torch.zeros((nb, o.stat_max + 1, STAT_M), dtype=torch.float64, device=dev)
+            d_sol_full = torch.empty((nb, red.full_layout.sol_stride), dtype=torch.float64, device=dev)
+            torch.cuda.synchronize(dev)
+            red.reduce(nb, d_full.data_ptr(), d_red.data_ptr(), st)
+            self._solver.solve_device(nb, d_red.data_ptr(), d_sol.data_ptr(), d_info.data_ptr(), o, sync=False, d_stat=d_stat.data_ptr())
+            red.restore(nb, d_full.data_ptr(), d_sol.data_ptr(), d_sol_full.data_ptr(), o.lam_min, o.t_min, st)
+            self._solver.wait()
+            self._sol = d_sol.cpu().numpy()
+            self.info = np.frombuffer(d_info.cpu().numpy().tobytes(), dtype=INFO_DTYPE).copy()
+            self.stat = d_stat.cpu().numpy()
+            self.result = self.packed.unpack(d_sol_full.cpu().numpy())
         return np.array([{0: 0, 1: 2, 2: 3, 3: 1, 4: 9}.get(int(s), -1) for s in self.info["status"]])
 
     def get(self, stage: int, field: str) -> np.ndarray:
@@ -432,14 +471,17 @@ class OcpQpBatchSolver:
 
     def close(self):
         self._solver.close()
+        if self._reducer is not None:
+            self._reducer.close()
 
 
 class OcpQpSolver:
     """Single-QP front end with the reference's method names (``AcadosOcpQpSolver``)."""
 
-    def __init__(self, qp: OcpQp, opts: Optional[OcpQpOptions] = None, verbose: bool = False, device: int = 0):
+    def __init__(self, qp: OcpQp, opts: Optional[OcpQpOptions] = None, verbose: bool = False, device: int = 0,
+                 device_reduce: bool = True):
         self.qp = qp
-        self._b = OcpQpBatchSolver([qp], opts, device)
+        self._b = OcpQpBatchSolver([qp], opts, device, device_reduce)
         self._status = None
 
     @property

@@ -205,6 +205,24 @@ int cuipm_sens_host(cuipm_solver *s, int nbatch, const double *seed, double *sen
 int cuipm_sens_device(cuipm_solver *s, int nbatch, const double *d_qp, const double *d_seed, double *d_sens, int adjoint,
                       const cuipm_opts *opts, int sync);
 
+/* ---- stage-0 equality elimination on the device ---------------------------------------------------------------------
+ * Reference: d_ocp_qp_reduce_eq_dof / d_ocp_qp_restore_eq_dof (external/hpipm/ocp_qp/x_ocp_qp_red.c:278-560, 848-994), which
+ * acados' ocp_qp_partial_condensing (acados/ocp_qp/ocp_qp_partial_condensing.c:523-689) runs around every QP solve; with
+ * the default N2 = N they are all that module does.  `full` is the shape as the user poses it (stage 0 carries x_0 with
+ * state bounds; idxe0[0..nbxe0) are the positions, in stage 0's bound list, of the bounds that are equalities lb = ub =
+ * x0).  cuipm_reduce_device maps QP records of the full shape to QP records of the reduced shape (the one to create the
+ * cuipm_solver with), cuipm_restore_device maps solution records back, multipliers of the dropped bounds included.
+ * All pointers are device pointers; stream is a cudaStream_t (may be NULL). */
+typedef struct cuipm_reducer cuipm_reducer;
+cuipm_reducer *cuipm_reducer_create(const cuipm_shape *full, int nbxe0, const int *idxe0, int device);
+void cuipm_reducer_destroy(cuipm_reducer *r);
+const cuipm_shape *cuipm_reducer_reduced_shape(const cuipm_reducer *r);     /* owned by r */
+const cuipm_layout *cuipm_reducer_full_layout(const cuipm_reducer *r);
+const cuipm_layout *cuipm_reducer_reduced_layout(const cuipm_reducer *r);
+int cuipm_reduce_device(cuipm_reducer *r, int nbatch, const double *d_qp_full, double *d_qp_red, void *stream);
+int cuipm_restore_device(cuipm_reducer *r, int nbatch, const double *d_qp_full, const double *d_sol_red, double *d_sol_full,
+                         double lam_min, double t_min, void *stream);
+
 /* Riccati quantities of the last factorisation (reference: ocp_qp_hpipm_solver_get, ocp_qp_hpipm.c:417-478).
  * field in {"P","p","K","k","Lr"}; copies column-major data of QP `iqp`, stage `stage` into `value`. */
 int cuipm_get_ric(cuipm_solver *s, int iqp, const char *field, int stage, double *value, int size1, int size2);

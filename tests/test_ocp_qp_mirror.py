@@ -223,12 +223,21 @@ def test_batch_solver_gpu(built):
     from acados_b200.ocp_qp import OcpQpBatchSolver
     rng = np.random.default_rng(5)
     qps = [random_ocp_qp(rng) for _ in range(16)]
-    bs = OcpQpBatchSolver(qps)
+    bs = OcpQpBatchSolver(qps)                     # elimination + restore on the device
     status = bs.solve()
     assert (status == 0).all()
-    osol, oinfo, o = _oracle_solve(bs.packed)
+    bh = OcpQpBatchSolver(qps, device_reduce=False)    # the same on the host: identical solve, identical restored solution
+    assert (bh.solve() == 0).all() and np.array_equal(bh.get_stats("iter"), bs.get_stats("iter"))
+    for k in range(bs.N + 1):
+        # the reduced records differ in the last bit (summation order of the x0 terms); the IPM amplifies that to ~1e-11
+        for f in ("u", "x", "sl", "su"):
+            assert np.allclose(bs.get(k, f), bh.get(k, f), rtol=0, atol=1e-9), (k, f)
+        for f in ("lam", "t"):
+            assert np.allclose(bs.get(k, f), bh.get(k, f), rtol=1e-6, atol=1e-8), (k, f)
+    bh.close()
+    osol, oinfo, o = _oracle_solve(PackedBatch(qps))
     assert np.array_equal(bs.get_stats("iter"), oinfo["iter"])
-    ores = bs.packed.unpack(osol, o.lam_min, o.t_min)
+    ores = PackedBatch(qps).unpack(osol, o.lam_min, o.t_min)
     for k in range(bs.N + 1):
         assert np.max(np.abs(bs.get(k, "u") - ores["u"][k]), initial=0.0) <= 1e-9
         assert np.max(np.abs(bs.get(k, "x") - ores["x"][k])) <= 1e-8
@@ -236,3 +245,48 @@ def test_batch_solver_gpu(built):
         stat, dyn, feas, comp = kkt_residuals(qp, bs.result, i)
         assert stat <= 1e-5 and dyn <= 1e-7 and feas <= 1e-7
     bs.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("soft,general", [(False, False), (True, True)])
+def test_device_elimination_matches_host(built, soft, general):
+    """cuipm_reduce_device / cuipm_restore_device (the batched reduce_eq_dof / restore_eq_dof of row a15) against the
+    host implementation above, which the CPU tests check against the reference's fixtures and the original KKT system."""
+    import torch
+    from acados_b200.binding import CuipmReducer, CuipmSolver
+    rng = np.random.default_rng(11)
+    qps = [random_ocp_qp(rng, soft=soft, general=general) for _ in range(32)]
+    full = PackedBatch(qps, eliminate=False)              # records as posed: x0 = coinciding stage-0 bounds
+    red = PackedBatch(qps)                                # host-side elimination
+    r = CuipmReducer(full.shape, [int(i) for i in qps[0].idxe[0]])
+    assert (r.reduced_shape.nx, r.reduced_shape.nb, r.reduced_shape.idxb, r.reduced_shape.idxs_rev) == \
+           (red.shape.nx, red.shape.nb, red.shape.idxb, red.shape.idxs_rev)
+    d_full = torch.from_numpy(full.qp).cuda()
+    d_red = torch.zeros((len(qps), red.layout.qp_stride), dtype=torch.float64, device="cuda")
+    r.reduce(len(qps), d_full.data_ptr(), d_red.data_ptr())
+    torch.cuda.synchronize()
+    got = d_red.cpu().numpy()
+    assert np.max(np.abs(got - red.qp)) <= 1e-13 * max(1.0, np.max(np.abs(red.qp)))
+    # solve the device-reduced records, restore on the device, compare with the host restore of the same solution
+    o = default_opts()
+    s = CuipmSolver(red.shape, len(qps))
+    sol_red, info = s.solve(got, o)
+    s.close()
+    assert (info["status"] == 0).all()
+    d_sol_red = torch.from_numpy(sol_red).cuda()
+    d_sol_full = torch.zeros((len(qps), full.layout.sol_stride), dtype=torch.float64, device="cuda")
+    r.restore(len(qps), d_full.data_ptr(), d_sol_red.data_ptr(), d_sol_full.data_ptr(), o.lam_min, o.t_min)
+    torch.cuda.synchronize()
+    sol_full = d_sol_full.cpu().numpy()
+    r.close()
+    ref = red.unpack(sol_red, o.lam_min, o.t_min)
+    Lf = full.layout
+    for k in range(full.N + 1):
+        nu, nx, ns = full.shape.nu[k], full.shape.nx[k], full.shape.ns[k]
+        ux = Lf.view(sol_full, "ux", k)
+        assert np.array_equal(ux[:, :nu], ref["u"][k]) and np.allclose(ux[:, nu:nu + nx], ref["x"][k], rtol=0, atol=1e-15)
+        assert np.array_equal(ux[:, nu + nx:nu + nx + ns], ref["sl"][k])
+        assert np.allclose(Lf.view(sol_full, "lam", k), ref["lam"][k], rtol=1e-12, atol=1e-12)
+        assert np.allclose(Lf.view(sol_full, "t", k), ref["t"][k], rtol=1e-12, atol=1e-14)
+        if k < full.N:
+            assert np.array_equal(Lf.view(sol_full, "pi", k), ref["pi"][k])
