@@ -260,6 +260,12 @@ extern "C" cuipm_reducer *cuipm_reducer_create(const cuipm_shape *full, int nbxe
     r->lf = cuipm_layout_create(full);
     r->lr = cuipm_layout_create(&r->red);
     const cuipm_layout *lf = r->lf, *lr = r->lr;
+    if (lf->qp_stride >= ((size_t) 1 << 32) || lf->sol_stride >= ((size_t) 1 << 32))
+    {
+        set_error("QP record too large for 32-bit offsets");
+        cuipm_reducer_destroy(r);
+        return nullptr;
+    }
     RedDesc &D = r->D;
     D.nu = nu0; D.nx_f = nx0; D.nx_r = r->nx[0]; D.n_f = nu0 + nx0; D.n_r = nu0 + r->nx[0]; D.nb_f = nb0; D.nb_r = r->nb[0];
     D.ng = ng0; D.ns = ns0; D.nx1 = N > 0 ? full->nx[1] : 0; D.ne = nbxe0;
