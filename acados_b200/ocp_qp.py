@@ -13,8 +13,9 @@ bounds marked as equalities (``idxe``: x0 = lbx_0) are eliminated before the sol
 external/hpipm/ocp_qp/x_ocp_qp_red.c:278-560) and restored afterwards, multipliers included
 (d_ocp_qp_restore_eq_dof, :848-994) -- here vectorised over the batch in numpy -- and the data are packed into the
 cuipm QP records (include/cuipm.h, HPIPM's conventions: BAt = [B'; A'], RSQ = [R S; S' Q] lower,
-DCt = [D'; C'], d = [lb, lg, -ub, -ug, lls, lus]).  Block condensing with N2 < N stays the reference's module
-behind the C plugin (acados_b200/plugin); on the GPU the uncondensed QP is the cheaper one to factorise.
+DCt = [D'; C'], d = [lb, lg, -ub, -ug, lls, lus]).  Block condensing with cond_N < N is acados_b200/condensing.py
+(the same module restated on the host, records to records); on the GPU the uncondensed QP is usually the cheaper one
+to factorise, so cond_N defaults to N as in the reference.
 
 The solve itself is the CUDA path behind the C ABI (binding.CuipmSolver): no CPU fallback.
 """
@@ -208,9 +209,8 @@ class OcpQpOptions:
         if self.qp_solver not in ("PARTIAL_CONDENSING_CUIPM", "PARTIAL_CONDENSING_HPIPM"):
             raise ValueError(f"qp_solver {self.qp_solver} is not served by this backend (PARTIAL_CONDENSING_CUIPM; "
                              "PARTIAL_CONDENSING_HPIPM is accepted as an alias so that existing scripts switch over).")
-        if self.cond_N is not None and self.cond_N != N:
-            raise ValueError("cond_N != N: block condensing is the reference's module behind the C plugin "
-                             "(acados_b200/plugin); this Python entry solves the uncondensed QP.")
+        if self.cond_N is not None and not 1 <= self.cond_N <= N:
+            raise ValueError(f"cond_N must be in 1..N={N}")
         if self.hpipm_mode != "BALANCE":
             raise ValueError("hpipm_mode: only BALANCE (the acados default) selects code paths that exist here")
 
@@ -400,14 +400,26 @@ class OcpQpBatchSolver:
         self.c_opts = self.opts.to_cuipm()
         self._reducer = None
         self._load(qps)
-        self._solver = CuipmSolver(self.packed.shape if not device_reduce else self._reducer.reduced_shape, len(qps), device)
+        solve_shape = self._cond.cshape if self._cond is not None else (self._reducer.reduced_shape if self.device_reduce else self.packed.shape)
+        self._solver = CuipmSolver(solve_shape, len(qps), device)
         self._sol = None
         self.info = None
         self.stat = None
         self.result = None
 
     def _load(self, qps):
-        if self.device_reduce:
+        N = qps[0].N
+        cond_N = self.opts.cond_N if self.opts.cond_N is not None else N
+        self._cond = None
+        if cond_N < N:
+            # block condensing (acados_b200/condensing.py, the reference's ocp_qp_partial_condensing restated on the host,
+            # batch-vectorised): eliminate x0, condense N -> cond_N stages, solve the condensed QPs on the GPU, expand
+            from .condensing import BlockCondenser
+            self.device_reduce = False
+            self.packed = PackedBatch(qps)
+            self._cond = BlockCondenser(self.packed.shape, cond_N)
+            self._cqp = self._cond.condense(self.packed.qp)
+        elif self.device_reduce:
             from .binding import CuipmReducer
             self.packed = PackedBatch(qps, eliminate=False)
             if self._reducer is None:
@@ -426,7 +438,10 @@ class OcpQpBatchSolver:
     def solve(self) -> np.ndarray:
         """Returns the acados status per QP (0 success, 2 max iter, 3 min step, 1 NaN; ocp_qp_hpipm.c:398-404)."""
         warm = self._sol if (self.c_opts.warm_start >= 2 and self._sol is not None) else None
-        if not self.device_reduce:
+        if self._cond is not None:
+            self._sol, self.info, self.stat = self._solver.solve(self._cqp, self.c_opts, sol0=warm, want_stat=True)
+            self.result = self.packed.unpack(self._cond.expand(self.packed.qp, self._sol), self.c_opts.lam_min, self.c_opts.t_min)
+        elif not self.device_reduce:
             self._sol, self.info, self.stat = self._solver.solve(self.packed.qp, self.c_opts, sol0=warm, want_stat=True)
             self.result = self.packed.unpack(self._sol, self.c_opts.lam_min, self.c_opts.t_min)
         else:

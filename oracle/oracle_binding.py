@@ -113,3 +113,17 @@ def oracle_solve_sens(batch: Batch, opts: CuipmOpts, seed, adjoint=False, nthrea
 def ref_solve_sens(batch: Batch, opts: CuipmOpts, seed, adjoint=False, nthreads=1, sol0=None):
     lib = _load(REF_LIB)
     return _solve_sens(lib, lib.ref_solve_sens, batch, opts, seed, adjoint, nthreads, sol0)
+
+
+def ref_solve_xcond(batch: Batch, idxe0, cond_N: int, opts: CuipmOpts):
+    """The reference's complete QP path (equality elimination, partial condensing to cond_N stages, HPIPM, expansion) on
+    records of the FULL shape (x0 a stage-0 equality).  Returns (sol, info) with info['status'] the acados return value."""
+    lib = _load(REF_LIB)
+    nb = batch.nbatch
+    sol = batch.layout.new_sol(nb)
+    info = np.zeros(nb, dtype=INFO_DTYPE)
+    idx = (C.c_int * max(1, len(idxe0)))(*[int(i) for i in idxe0])
+    lib.ref_solve_xcond.restype = C.c_int
+    lib.ref_solve_xcond(C.byref(batch.shape.as_ctypes()), C.c_int(len(idxe0)), idx, C.c_int(cond_N), C.c_int(nb),
+                        C.c_void_p(batch.qp.ctypes.data), C.c_void_p(sol.ctypes.data), C.c_void_p(info.ctypes.data), C.byref(opts))
+    return sol, info

@@ -22,6 +22,7 @@
 
 #include "acados/ocp_qp/ocp_qp_common.h"
 #include "acados/ocp_qp/ocp_qp_hpipm.h"
+#include "acados/ocp_qp/ocp_qp_xcond_solver.h"
 #include "acados_c/ocp_qp_interface.h"
 #include "blasfeo/include/blasfeo_d_aux.h"
 #include "hpipm/include/hpipm_d_ocp_qp.h"
@@ -292,6 +293,82 @@ int ref_solve_sens(const cuipm_shape *sh, int nbatch, const double *qp, double *
         ocp_qp_out_free(sout);
         obj_free(o);
     }
+    oracle_layout_destroy(l);
+    return 0;
+}
+
+/* The reference's complete QP path (ocp_qp_solve -> ocp_qp_xcond_solve: stage-0 equality elimination, partial condensing to N2
+ * stages, HPIPM, expansion; acados/ocp_qp/ocp_qp_xcond_solver.c:529-590) on QP records of the FULL shape: stage 0 carries x_0,
+ * idxe0[0..nbxe0) are the positions (in stage 0's bound list) of the state bounds that are equalities.  sol: records of the full
+ * shape.  Single-threaded (one solver object), used to pin the host-side condensing of acados_b200/ocp_qp.py. */
+int ref_solve_xcond(const cuipm_shape *sh, int nbxe0, const int *idxe0, int N2, int nbatch, const double *qp, double *sol,
+                    cuipm_info *info, const cuipm_opts *co)
+{
+    cuipm_layout *l = oracle_layout_create(sh);
+    ocp_qp_solver_plan_t plan;
+    plan.qp_solver = PARTIAL_CONDENSING_HPIPM;
+    ocp_qp_xcond_solver_config *config = ocp_qp_xcond_solver_config_create(plan);
+    ocp_qp_xcond_solver_dims *dims = ocp_qp_xcond_solver_dims_create(config, sh->N);
+    for (int k = 0; k <= sh->N; k++)
+    {
+        int nbu = 0, nbx = 0;
+        for (int i = 0; i < sh->nb[k]; i++)
+            if (sh->idxb[k][i] < sh->nu[k]) nbu++; else nbx++;
+        int nx = sh->nx[k], nu = sh->nu[k], ng = sh->ng[k], ns = sh->ns[k];
+        config->dims_set(config, dims, k, "nx", &nx);
+        config->dims_set(config, dims, k, "nu", &nu);
+        config->dims_set(config, dims, k, "nbx", &nbx);
+        config->dims_set(config, dims, k, "nbu", &nbu);
+        config->dims_set(config, dims, k, "ng", &ng);
+        config->dims_set(config, dims, k, "ns", &ns);
+    }
+    config->dims_set(config, dims, 0, "nbxe", &nbxe0);
+    void *opts = ocp_qp_xcond_solver_opts_create(config, dims);
+    ocp_qp_xcond_solver_opts_set(config, opts, "cond_N", &N2);
+    int iter_max = co->iter_max, ws = co->warm_start;
+    double tg = co->res_g_max, tb = co->res_b_max, td = co->res_d_max, tm = co->res_m_max;
+    ocp_qp_xcond_solver_opts_set(config, opts, "iter_max", &iter_max);
+    ocp_qp_xcond_solver_opts_set(config, opts, "tol_stat", &tg);
+    ocp_qp_xcond_solver_opts_set(config, opts, "tol_eq", &tb);
+    ocp_qp_xcond_solver_opts_set(config, opts, "tol_ineq", &td);
+    ocp_qp_xcond_solver_opts_set(config, opts, "tol_comp", &tm);
+    ocp_qp_xcond_solver_opts_set(config, opts, "warm_start", &ws);
+    ocp_qp_solver *solver = ocp_qp_create(config, dims, opts);
+    ref_obj o;
+    memset(&o, 0, sizeof(o));
+    o.in = ocp_qp_in_create(dims->orig_dims);
+    o.out = ocp_qp_out_create(dims->orig_dims);
+    int *idxbxe = (int *) calloc(nbxe0 + 1, sizeof(int));
+    int nbu0 = 0;
+    for (int i = 0; i < sh->nb[0]; i++) nbu0 += sh->idxb[0][i] < sh->nu[0];
+    for (int e = 0; e < nbxe0; e++) idxbxe[e] = idxe0[e] - nbu0;      /* HPIPM counts within the state bounds */
+    for (int k = 0; k <= sh->N; k++)
+    {
+        if (sh->nb[k] > 0) d_ocp_qp_set_idxb(k, (int *) sh->idxb[k], o.in);
+        if (sh->nb[k] + sh->ng[k] > 0 && sh->ns[k] > 0) d_ocp_qp_set_idxs_rev(k, (int *) sh->idxs_rev[k], o.in);
+    }
+    if (nbxe0 > 0) d_ocp_qp_set_idxbxe(0, idxbxe, o.in);
+    for (int q = 0; q < nbatch; q++)
+    {
+        load_qp(&o, sh, l, qp + (size_t) q * l->qp_stride);
+        int st = ocp_qp_solve(solver, o.in, o.out);
+        store_sol(&o, sh, l, sol + (size_t) q * l->sol_stride);
+        if (info)
+        {
+            int it = 0;
+            config->qp_solver->memory_get(config->qp_solver, ((ocp_qp_xcond_solver_memory *) solver->mem)->solver_memory, "iter", &it);
+            memset(info + q, 0, sizeof(cuipm_info));
+            info[q].status = st;       /* acados return value (0 success, 2 max iter, 3 min step, ...) */
+            info[q].iter = it;
+        }
+    }
+    config->terminate(config, solver->mem, solver->work);
+    free(idxbxe);
+    ocp_qp_out_free(o.out); ocp_qp_in_free(o.in);
+    ocp_qp_solver_destroy(solver);
+    ocp_qp_xcond_solver_opts_free(opts);
+    ocp_qp_xcond_solver_dims_free(dims);
+    ocp_qp_xcond_solver_config_free(config);
     oracle_layout_destroy(l);
     return 0;
 }
