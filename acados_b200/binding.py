@@ -104,6 +104,15 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.cuipm_reduce_device.restype = ip
     lib.cuipm_restore_device.argtypes = [vp, ip, vp, vp, vp, C.c_double, C.c_double, vp]
     lib.cuipm_restore_device.restype = ip
+    lib.cuipm_condenser_create.argtypes = [vp, ip, ip]
+    lib.cuipm_condenser_create.restype = vp
+    lib.cuipm_condenser_destroy.argtypes = [vp]
+    lib.cuipm_condenser_condensed_shape.argtypes = [vp]
+    lib.cuipm_condenser_condensed_shape.restype = vp
+    lib.cuipm_condense_device.argtypes = [vp, ip, vp, vp, vp]
+    lib.cuipm_condense_device.restype = ip
+    lib.cuipm_expand_device.argtypes = [vp, ip, vp, vp, vp, vp]
+    lib.cuipm_expand_device.restype = ip
     lib.cuipm_set_tuning.argtypes = [vp, C.c_char_p, ip]
     lib.cuipm_set_tuning.restype = ip
     _lib = lib
@@ -230,6 +239,52 @@ class CuipmSolver:
         out = np.zeros(shape2[::-1])  # column-major (size1 x size2)
         self._check(self.lib.cuipm_get_ric(self.handle, iqp, field.encode(), stage, out.ctypes.data, shape2[0], shape2[1]))
         return out.T
+
+
+def _shape_from_c(ptr: int) -> Shape:
+    """Python copy of a ``const cuipm_shape *`` owned by a C object."""
+    class _CS(C.Structure):
+        _fields_ = [("N", C.c_int)] + [(n, C.POINTER(C.c_int)) for n in ("nx", "nu", "nb", "ng", "ns")] + \
+                   [("idxb", C.POINTER(C.POINTER(C.c_int))), ("idxs_rev", C.POINTER(C.POINTER(C.c_int)))]
+    cs = C.cast(ptr, C.POINTER(_CS)).contents
+    N = cs.N
+    g = lambda a: [int(a[k]) for k in range(N + 1)]
+    nx, nu, nb, ng, ns = g(cs.nx), g(cs.nu), g(cs.nb), g(cs.ng), g(cs.ns)
+    return Shape(N, nx, nu, nb, ng, ns, [[int(cs.idxb[k][i]) for i in range(nb[k])] for k in range(N + 1)],
+                 [[int(cs.idxs_rev[k][i]) for i in range(nb[k] + ng[k])] for k in range(N + 1)])
+
+
+class CuipmCondenser:
+    """Partial (block) condensing / expansion on the device (``cuipm_condenser_*``, include/cuipm.h)."""
+
+    def __init__(self, shape: Shape, cond_N: int, device: int = 0):
+        self.lib = load_library()
+        self.shape = shape
+        self._cshape = shape.as_ctypes()
+        self.handle = self.lib.cuipm_condenser_create(C.byref(self._cshape), cond_N, device)
+        if not self.handle:
+            raise RuntimeError("cuipm_condenser_create failed: " + self.lib.cuipm_last_error().decode())
+        self.condensed_shape = _shape_from_c(self.lib.cuipm_condenser_condensed_shape(self.handle))
+        self.layout, self.condensed_layout = Layout(shape), Layout(self.condensed_shape)
+
+    def condense(self, nbatch: int, d_qp: int, d_qp_cond: int, stream: int = 0):
+        if self.lib.cuipm_condense_device(self.handle, nbatch, d_qp, d_qp_cond, stream or None) != 0:
+            raise RuntimeError(self.lib.cuipm_last_error().decode())
+
+    def expand(self, nbatch: int, d_qp: int, d_sol_cond: int, d_sol: int, stream: int = 0):
+        if self.lib.cuipm_expand_device(self.handle, nbatch, d_qp, d_sol_cond, d_sol, stream or None) != 0:
+            raise RuntimeError(self.lib.cuipm_last_error().decode())
+
+    def close(self):
+        if self.handle:
+            self.lib.cuipm_condenser_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class CuipmReducer:

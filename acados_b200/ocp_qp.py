@@ -399,8 +399,14 @@ class OcpQpBatchSolver:
         self.device, self.device_reduce = device, device_reduce
         self.c_opts = self.opts.to_cuipm()
         self._reducer = None
+        self._dcond = None
         self._load(qps)
-        solve_shape = self._cond.cshape if self._cond is not None else (self._reducer.reduced_shape if self.device_reduce else self.packed.shape)
+        if self._dcond is not None:
+            solve_shape = self._dcond.condensed_shape
+        elif self._cond is not None:
+            solve_shape = self._cond.cshape
+        else:
+            solve_shape = self._reducer.reduced_shape if self.device_reduce else self.packed.shape
         self._solver = CuipmSolver(solve_shape, len(qps), device)
         self._sol = None
         self.info = None
@@ -411,21 +417,21 @@ class OcpQpBatchSolver:
         N = qps[0].N
         cond_N = self.opts.cond_N if self.opts.cond_N is not None else N
         self._cond = None
-        if cond_N < N:
-            # block condensing (acados_b200/condensing.py, the reference's ocp_qp_partial_condensing restated on the host,
-            # batch-vectorised): eliminate x0, condense N -> cond_N stages, solve the condensed QPs on the GPU, expand
-            from .condensing import BlockCondenser
-            self.device_reduce = False
-            self.packed = PackedBatch(qps)
-            self._cond = BlockCondenser(self.packed.shape, cond_N)
-            self._cqp = self._cond.condense(self.packed.qp)
-        elif self.device_reduce:
-            from .binding import CuipmReducer
+        if self.device_reduce:
+            # records travel as posed; elimination, block condensing, expansion and restore all run on the GPU
+            from .binding import CuipmCondenser, CuipmReducer
             self.packed = PackedBatch(qps, eliminate=False)
             if self._reducer is None:
                 self._reducer = CuipmReducer(self.packed.shape, [int(i) for i in qps[0].idxe[0]], self.device)
+            if cond_N < N and self._dcond is None:
+                self._dcond = CuipmCondenser(self._reducer.reduced_shape, cond_N, self.device)
         else:
             self.packed = PackedBatch(qps)
+            if cond_N < N:
+                # the same on the host (acados_b200/condensing.py, numpy)
+                from .condensing import BlockCondenser
+                self._cond = BlockCondenser(self.packed.shape, cond_N)
+                self._cqp = self._cond.condense(self.packed.qp)
 
     @property
     def N(self) -> int:
@@ -447,20 +453,26 @@ class OcpQpBatchSolver:
         else:
             import torch   # device buffers and copies only
             from .binding import INFO_DTYPE
-            nb, red, o = self.packed.nbatch, self._reducer, self.c_opts
+            nb, red, dc, o = self.packed.nbatch, self._reducer, self._dcond, self.c_opts
             dev = torch.device("cuda", self.device)
             st = self._solver.lib.cuipm_stream(self._solver.handle)
+            slay = dc.condensed_layout if dc is not None else red.reduced_layout          # layout the solver works on
             d_full = torch.from_numpy(self.packed.qp).to(dev)
             d_red = torch.empty((nb, red.reduced_layout.qp_stride), dtype=torch.float64, device=dev)
-            d_sol = torch.zeros((nb, red.reduced_layout.sol_stride), dtype=torch.float64, device=dev) if warm is None \
-                else torch.from_numpy(warm).to(dev)
+            d_qp = d_red if dc is None else torch.empty((nb, slay.qp_stride), dtype=torch.float64, device=dev)
+            d_sol = torch.zeros((nb, slay.sol_stride), dtype=torch.float64, device=dev) if warm is None else torch.from_numpy(warm).to(dev)
             d_info = torch.zeros(nb * INFO_DTYPE.itemsize, dtype=torch.uint8, device=dev)
             d_stat = torch.zeros((nb, o.stat_max + 1, STAT_M), dtype=torch.float64, device=dev)
+            d_sol_red = d_sol if dc is None else torch.empty((nb, red.reduced_layout.sol_stride), dtype=torch.float64, device=dev)
             d_sol_full = torch.empty((nb, red.full_layout.sol_stride), dtype=torch.float64, device=dev)
             torch.cuda.synchronize(dev)
             red.reduce(nb, d_full.data_ptr(), d_red.data_ptr(), st)
-            self._solver.solve_device(nb, d_red.data_ptr(), d_sol.data_ptr(), d_info.data_ptr(), o, sync=False, d_stat=d_stat.data_ptr())
-            red.restore(nb, d_full.data_ptr(), d_sol.data_ptr(), d_sol_full.data_ptr(), o.lam_min, o.t_min, st)
+            if dc is not None:
+                dc.condense(nb, d_red.data_ptr(), d_qp.data_ptr(), st)
+            self._solver.solve_device(nb, d_qp.data_ptr(), d_sol.data_ptr(), d_info.data_ptr(), o, sync=False, d_stat=d_stat.data_ptr())
+            if dc is not None:
+                dc.expand(nb, d_red.data_ptr(), d_sol.data_ptr(), d_sol_red.data_ptr(), st)
+            red.restore(nb, d_full.data_ptr(), d_sol_red.data_ptr(), d_sol_full.data_ptr(), o.lam_min, o.t_min, st)
             self._solver.wait()
             self._sol = d_sol.cpu().numpy()
             self.info = np.frombuffer(d_info.cpu().numpy().tobytes(), dtype=INFO_DTYPE).copy()
@@ -488,6 +500,8 @@ class OcpQpBatchSolver:
         self._solver.close()
         if self._reducer is not None:
             self._reducer.close()
+        if self._dcond is not None:
+            self._dcond.close()
 
 
 class OcpQpSolver:

@@ -223,6 +223,21 @@ int cuipm_reduce_device(cuipm_reducer *r, int nbatch, const double *d_qp_full, d
 int cuipm_restore_device(cuipm_reducer *r, int nbatch, const double *d_qp_full, const double *d_sol_red, double *d_sol_full,
                          double lam_min, double t_min, void *stream);
 
+/* ---- partial (block) condensing on the device -----------------------------------------------------------------------
+ * Reference: ocp_qp_partial_condensing (acados/ocp_qp/ocp_qp_partial_condensing.c:523-689) -> d_part_cond_qp_cond /
+ * d_part_cond_qp_expand_sol (external/hpipm/cond/x_part_cond.c:410-866), for cond_N < N.  `shape` is the shape the solver
+ * would otherwise be created with (after the stage-0 equality elimination); the N stages are grouped into cond_N blocks
+ * (sizes as d_part_cond_qp_compute_block_size, the terminal stage stays), cuipm_condense_device maps QP records of `shape`
+ * to QP records of the condensed shape (create the cuipm_solver with that one), cuipm_expand_device maps solution records
+ * of the condensed QPs back (inner states from the dynamics, inner multipliers from stationarity).  Device pointers;
+ * stream is a cudaStream_t (may be NULL). */
+typedef struct cuipm_condenser cuipm_condenser;
+cuipm_condenser *cuipm_condenser_create(const cuipm_shape *shape, int cond_N, int device);
+void cuipm_condenser_destroy(cuipm_condenser *c);
+const cuipm_shape *cuipm_condenser_condensed_shape(const cuipm_condenser *c);     /* owned by c */
+int cuipm_condense_device(cuipm_condenser *c, int nbatch, const double *d_qp, double *d_qp_cond, void *stream);
+int cuipm_expand_device(cuipm_condenser *c, int nbatch, const double *d_qp, const double *d_sol_cond, double *d_sol, void *stream);
+
 /* Riccati quantities of the last factorisation (reference: ocp_qp_hpipm_solver_get, ocp_qp_hpipm.c:417-478).
  * field in {"P","p","K","k","Lr"}; copies column-major data of QP `iqp`, stage `stage` into `value`. */
 int cuipm_get_ric(cuipm_solver *s, int iqp, const char *field, int stage, double *value, int size1, int size2);

@@ -127,3 +127,30 @@ def ref_solve_xcond(batch: Batch, idxe0, cond_N: int, opts: CuipmOpts):
     lib.ref_solve_xcond(C.byref(batch.shape.as_ctypes()), C.c_int(len(idxe0)), idx, C.c_int(cond_N), C.c_int(nb),
                         C.c_void_p(batch.qp.ctypes.data), C.c_void_p(sol.ctypes.data), C.c_void_p(info.ctypes.data), C.byref(opts))
     return sol, info
+
+
+EMUL_LIB = os.path.join(_HERE, "libcondense_emul.so")
+
+
+def emul_condense(batch: Batch, cond_N: int, nthreads: int = 128):
+    """The product's block-condensing kernel body run sequentially on the host (oracle/condense_emul.cpp): returns the
+    condensed records.  ``nthreads`` is the emulated CTA size (results must not depend on it)."""
+    lib = _load(EMUL_LIB)
+    qs, ss = C.c_size_t(0), C.c_size_t(0)
+    if not lib.emul_condensed_strides(C.byref(batch.shape.as_ctypes()), C.c_int(cond_N), C.byref(qs), C.byref(ss)):
+        raise ValueError("bad cond_N")
+    out = np.zeros((batch.nbatch, qs.value))
+    rc = lib.emul_condense(C.byref(batch.shape.as_ctypes()), C.c_int(cond_N), C.c_int(batch.nbatch), C.c_void_p(batch.qp.ctypes.data),
+                           C.c_void_p(out.ctypes.data), C.c_int(nthreads))
+    assert rc == 0
+    return out
+
+
+def emul_expand(batch: Batch, cond_N: int, sol2: np.ndarray, nthreads: int = 128):
+    lib = _load(EMUL_LIB)
+    sol2 = np.ascontiguousarray(sol2)
+    out = batch.layout.new_sol(batch.nbatch)
+    rc = lib.emul_expand(C.byref(batch.shape.as_ctypes()), C.c_int(cond_N), C.c_int(batch.nbatch), C.c_void_p(batch.qp.ctypes.data),
+                         C.c_void_p(sol2.ctypes.data), C.c_void_p(out.ctypes.data), C.c_int(nthreads))
+    assert rc == 0
+    return out
