@@ -101,6 +101,20 @@ def test_create_without_gpu_fails_loudly(built):
         CuipmSolver(P.mass_spring(1).shape, 1)
 
 
+def test_reducer_and_condenser_without_gpu_fail_loudly(built):
+    """The device-side elimination / condensing objects need a CUDA device too: no host fallback behind the C ABI."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from acados_b200.binding import CuipmCondenser, CuipmReducer
+    sh = P.chain_mass(1, N=6).shape
+    with pytest.raises(RuntimeError, match="CUDA"):
+        CuipmCondenser(sh, 3)
+    full = P.random_shape(4, 3, 2, nbx=3, x0_eliminated=False)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        CuipmReducer(full, [full.nu[0]])
+
+
 def test_problem_generators_are_deterministic_and_well_formed():
     a, b = P.chain_mass(3, N=5, seed=7), P.chain_mass(3, N=5, seed=7)
     assert np.array_equal(a.qp, b.qp)
