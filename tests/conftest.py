@@ -16,7 +16,7 @@ def pytest_configure(config):
 def built():
     """Build (or reuse) the native libraries once per session."""
     import __graft_entry__ as g
-    if not os.path.exists(os.path.join(ROOT, "acados_b200", "csrc", "libcuipm.so")) or \
-            not os.path.exists(os.path.join(ROOT, "oracle", "liboracle_ipm.so")):
+    need = [("acados_b200", "csrc", "libcuipm.so"), ("oracle", "liboracle_ipm.so"), ("oracle", "libcondense_emul.so")]
+    if not all(os.path.exists(os.path.join(ROOT, *p)) for p in need):
         g.build()
     return True
