@@ -15,6 +15,7 @@
 #include "cuipm.h"
 #include "cuipm_device.h"
 #include "cuipm_internal.h"
+#include "cuipm_plan.h"
 
 using namespace cuipm;
 
@@ -41,6 +42,12 @@ struct cuipm_solver
     int pending = 0;                         // an asynchronous host solve has been enqueued and not waited for
     float last_ms = 0.f;
     cuipm_opts last_opts{};
+    // throughput kernel (cuipm_fast.cu)
+    bool fast_ok = false;
+    int use_fast = 1;                        // tuning key "fast"
+    int fast_qpw = 1;
+    FastArgs F{};
+    int *d_redo_list = nullptr, *d_redo_count = nullptr;
 };
 
 #define CK(call)                                                                                        \
@@ -53,102 +60,53 @@ struct cuipm_solver
         }                                                                                               \
     } while (0)
 
-static inline unsigned ev2u(size_t n) { return (unsigned) ((n + 1) & ~(size_t) 1); }
-
 static int build_desc(cuipm_solver *s, const cuipm_shape *sh)
 {
-    const int N = sh->N;
-    const cuipm_layout *l = s->layout;
     std::vector<int> ipool;
-    s->sd_host.assign(N + 1, StageDesc{});
-    ProbDesc &P = s->P;
-    P = ProbDesc{};
-    P.N = N;
-    size_t w = 0;
-    for (int k = 0; k <= N; k++)
-    {
-        StageDesc &d = s->sd_host[k];
-        d.nx = sh->nx[k]; d.nu = sh->nu[k]; d.n = d.nx + d.nu; d.nb = sh->nb[k]; d.ng = sh->ng[k]; d.ns = sh->ns[k];
-        d.nbg = d.nb + d.ng; d.nc = 2 * (d.nbg + d.ns);
-        d.nx1 = k < N ? sh->nx[k + 1] : 0; d.nu1 = k < N ? sh->nu[k + 1] : 0; d.n1 = d.nx1 + d.nu1;
-        if (d.nx < 0 || d.nu < 0 || d.nb < 0 || d.ng < 0 || d.ns < 0) { set_error("negative dimension"); return CUIPM_ERR_INVALID; }
-        if (d.ns > 0 && !sh->idxs_rev) { set_error("ns>0 needs idxs_rev"); return CUIPM_ERR_INVALID; }
-        d.idx_off = (int) ipool.size();
-        d.dup_idxb = 0;
-        for (int i = 0; i < d.nb; i++)
-        {
-            const int ix = sh->idxb[k][i];
-            if (ix < 0 || ix >= d.n) { set_error("idxb out of range"); return CUIPM_ERR_INVALID; }
-            for (int j = 0; j < i; j++) d.dup_idxb |= sh->idxb[k][j] == ix;
-            ipool.push_back(ix);
-        }
-        for (int i = 0; i < d.nbg; i++)
-        {
-            const int r = (d.ns > 0 && sh->idxs_rev) ? sh->idxs_rev[k][i] : -1;
-            if (r < -1 || r >= d.ns) { set_error("idxs_rev out of range"); return CUIPM_ERR_INVALID; }
-            ipool.push_back(r);
-        }
-        d.q_BAt = (unsigned) l->off_BAt[k]; d.q_RSQ = (unsigned) l->off_RSQ[k]; d.q_DCt = (unsigned) l->off_DCt[k];
-        d.q_b = (unsigned) l->off_b[k]; d.q_rq = (unsigned) l->off_rq[k]; d.q_d = (unsigned) l->off_d[k];
-        d.q_dmask = (unsigned) l->off_dmask[k]; d.q_Z = (unsigned) l->off_Z[k]; d.q_z = (unsigned) l->off_z[k];
-        d.sol = VOff{(unsigned) l->off_ux[k], (unsigned) l->off_pi[k], (unsigned) l->off_lam[k], (unsigned) l->off_t[k]};
-        const size_t nvs = (size_t) d.n + 2 * d.ns;
-        auto take = [&](size_t n) { unsigned o = (unsigned) w; w += ev2u(n); return o; };
-        // factor first (read by two sweeps per solve), then the vectors
-        d.q_stage = (unsigned) l->qp_stage[k];
-        d.q_stage_bytes = (unsigned) ((l->qp_stage[k + 1] - l->qp_stage[k]) * sizeof(double));
-        d.w_fac = (unsigned) w;
-        d.w_L = take((size_t) d.n * d.n); d.w_Linv = take(d.n); d.w_lrow = take(d.n); d.w_Pb = take(d.nx1); d.w_Zsi = take(2 * d.ns);
-        d.w_fac_bytes = (unsigned) ((w - d.w_fac) * sizeof(double));
-        d.w_vec = (unsigned) w;
-        d.step = VOff{take(nvs), take(d.nx1), take(d.nc), take(d.nc)};
-        d.res = ROff{take(nvs), take(d.nx1), take(d.nc), take(d.nc)};
-        d.w_rmb = take(d.nc);
-        d.ires = ROff{take(nvs), take(d.nx1), take(d.nc), take(d.nc)};
-        d.itref = VOff{take(nvs), take(d.nx1), take(d.nc), take(d.nc)};
-        d.w_vec_bytes = (unsigned) ((w - d.w_vec) * sizeof(double));
-        P.nmax = std::max(P.nmax, d.n); P.nxmax = std::max(P.nxmax, std::max(d.nx, d.nx1)); P.ngmax = std::max(P.ngmax, d.ng);
-        P.nsmax = std::max(P.nsmax, d.ns); P.nbgmax = std::max(P.nbgmax, d.nbg); P.ncmax = std::max(P.ncmax, d.nc);
-        P.nvsmax = std::max(P.nvsmax, (int) nvs);
-        P.nct += d.nc;
-    }
-    // uniform interior stages? (stages 1..N-1 share (nx, nu); stage N has the same nx) -> compile-time specialised sweeps
-    P.mid_nx = P.mid_nu = 0;
-    if (N >= 3)
-    {
-        bool uni = true;
-        for (int k = 1; k <= N - 1; k++) uni = uni && sh->nx[k] == sh->nx[1] && sh->nu[k] == sh->nu[1];
-        uni = uni && sh->nx[N] == sh->nx[1];
-        if (uni) { P.mid_nx = sh->nx[1]; P.mid_nu = sh->nu[1]; }
-    }
-    P.w_lq = (unsigned) w;
-    w += ev2u((size_t) P.nmax * (P.nbgmax + P.nxmax));
-    P.w_bkp = (unsigned) w;
-    w += ev2u(l->sol_stride);
-    if (w >= (size_t) 1 << 32 || l->qp_stride >= (size_t) 1 << 32) { set_error("QP record too large for 32-bit offsets"); return CUIPM_ERR_TOO_LARGE; }
-    P.qp_stride = l->qp_stride; P.sol_stride = l->sol_stride; P.work_stride = w;
-    auto e = [](int n) { return (n + 1) & ~1; };
-    // leading dimensions used on chip: nmax|1 (odd, conflict-free row/column access) or even(nmax+1) (factorisation:
-    // rows incl. the gradient row, 16-byte aligned column starts); both <= nmax+2
-    P.sm_M = e((P.nmax + 2) * P.nmax + 8);                       // factor of the stage being eliminated (rows incl. gradient row)
-    P.sm_A = 0;                                                  // (matrices of the substitution / residual sweeps are streamed from global memory)
-    P.sm_AL = e(std::max((P.nmax + 2) * (P.nxmax + P.ngmax), e(P.nmax) + e(P.nxmax) + 4 * e(P.ncmax)) + 8);   // [A; b'] -> A L_xx in place (+ general-constraint columns); staging area of the substitution sweeps
-    P.sm_C = P.ngmax > 0 ? 2 * e((P.nmax + 2) * P.ngmax) + 8 : 0;
-    {
-        const int nvs = e(P.nvsmax), nx = e(P.nxmax), nc = e(P.ncmax), nbg = e(P.nbgmax), n = e(P.nmax + 1), ns2 = e(2 * P.nsmax);
-        const int v_res = 2 * nvs + 3 * nx + 4 * nc + 2 * nbg;
-        const int v_fwd = 2 * nvs + 5 * nx + 4 * nc + 2 * ns2 + nbg;
-        const int v_fact = 2 * nc + 2 * nbg + 3 * n + 2 * ns2 + 16;
-        const int v_slv = nvs + 2 * nc + 2 * nbg + 2 * ns2 + 3 * nx;
-        const int v_init = nvs + nc + e(P.ngmax);
-        P.sm_V = std::max(std::max(std::max(v_res, v_fwd), std::max(v_fact, v_slv)), v_init) + 8;
-    }
-    P.sm_total = P.sm_M + P.sm_A + P.sm_AL + P.sm_C + P.sm_V;
-    if (smem_bytes(P) > 227 * 1024) { set_error("stage dimensions need more than 227 KB of shared memory"); return CUIPM_ERR_TOO_LARGE; }
+    std::string err;
+    int rc = build_plan(sh, s->layout, s->sd_host, ipool, s->P, err);
+    if (rc != CUIPM_OK) { set_error(err); return rc; }
+    const int N = sh->N;
     CK(cudaMalloc(&s->d_sd, sizeof(StageDesc) * (N + 1)));
     CK(cudaMemcpy(s->d_sd, s->sd_host.data(), sizeof(StageDesc) * (N + 1), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&s->d_ipool, sizeof(int) * (ipool.size() + 1)));
     if (!ipool.empty()) CK(cudaMemcpy(s->d_ipool, ipool.data(), sizeof(int) * ipool.size(), cudaMemcpyHostToDevice));
+    // throughput kernel: eligible shape with a compiled instance
+    s->fast_ok = fast_plan(s->sd_host, s->P, s->F) && fast_available(s->F.s1.nx, s->F.s1.nu, s->F, &s->fast_qpw);
+    if (s->fast_ok)
+    {
+        CK(cudaMalloc(&s->d_redo_list, sizeof(int) * (size_t) s->max_batch));
+        CK(cudaMalloc(&s->d_redo_count, sizeof(int) * cuipm_solver::kPipe));
+        CK(cudaMemset(s->d_redo_count, 0, sizeof(int) * cuipm_solver::kPipe));
+    }
+    return CUIPM_OK;
+}
+
+// One batch (or one chunk of it) on `stream`: the throughput kernel where the shape and the options allow it, then the
+// generic kernel over the QPs it handed back (cold paths); otherwise the generic kernel over everything.
+// slot selects the hand-back counter (chunks run concurrently on different streams).
+static int launch_batch(cuipm_solver *s, const LaunchArgs &a0, int slot, size_t lo, cudaStream_t stream, int *launches)
+{
+    LaunchArgs a = a0;
+    a.redo_list = nullptr;
+    a.redo_count = nullptr;
+    const cuipm_opts &o = a.o;
+    if (s->fast_ok && s->use_fast && o.lq_fact <= 1)
+    {
+        FastArgs F = s->F;
+        F.nbatch = a.nbatch; F.ipool = a.ipool; F.qp = a.qp; F.sol = a.sol; F.work = a.work; F.info = a.info; F.stat = a.stat;
+        F.redo_list = s->d_redo_list + lo; F.redo_count = s->d_redo_count + slot; F.o = o;
+        cudaError_t e = cudaMemsetAsync(F.redo_count, 0, sizeof(int), stream);
+        if (e != cudaSuccess) { set_error(std::string("cudaMemsetAsync: ") + cudaGetErrorString(e)); return CUIPM_ERR_CUDA; }
+        int rc = launch_fast(F, (void *) stream);
+        if (rc != 0) { set_error(std::string("kernel launch (throughput kernel): ") + cudaGetErrorString((cudaError_t) rc)); return CUIPM_ERR_CUDA; }
+        (*launches)++;
+        a.redo_list = F.redo_list;
+        a.redo_count = F.redo_count;
+    }
+    int rc = launch_solve(a, s->warps, (void *) stream);
+    if (rc != 0) { set_error(std::string("kernel launch: ") + cudaGetErrorString((cudaError_t) rc)); return CUIPM_ERR_CUDA; }
+    (*launches)++;
     return CUIPM_OK;
 }
 
@@ -201,6 +159,7 @@ extern "C" void cuipm_destroy(cuipm_solver *s)
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->d_sd); cudaFree(s->d_ipool); cudaFree(s->d_qp); cudaFree(s->d_sol); cudaFree(s->d_work);
     cudaFree(s->d_stat); cudaFree(s->d_info); cudaFree(s->d_seed); cudaFree(s->d_sens);
+    cudaFree(s->d_redo_list); cudaFree(s->d_redo_count);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     for (int i = 0; i < cuipm_solver::kPipe; i++)
@@ -235,6 +194,11 @@ extern "C" int cuipm_set_tuning(cuipm_solver *s, const char *key, int value)
         s->npipe = value;
         return CUIPM_OK;
     }
+    if (!std::strcmp(key, "fast"))
+    {
+        s->use_fast = value != 0;
+        return CUIPM_OK;
+    }
     set_error("unknown tuning key");
     return CUIPM_ERR_INVALID;
 }
@@ -257,9 +221,8 @@ extern "C" int cuipm_solve_device(cuipm_solver *s, int nbatch, const double *d_q
     a.stat = d_stat; a.o = *opts; a.nbatch = nbatch; a.seed = nullptr; a.sens = nullptr; a.adjoint = 0;
     s->last_opts = *opts;
     CK(cudaEventRecord(s->ev0, s->stream));
-    int e = launch_solve(a, s->warps, (void *) s->stream);
-    if (e != 0) { set_error(std::string("kernel launch: ") + cudaGetErrorString((cudaError_t) e)); return CUIPM_ERR_CUDA; }
-    s->last_launches = 1;
+    rc = launch_batch(s, a, 0, 0, s->stream, &s->last_launches);
+    if (rc != CUIPM_OK) return rc;
     CK(cudaEventRecord(s->ev1, s->stream));
     if (sync)
     {
@@ -296,6 +259,7 @@ extern "C" int cuipm_solve_host_async(cuipm_solver *s, int nbatch, const double 
     // Chunked pipeline: chunk c is copied in, solved and copied out on its own stream, so the H2D copy of the next chunk
     // (the batch is ~0.4 MB per QP) overlaps the solve of the previous ones; kernels of different chunks share the SMs.
     const int nchunk = nbatch >= 512 ? s->npipe : 1;
+    int nlaunch = 0;
     const int per = (nbatch + nchunk - 1) / nchunk;
     CK(cudaEventRecord(s->ev0, s->stream));
     for (int c = 0; c < nchunk; c++)
@@ -313,8 +277,8 @@ extern "C" int cuipm_solve_host_async(cuipm_solver *s, int nbatch, const double 
         a.work = s->d_work + s->P.work_stride * (size_t) lo; a.info = s->d_info + lo;
         a.stat = stat ? s->d_stat + (size_t) lo * CUIPM_STAT_M * (opts->stat_max + 1) : nullptr;
         a.o = *opts; a.nbatch = n; a.seed = nullptr; a.sens = nullptr; a.adjoint = 0;
-        int e = launch_solve(a, s->warps, (void *) st);
-        if (e != 0) { set_error(std::string("kernel launch: ") + cudaGetErrorString((cudaError_t) e)); return CUIPM_ERR_CUDA; }
+        rc = launch_batch(s, a, c, (size_t) lo, st, &nlaunch);
+        if (rc != CUIPM_OK) return rc;
         CK(cudaMemcpyAsync(sol + so, s->d_sol + so, sizeof(double) * s->P.sol_stride * n, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(info + lo, s->d_info + lo, sizeof(cuipm_info) * n, cudaMemcpyDeviceToHost, st));
         if (stat)
@@ -323,7 +287,7 @@ extern "C" int cuipm_solve_host_async(cuipm_solver *s, int nbatch, const double 
         CK(cudaEventRecord(s->pipe_done[c], st));
         CK(cudaStreamWaitEvent(s->stream, s->pipe_done[c], 0));
     }
-    s->last_launches = nchunk;
+    s->last_launches = nlaunch;
     s->last_opts = *opts;
     CK(cudaEventRecord(s->ev1, s->stream));
     s->pending = 1;
@@ -367,6 +331,7 @@ extern "C" int cuipm_sens_device(cuipm_solver *s, int nbatch, const double *d_qp
     LaunchArgs a;
     a.P = s->P; a.sd = s->d_sd; a.ipool = s->d_ipool; a.qp = d_qp; a.sol = nullptr; a.work = s->d_work; a.info = nullptr;
     a.stat = nullptr; a.o = *opts; a.nbatch = nbatch; a.seed = d_seed; a.sens = d_sens; a.adjoint = adjoint != 0;
+    a.redo_list = nullptr; a.redo_count = nullptr;
     CK(cudaEventRecord(s->ev0, s->stream));
     int e = launch_sens(a, s->warps, (void *) s->stream);
     if (e != 0) { set_error(std::string("kernel launch: ") + cudaGetErrorString((cudaError_t) e)); return CUIPM_ERR_CUDA; }

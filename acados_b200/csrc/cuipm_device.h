@@ -62,10 +62,46 @@ struct LaunchArgs
     const double *seed;
     double *sens;
     int adjoint;
+    // second pass behind the throughput kernel: solve only the QPs it handed back (indices redo_list[0 .. *redo_count));
+    // both null for a plain launch over the whole batch
+    const int *redo_list;
+    const int *redo_count;
 };
+
+// Arguments of the throughput kernel (cuipm_fast.cu): shapes whose interior stages are uniform need three stage
+// descriptors only -- stage 0, stage 1 (stage k = stage 1 shifted by (k-1) strides) and stage N -- which travel as
+// kernel parameters (constant bank), so that every array offset is an immediate operand.
+struct FastArgs
+{
+    int N, nbatch, nct;
+    int nce, nbe, ns2e, nve;       // even-rounded maxima over the stages: constraints, bounds, 2*slacks, nu+nx+2*ns
+    int is;                        // index-pool stride of the interior stages
+    unsigned qs, ss, ws;           // strides (doubles) of an interior stage in the QP / solution / work record
+    unsigned w_bkp;                // work record: lam, t of the iterate of the last factorisation (solution layout)
+    int vsize;                     // doubles of the per-QP vector pool in shared memory
+    int gstride;                   // doubles of shared memory per QP
+    size_t qp_stride, sol_stride, work_stride;
+    StageDesc s0, s1, sN;
+    const int *ipool;
+    const double *qp;
+    double *sol;
+    double *work;
+    cuipm_info *info;
+    double *stat;                  // may be null
+    int *redo_list;                // QPs that need a cold path (LQ refactorisation, iterative refinement, no active constraint):
+    int *redo_count;               //   handed to the generic kernel, which solves them from scratch
+    cuipm_opts o;
+};
+
+// status value the throughput kernel leaves in cuipm_info::status of a QP it hands back (never seen by callers)
+#define CUIPM_FAST_REDO 100
 
 // launches the solve kernel with `warps` warps per QP on `stream`; returns cudaError_t as int
 int launch_solve(const LaunchArgs &a, int warps, void *stream);
+// throughput path: true if a kernel instance exists for interior (nx, nu); fills the shared-memory figures of F
+bool fast_available(int nx, int nu, FastArgs &F, int *qp_per_warp);
+// launches the throughput kernel for F on `stream`; returns cudaError_t as int
+int launch_fast(const FastArgs &F, void *stream);
 // launches the sensitivity kernel (one substitution with the factorisation the last solve left in the work records)
 int launch_sens(const LaunchArgs &a, int warps, void *stream);
 // dynamic shared memory (bytes) the kernel needs for P

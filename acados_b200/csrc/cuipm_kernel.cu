@@ -1575,6 +1575,22 @@ struct Ker
         sync();
     }
 
+    // the throughput kernel keeps the caller's pi, lam, t of a warm start in the refinement vectors before it touches them
+    __device__ __noinline__ void restore_warm_start()
+    {
+        for (int k = 0; k <= CX.P.N; k++)
+        {
+            const StageDesc s = CX.SD[k];
+            for (int i = tid; i < s.nx1; i += NT) (CX.sol + s.sol.pi)[i] = (CX.wk + s.itref.pi)[i];
+            for (int i = tid; i < s.nc; i += NT)
+            {
+                (CX.sol + s.sol.lam)[i] = (CX.wk + s.itref.lam)[i];
+                (CX.sol + s.sol.t)[i] = (CX.wk + s.itref.t)[i];
+            }
+        }
+        sync();
+    }
+
     // OCP_QP_INIT_VAR, var_init_scheme 1 (x_ocp_qp_ipm.c:1611-1760,1884-2022)
     __device__ __noinline__ void init_var()
     {
@@ -1944,8 +1960,11 @@ __global__ void __launch_bounds__(32 * W, (W == 1 ? CUIPM_MINB : (W == 2 ? 8 : 4
         CX.o = a.o;
     }
     Ker<W, SNX, SNU> K;
-    for (int q = blockIdx.x; q < a.nbatch; q += gridDim.x)
+    // second pass behind the throughput kernel: only the QPs it handed back
+    const int nq = a.redo_count ? *a.redo_count : a.nbatch;
+    for (int i = blockIdx.x; i < nq; i += gridDim.x)
     {
+        const int q = a.redo_list ? a.redo_list[i] : i;
         if (threadIdx.x == 0)
         {
             CX.qp = a.qp + (size_t) q * a.P.qp_stride;
@@ -1953,6 +1972,7 @@ __global__ void __launch_bounds__(32 * W, (W == 1 ? CUIPM_MINB : (W == 2 ? 8 : 4
             CX.wk = a.work + (size_t) q * a.P.work_stride;
         }
         K.sync();
+        if (a.redo_list && a.o.warm_start >= 2) K.restore_warm_start();
         K.solve(a.info + q, a.stat ? a.stat + (size_t) q * CUIPM_STAT_M * (a.o.stat_max + 1) : nullptr);
         K.sync();
     }
@@ -1996,7 +2016,9 @@ static cudaError_t launch_one(const LaunchArgs &a, size_t smem, cudaStream_t str
 {
     cudaError_t err = cudaFuncSetAttribute(cuipm_solve_kernel<W, SNX, SNU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (err != cudaSuccess) return err;
-    cuipm_solve_kernel<W, SNX, SNU><<<a.nbatch, 32 * W, smem, stream>>>(a);
+    // behind the throughput kernel only a few QPs are left: a small grid whose blocks walk the hand-back list
+    const int grid = a.redo_list ? (a.nbatch < 1184 ? a.nbatch : 1184) : a.nbatch;
+    cuipm_solve_kernel<W, SNX, SNU><<<grid, 32 * W, smem, stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,100 @@
+// fast_emul.cpp -- TEST INFRASTRUCTURE ONLY: runs the body of the product's throughput kernel
+// (acados_b200/csrc/cuipm_fast_core.h) on a host emulation of a warp (simt_emul.h), so that the CPU test-suite can
+// compare the kernel's arithmetic, index maps and barrier placement with the oracle on a machine without a GPU
+// (tests/test_fast_emul.py).  The GPU suite then confirms the same body as compiled by nvcc.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "simt_emul.h"
+
+#define FK_DEV inline
+static inline int fk_lane() { return simt::lane(); }
+static inline void fk_sync() { simt::sync(); }
+static inline double fk_shfl_xor(double v, int m) { return simt::shfl(v, simt::lane() ^ m); }
+static inline int fk_shfl_xor_i(int v, int m) { return simt::shfl_i(v, simt::lane() ^ m); }
+static inline bool fk_any(bool p) { return simt::ballot(p) != 0u; }
+static inline void fk_cp16(double *dst, const double *src)
+{
+    if (((size_t) dst & 15) || ((size_t) src & 15)) { std::fprintf(stderr, "fast_emul: misaligned 16-byte copy\n"); std::abort(); }
+    simt::cp_async(dst, src, 16);
+}
+static inline void fk_cp8(double *dst, const double *src) { simt::cp_async(dst, src, 8); }
+static inline void fk_cp_wait() { simt::cp_wait(); }
+static inline double fk_ldg(const double *p) { return *p; }
+static inline double fk_rsqrt(double x) { return 1.0 / std::sqrt(x); }
+static inline int fk_atomic_inc(int *p) { return (*p)++; }
+using std::fabs;
+using std::fmax;
+using std::fmin;
+using std::sqrt;
+
+#include "cuipm_fast_core.h"
+#include "cuipm_plan.h"
+
+namespace {
+
+template <int NX, int NU, int G>
+int run(cuipm::FastArgs F, int order)
+{
+    using K = cuipm::fastk::Ker<NX, NU, G>;
+    F.vsize = cuipm::fastk::vector_pool_doubles(NX, NX + NU, F.nce, F.nbe, F.ns2e, F.nve);
+    int gs = K::MATS + F.vsize;
+    while (gs % 16 != 4) gs++;
+    F.gstride = gs;
+    std::vector<double> smem((size_t) gs * K::QPW + 64);
+    // 16-byte aligned base
+    double *base = smem.data();
+    while ((size_t) base & 15) base++;
+    const int nwarp = (F.nbatch + K::QPW - 1) / K::QPW;
+    for (int w = 0; w < nwarp; w++)
+    {
+        for (double &x : smem) x = std::nan("");      // uninitialised shared memory
+        simt::run_warp([&]() {
+            K k(F, base);
+            int q = w * K::QPW + k.gq;
+            const bool valid = q < F.nbatch;
+            if (!valid) q = F.nbatch - 1;
+            k.solve(q, valid);
+        }, order);
+    }
+    return 0;
+}
+
+}  // namespace
+
+// Solves nbatch QPs of `shape` (records in the layout of cuipm_layout_create) with the throughput kernel body; QPs the
+// kernel hands back are listed in redo[0..*nredo) and keep status CUIPM_FAST_REDO.  g = lanes per QP.
+// Returns 0, -1 if the shape is not eligible, -2 if no instance for (nx, nu, g) is compiled in.
+extern "C" int fast_emul_solve(const cuipm_shape *sh, int nbatch, const double *qp, double *sol, cuipm_info *info, double *stat,
+                               const cuipm_opts *opts, int g, int order, int *redo, int *nredo)
+{
+    cuipm_layout *l = cuipm_layout_create(sh);
+    std::vector<cuipm::StageDesc> sd;
+    std::vector<int> ipool;
+    cuipm::ProbDesc P;
+    std::string err;
+    if (cuipm::build_plan(sh, l, sd, ipool, P, err) != CUIPM_OK) { cuipm_layout_destroy(l); return -3; }
+    cuipm::FastArgs F{};
+    if (!cuipm::fast_plan(sd, P, F)) { cuipm_layout_destroy(l); return -1; }
+    std::vector<double> work((size_t) P.work_stride * nbatch, 0.0);
+    ipool.push_back(0);
+    F.nbatch = nbatch;
+    F.ipool = ipool.data(); F.qp = qp; F.sol = sol; F.work = work.data(); F.info = info; F.stat = stat;
+    F.redo_list = redo; F.redo_count = nredo; F.o = *opts;
+    *nredo = 0;
+    const int nx = F.s1.nx, nu = F.s1.nu;
+    int rc = -2;
+#define INST(NX_, NU_, G_) if (nx == NX_ && nu == NU_ && g == G_) rc = run<NX_, NU_, G_>(F, order);
+    INST(21, 3, 8) INST(21, 3, 16) INST(21, 3, 32)
+    INST(8, 3, 4) INST(8, 3, 8) INST(8, 3, 16)
+    INST(4, 1, 2) INST(4, 1, 4) INST(4, 1, 8)
+    INST(12, 4, 8) INST(12, 4, 16)
+    INST(5, 2, 4) INST(6, 2, 8)
+#undef INST
+    cuipm_layout_destroy(l);
+    return rc;
+}

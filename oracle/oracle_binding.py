@@ -154,3 +154,28 @@ def emul_expand(batch: Batch, cond_N: int, sol2: np.ndarray, nthreads: int = 128
                          C.c_void_p(sol2.ctypes.data), C.c_void_p(out.ctypes.data), C.c_int(nthreads))
     assert rc == 0
     return out
+
+
+FAST_EMUL_LIB = os.path.join(_HERE, "libfast_emul.so")
+
+
+def fast_emul_solve(batch: Batch, opts: CuipmOpts, g: int = 8, order: int = 0, sol0=None, want_stat=False):
+    """The product's throughput kernel body (acados_b200/csrc/cuipm_fast_core.h) executed on the host emulation of a
+    warp (oracle/simt_emul.h).  Returns (sol, info[, stat], redo) with redo = indices of the QPs the kernel hands back
+    to the generic kernel (cold paths)."""
+    lib = _load(FAST_EMUL_LIB)
+    nb = batch.nbatch
+    sol = batch.layout.new_sol(nb) if sol0 is None else np.ascontiguousarray(sol0).copy()
+    info = np.zeros(nb, dtype=INFO_DTYPE)
+    stat = np.zeros((nb, opts.stat_max + 1, STAT_M)) if want_stat else None
+    redo = np.zeros(nb + 1, dtype=np.int32)
+    nredo = C.c_int(0)
+    lib.fast_emul_solve.restype = C.c_int
+    rc = lib.fast_emul_solve(C.byref(batch.shape.as_ctypes()), C.c_int(nb), C.c_void_p(batch.qp.ctypes.data),
+                             C.c_void_p(sol.ctypes.data), C.c_void_p(info.ctypes.data),
+                             C.c_void_p(stat.ctypes.data if want_stat else None), C.byref(opts), C.c_int(g), C.c_int(order),
+                             C.c_void_p(redo.ctypes.data), C.byref(nredo))
+    if rc != 0:
+        raise RuntimeError(f"fast_emul_solve: rc={rc} (-1 shape not eligible, -2 no instance for this (nx, nu, g))")
+    redo = np.sort(redo[:nredo.value])
+    return (sol, info, stat, redo) if want_stat else (sol, info, redo)

@@ -1,0 +1,165 @@
+// simt_emul.h -- TEST INFRASTRUCTURE ONLY: a cooperative (fiber based) emulation of one CUDA warp on the host.
+//
+// The throughput kernel of the product (acados_b200/csrc/cuipm_fast_core.h) is written against a handful of
+// warp primitives (lane id, warp barrier, shuffles, votes, asynchronous global->shared copies).  On the GPU they
+// map to the hardware instructions (acados_b200/csrc/cuipm_fast.cu); here they map to 32 ucontext fibers that are
+// switched at every barrier, so that the SAME kernel body runs on the CPU of a machine without a GPU and can be
+// compared with the oracle (tests/test_fast_emul.py).  Lanes run one after the other between barriers, in an order
+// that can be reversed (SIMT_EMUL_ORDER) to expose missing barriers in either direction; asynchronous copies are
+// deferred until the wait, so that reading a staged block before the wait shows up as a wrong result.
+// Nothing in the product includes this file.
+#ifndef SIMT_EMUL_H_
+#define SIMT_EMUL_H_
+
+#include <ucontext.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <vector>
+
+namespace simt {
+
+struct PendingCopy { void *dst; const void *src; int bytes; };
+
+struct Warp
+{
+    static constexpr int NL = 32;
+    ucontext_t main_ctx;
+    ucontext_t ctx[NL];
+    std::vector<char> stack[NL];
+    bool done[NL];
+    int cur = 0;
+    int gen = 0, arrived = 0;
+    int order = 0;                 // 0: lanes 0..31, 1: lanes 31..0
+    double xd[NL];
+    int xi[NL];
+    std::vector<PendingCopy> pend[NL];
+    std::function<void()> body;
+    long barriers = 0;
+};
+
+inline Warp *&cur_warp()
+{
+    static thread_local Warp *w = nullptr;
+    return w;
+}
+
+inline int lane() { return cur_warp()->cur; }
+
+inline void yield_()
+{
+    Warp *w = cur_warp();
+    swapcontext(&w->ctx[w->cur], &w->main_ctx);
+}
+
+// warp barrier: every lane must call it the same number of times
+inline void sync()
+{
+    Warp *w = cur_warp();
+    const int g = w->gen;
+    if (++w->arrived == Warp::NL)
+    {
+        w->arrived = 0;
+        w->gen++;
+        w->barriers++;
+    }
+    while (w->gen == g) yield_();
+}
+
+inline double shfl(double v, int src)
+{
+    Warp *w = cur_warp();
+    w->xd[w->cur] = v;
+    sync();
+    const double r = w->xd[src & 31];
+    sync();
+    return r;
+}
+inline int shfl_i(int v, int src)
+{
+    Warp *w = cur_warp();
+    w->xi[w->cur] = v;
+    sync();
+    const int r = w->xi[src & 31];
+    sync();
+    return r;
+}
+inline unsigned ballot(bool p)
+{
+    Warp *w = cur_warp();
+    w->xi[w->cur] = p ? 1 : 0;
+    sync();
+    unsigned m = 0;
+    for (int i = 0; i < Warp::NL; i++) m |= (unsigned) w->xi[i] << i;
+    sync();
+    return m;
+}
+inline void cp_async(void *dst, const void *src, int bytes)
+{
+    Warp *w = cur_warp();
+    w->pend[w->cur].push_back({dst, src, bytes});
+}
+inline void cp_wait()
+{
+    Warp *w = cur_warp();
+    for (const PendingCopy &c : w->pend[w->cur]) std::memcpy(c.dst, c.src, (size_t) c.bytes);
+    w->pend[w->cur].clear();
+}
+
+inline void trampoline_()
+{
+    Warp *w = cur_warp();
+    w->body();
+    w->done[w->cur] = true;
+    swapcontext(&w->ctx[w->cur], &w->main_ctx);
+}
+
+// runs body() once per lane as one warp; returns the number of barriers executed
+inline long run_warp(const std::function<void()> &body, int order = 0, size_t stack_bytes = 1 << 20)
+{
+    Warp w;
+    w.body = body;
+    w.order = order;
+    Warp *prev = cur_warp();
+    cur_warp() = &w;
+    for (int i = 0; i < Warp::NL; i++)
+    {
+        w.stack[i].resize(stack_bytes);
+        w.done[i] = false;
+        getcontext(&w.ctx[i]);
+        w.ctx[i].uc_stack.ss_sp = w.stack[i].data();
+        w.ctx[i].uc_stack.ss_size = stack_bytes;
+        w.ctx[i].uc_link = &w.main_ctx;
+        makecontext(&w.ctx[i], (void (*)()) trampoline_, 0);
+    }
+    for (;;)
+    {
+        bool all = true;
+        const int g0 = w.gen, a0 = w.arrived;
+        int ndone0 = 0;
+        for (int i = 0; i < Warp::NL; i++) ndone0 += w.done[i];
+        for (int s = 0; s < Warp::NL; s++)
+        {
+            const int i = w.order ? Warp::NL - 1 - s : s;
+            if (w.done[i]) continue;
+            all = false;
+            w.cur = i;
+            swapcontext(&w.main_ctx, &w.ctx[i]);
+        }
+        if (all) break;
+        int ndone1 = 0;
+        for (int i = 0; i < Warp::NL; i++) ndone1 += w.done[i];
+        if (w.gen == g0 && ndone1 == ndone0 && w.arrived == a0)
+        {
+            std::fprintf(stderr, "simt_emul: no progress (divergent barrier: %d lanes wait, %d finished)\n", w.arrived, ndone1);
+            std::abort();
+        }
+    }
+    cur_warp() = prev;
+    return w.barriers;
+}
+
+}  // namespace simt
+#endif
