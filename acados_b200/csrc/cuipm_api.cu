@@ -48,6 +48,7 @@ struct cuipm_solver
     int fast_qpw = 1;
     FastArgs F{};
     int *d_redo_list = nullptr, *d_redo_count = nullptr;
+    double *d_qpk = nullptr;                 // kernel-side QP records (repack pass)
 };
 
 #define CK(call)                                                                                        \
@@ -78,6 +79,8 @@ static int build_desc(cuipm_solver *s, const cuipm_shape *sh)
         CK(cudaMalloc(&s->d_redo_list, sizeof(int) * (size_t) s->max_batch));
         CK(cudaMalloc(&s->d_redo_count, sizeof(int) * cuipm_solver::kPipe));
         CK(cudaMemset(s->d_redo_count, 0, sizeof(int) * cuipm_solver::kPipe));
+        CK(cudaMalloc(&s->d_qpk, sizeof(double) * s->F.qpk_stride * (size_t) s->max_batch));
+        CK(cudaMemset(s->d_qpk, 0, sizeof(double) * s->F.qpk_stride * (size_t) s->max_batch));
     }
     return CUIPM_OK;
 }
@@ -91,14 +94,18 @@ static int launch_batch(cuipm_solver *s, const LaunchArgs &a0, int slot, size_t 
     a.redo_list = nullptr;
     a.redo_count = nullptr;
     const cuipm_opts &o = a.o;
-    if (s->fast_ok && s->use_fast && o.lq_fact <= 1)
+    if (s->fast_ok && s->use_fast && o.lq_fact <= 1 && !(((size_t) a.sol | (size_t) a.work) & 15))
     {
         FastArgs F = s->F;
         F.nbatch = a.nbatch; F.ipool = a.ipool; F.qp = a.qp; F.sol = a.sol; F.work = a.work; F.info = a.info; F.stat = a.stat;
+        F.qpk = s->d_qpk + s->F.qpk_stride * lo;
         F.redo_list = s->d_redo_list + lo; F.redo_count = s->d_redo_count + slot; F.o = o;
         cudaError_t e = cudaMemsetAsync(F.redo_count, 0, sizeof(int), stream);
         if (e != cudaSuccess) { set_error(std::string("cudaMemsetAsync: ") + cudaGetErrorString(e)); return CUIPM_ERR_CUDA; }
-        int rc = launch_fast(F, (void *) stream);
+        int rc = launch_repack(F, s->d_sd, (void *) stream);
+        if (rc != 0) { set_error(std::string("kernel launch (repack): ") + cudaGetErrorString((cudaError_t) rc)); return CUIPM_ERR_CUDA; }
+        (*launches)++;
+        rc = launch_fast(F, (void *) stream);
         if (rc != 0) { set_error(std::string("kernel launch (throughput kernel): ") + cudaGetErrorString((cudaError_t) rc)); return CUIPM_ERR_CUDA; }
         (*launches)++;
         a.redo_list = F.redo_list;
@@ -159,7 +166,7 @@ extern "C" void cuipm_destroy(cuipm_solver *s)
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->d_sd); cudaFree(s->d_ipool); cudaFree(s->d_qp); cudaFree(s->d_sol); cudaFree(s->d_work);
     cudaFree(s->d_stat); cudaFree(s->d_info); cudaFree(s->d_seed); cudaFree(s->d_sens);
-    cudaFree(s->d_redo_list); cudaFree(s->d_redo_count);
+    cudaFree(s->d_redo_list); cudaFree(s->d_redo_count); cudaFree(s->d_qpk);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     for (int i = 0; i < cuipm_solver::kPipe; i++)

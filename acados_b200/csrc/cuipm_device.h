@@ -82,6 +82,14 @@ struct FastArgs
     int gstride;                   // doubles of shared memory per QP
     size_t qp_stride, sol_stride, work_stride;
     StageDesc s0, s1, sN;
+    // kernel-side QP records (written by the repack pass from the caller's records): per stage [BAt with leading dimension
+    // ld | RSQ as a full symmetric matrix with leading dimension ld | the vectors b, rq, d, d_mask, Z, z as in the caller's
+    // record]; kq = start of the stage (stages 0, 1, N), kqs = stride of the interior stages, kH / kV = offsets of the
+    // symmetric Hessian / the vector part inside the stage
+    unsigned kq[3], kH[3], kV[3], kqs;
+    int ld;
+    size_t qpk_stride;
+    const double *qpk;
     const int *ipool;
     const double *qp;
     double *sol;
@@ -100,6 +108,8 @@ struct FastArgs
 int launch_solve(const LaunchArgs &a, int warps, void *stream);
 // throughput path: true if a kernel instance exists for interior (nx, nu); fills the shared-memory figures of F
 bool fast_available(int nx, int nu, FastArgs &F, int *qp_per_warp);
+// caller's QP records -> kernel-side records (F.qpk) for F.nbatch QPs on `stream`; sd = device stage table; returns cudaError_t as int
+int launch_repack(const FastArgs &F, const StageDesc *sd, void *stream);
 // launches the throughput kernel for F on `stream`; returns cudaError_t as int
 int launch_fast(const FastArgs &F, void *stream);
 // launches the sensitivity kernel (one substitution with the factorisation the last solve left in the work records)

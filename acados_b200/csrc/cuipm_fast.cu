@@ -20,19 +20,39 @@ static __device__ __forceinline__ void fk_sync() { __syncwarp(); }
 static __device__ __forceinline__ double fk_shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 static __device__ __forceinline__ int fk_shfl_xor_i(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 static __device__ __forceinline__ bool fk_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
-// asynchronous global -> shared copies (LDGSTS): no register staging; 16-byte copies bypass L1 (each stage block is read
-// once per sweep), completion through the per-thread group wait + a warp barrier
-static __device__ __forceinline__ void fk_cp16(double *sdst, const double *gsrc)
+// bulk asynchronous copies (TMA, cp.async.bulk): global -> shared, 16-byte aligned, multiple of 16 bytes, completion
+// counted in bytes on an mbarrier in shared memory (no register staging, one instruction per contiguous range)
+typedef unsigned long long fk_mbar_t;
+static __device__ __forceinline__ void fk_mbar_init(fk_mbar_t *b, int count)
 {
-    const unsigned sa = (unsigned) __cvta_generic_to_shared(sdst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+    const unsigned ba = (unsigned) __cvta_generic_to_shared(b);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ba), "r"(count) : "memory");
 }
-static __device__ __forceinline__ void fk_cp8(double *sdst, const double *gsrc)
+static __device__ __forceinline__ void fk_bulk(double *sdst, const double *gsrc, unsigned bytes, fk_mbar_t *b)
 {
-    const unsigned sa = (unsigned) __cvta_generic_to_shared(sdst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+    const unsigned sa = (unsigned) __cvta_generic_to_shared(sdst), ba = (unsigned) __cvta_generic_to_shared(b);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa), "l"(gsrc), "r"(bytes), "r"(ba)
+                 : "memory");
 }
-static __device__ __forceinline__ void fk_cp_wait() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+static __device__ __forceinline__ void fk_mbar_arrive_tx(fk_mbar_t *b, unsigned bytes)
+{
+    const unsigned ba = (unsigned) __cvta_generic_to_shared(b);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ba), "r"(bytes) : "memory");
+}
+static __device__ __forceinline__ void fk_mbar_wait(fk_mbar_t *b, unsigned parity)
+{
+    const unsigned ba = (unsigned) __cvta_generic_to_shared(b);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(ba), "r"(parity)
+        : "memory");
+}
+// orders this thread's earlier generic-proxy accesses to shared memory before later asynchronous-proxy (bulk copy) writes
+static __device__ __forceinline__ void fk_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 static __device__ __forceinline__ double fk_ldg(const double *p) { return __ldg(p); }
 static __device__ __forceinline__ double fk_rsqrt(double x) { return rsqrt(x); }
 static __device__ __forceinline__ int fk_atomic_inc(int *p) { return atomicAdd(p, 1); }
@@ -49,11 +69,44 @@ template <int NX, int NU, int G, int MINB>
 __global__ void __launch_bounds__(32, MINB) cuipm_fast_kernel(const __grid_constant__ FastArgs A)
 {
     using K = fastk::Ker<NX, NU, G>;
-    K k(A, g_fsmem);
+    __shared__ __align__(8) fk_mbar_t bars[2];
+    K k(A, g_fsmem, bars, (int) blockIdx.x * K::QPW);
     int q = (int) blockIdx.x * K::QPW + k.gq;
     const bool valid = q < A.nbatch;
     if (!valid) q = A.nbatch - 1;
     k.solve(q, valid);
+}
+
+// caller's QP records -> kernel-side records: dynamics block with leading dimension ld, Hessian as a full symmetric matrix
+// with leading dimension ld (lower triangle mirrored), vector part verbatim.  One CTA per QP, coalesced writes.
+__global__ void __launch_bounds__(256) cuipm_repack_kernel(const FastArgs A, const StageDesc *__restrict__ sd)
+{
+    const int N = A.N, ld = A.ld;
+    for (int q = blockIdx.x; q < A.nbatch; q += gridDim.x)
+    {
+        const double *__restrict__ qp = A.qp + (size_t) q * A.qp_stride;
+        double *__restrict__ qk = const_cast<double *>(A.qpk) + (size_t) q * A.qpk_stride;
+        for (int k = 0; k <= N; k++)
+        {
+            const StageDesc d = sd[k];
+            const int kind = k == 0 ? 0 : (k == N ? 2 : 1);
+            double *o = qk + A.kq[kind] + (kind == 1 ? (size_t) (k - 1) * A.kqs : 0);
+            const int n = d.n, nx1 = d.nx1;
+            for (int e = threadIdx.x; e < n * nx1; e += blockDim.x)
+            {
+                const int c = e / n, r = e - c * n;
+                o[r + ld * c] = qp[d.q_BAt + e];
+            }
+            double *H = o + A.kH[kind];
+            for (int e = threadIdx.x; e < n * n; e += blockDim.x)
+            {
+                const int j = e / n, i = e - j * n;
+                H[i + ld * j] = i >= j ? qp[d.q_RSQ + e] : qp[d.q_RSQ + j + n * i];
+            }
+            const int nv = (int) (d.q_stage + d.q_stage_bytes / 8u - d.q_b);
+            for (int e = threadIdx.x; e < nv; e += blockDim.x) o[A.kV[kind] + e] = qp[d.q_b + e];
+        }
+    }
 }
 
 template <int NX, int NU, int G>
@@ -73,6 +126,7 @@ cudaError_t launch_one(const FastArgs &F, cudaStream_t stream)
 {
     using K = fastk::Ker<NX, NU, G>;
     const size_t smem = sizeof(double) * (size_t) F.gstride * K::QPW;
+    if (((size_t) F.qpk | (size_t) F.sol | (size_t) F.work) & 15) return cudaErrorMisalignedAddress;      // bulk copies need 16-byte aligned records
     cudaError_t err = cudaFuncSetAttribute(cuipm_fast_kernel<NX, NU, G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (err != cudaSuccess) return err;
     // the CTAs of one SM together need most of its shared memory: ask for the largest carve-out (the default heuristic
@@ -99,19 +153,45 @@ cudaError_t launch_one(const FastArgs &F, cudaStream_t stream)
     X(4, 1, 2, 8)               \
     X(12, 4, 8, 6)
 
+// development: other lanes-per-QP mappings of the headline shape, selected with CUIPM_FAST_G=16|32
+#ifdef CUIPM_FAST_DEV
+#define CUIPM_FAST_DEV_INSTANCES(X) \
+    X(21, 3, 16, 8)                 \
+    X(21, 3, 32, 16)
+#else
+#define CUIPM_FAST_DEV_INSTANCES(X)
+#endif
+static int dev_g() { const char *e = getenv("CUIPM_FAST_G"); return e ? atoi(e) : 0; }
+
 bool fast_available(int nx, int nu, FastArgs &F, int *qp_per_warp)
 {
 #define X(NX_, NU_, G_, MB_) \
-    if (nx == NX_ && nu == NU_) { sizes<NX_, NU_, G_>(F, qp_per_warp); return sizeof(double) * (size_t) F.gstride * (32 / G_) <= 227 * 1024; }
+    if (nx == NX_ && nu == NU_ && dev_g() == G_) { sizes<NX_, NU_, G_>(F, qp_per_warp); return sizeof(double) * (size_t) F.gstride * (32 / G_) <= 226 * 1024; }
+    CUIPM_FAST_DEV_INSTANCES(X)
+#undef X
+#define X(NX_, NU_, G_, MB_) \
+    if (nx == NX_ && nu == NU_) { sizes<NX_, NU_, G_>(F, qp_per_warp); return sizeof(double) * (size_t) F.gstride * (32 / G_) <= 226 * 1024; }
     CUIPM_FAST_INSTANCES(X)
 #undef X
     return false;
+}
+
+int launch_repack(const FastArgs &F, const StageDesc *sd, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t) stream_;
+    const int grid = F.nbatch < 148 * 8 ? F.nbatch : 148 * 8;
+    cuipm_repack_kernel<<<grid, 256, 0, stream>>>(F, sd);
+    return (int) cudaGetLastError();
 }
 
 int launch_fast(const FastArgs &F, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t) stream_;
     const int nx = F.s1.nx, nu = F.s1.nu;
+#define X(NX_, NU_, G_, MB_) \
+    if (nx == NX_ && nu == NU_ && dev_g() == G_) return (int) launch_one<NX_, NU_, G_, MB_>(F, stream);
+    CUIPM_FAST_DEV_INSTANCES(X)
+#undef X
 #define X(NX_, NU_, G_, MB_) \
     if (nx == NX_ && nu == NU_) return (int) launch_one<NX_, NU_, G_, MB_>(F, stream);
     CUIPM_FAST_INSTANCES(X)

@@ -3,20 +3,27 @@
 // Mapping: a GROUP of G lanes owns one QP for the whole solve and a warp carries 32/G QPs in lock step, so that every
 // serial piece of the algorithm (pivots, reciprocal square roots, the scalar logic of the IPM) is one instruction stream
 // for 32/G QPs.  Lane l of a group owns rows l, l+G, l+2G, ... of the stage block; the rank-k updates are register tiles
-// of (row slots) x 8 columns fed by one LDS per own row and 128-bit broadcast loads of the other operand.  Stage blocks
-// are staged into shared memory with asynchronous copies (leading dimension LD = 2 mod 4: row and column accesses are
-// both bank-conflict free, column starts 16-byte aligned).
+// of (row slots) x 8 columns fed by one LDS per own row and 128-bit broadcast loads of the other operand; the gradient
+// travels as a vector next to the factorisation (a fused right-looking substitution), so the row slots hold matrix rows only.
 //
-// Algorithm and data layout are those of the generic kernel (cuipm_kernel.cu), which restates HPIPM's
-// d_ocp_qp_ipm_solve (external/hpipm/ocp_qp/x_ocp_qp_ipm.c:2684-3120): same records, same work-record layout (the
-// sensitivity kernel and the Riccati getters read what this kernel leaves behind).  Restrictions (checked on the host,
-// cuipm_plan.h fast_plan): x0 eliminated, uniform interior stages, no general constraints.  Cold paths -- the LQ
-// refactorisation, iterative refinement steps, a QP without active constraints -- are not here: a QP that needs one is
-// handed back (status CUIPM_FAST_REDO, index appended to redo_list) and solved from scratch by the generic kernel.
+// Data movement: every input of a stage -- the dynamics block, the Hessian block, the factor of the next stage and the
+// "images" of the contiguous vector ranges of the three records -- is brought into shared memory by bulk asynchronous
+// copies (TMA, cp.async.bulk) issued by one lane with warp-uniform operands and completed on an mbarrier; the arithmetic
+// then runs on shared memory and registers only, results leave through plain stores.  The matrices come from the
+// kernel-side QP record (FastArgs::qpk, written by the repack pass): leading dimension LD = 2 (mod 4) (row and column
+// accesses both bank-conflict free, 16-byte aligned columns), Hessian stored as a full symmetric matrix.
+//
+// Algorithm and work-record layout are those of the generic kernel (cuipm_kernel.cu), which restates HPIPM's
+// d_ocp_qp_ipm_solve (external/hpipm/ocp_qp/x_ocp_qp_ipm.c:2684-3120): the sensitivity kernel and the Riccati getters
+// read what this kernel leaves behind.  Restrictions (checked on the host, cuipm_plan.h fast_plan): x0 eliminated,
+// uniform interior stages, no general constraints.  Cold paths -- the LQ refactorisation, iterative refinement steps, a QP
+// without active constraints -- are not here: a QP that needs one is handed back (status CUIPM_FAST_REDO, index appended to
+// redo_list) and solved from scratch by the generic kernel.
 //
 // The file is written against a few warp primitives supplied by the including translation unit (FK_DEV, fk_lane,
-// fk_sync, fk_shfl_xor, fk_any, fk_cp16, fk_cp8, fk_cp_wait, fk_ldg, fk_rsqrt, fk_atomic_inc): the CUDA instantiation is
-// cuipm_fast.cu; oracle/fast_emul.cpp instantiates the same body on a host emulation of a warp for the CPU test-suite.
+// fk_sync, fk_shfl_xor, fk_any, fk_bulk, fk_mbar_*, fk_fence_async, fk_ldg, fk_rsqrt, fk_atomic_inc): the CUDA
+// instantiation is cuipm_fast.cu; oracle/fast_emul.cpp instantiates the same body on a host emulation of a warp for the
+// CPU test-suite.
 #ifndef CUIPM_FAST_CORE_H_
 #define CUIPM_FAST_CORE_H_
 
@@ -39,13 +46,13 @@ struct Ker
 {
     static constexpr int NM = NX + NU;                    // rows of an interior stage block
     static constexpr int QPW = 32 / G;                    // QPs per warp
-    static constexpr int LD = ((NM + 2) / 4) * 4 + 2;     // >= NM+1, = 2 mod 4
-    static constexpr int RPM = (NM + 1 + G - 1) / G;      // row slots per lane (rows incl. the gradient row)
-    static constexpr int PADR = ((G * RPM > LD ? G * RPM - LD : 0) + 3) & ~1;
-    static constexpr int SZA = LD * NX + PADR;            // [A; b'] / A Lxx / staged BAt
-    static constexpr int SZL = LD * NM + PADR;            // L_{k+1} -> L_k (factorisation); L_{k+1} (substitutions)
-    static constexpr int SZU = LD * NU + 2;               // first nu columns of L_k (substitutions)
-    static constexpr int SZD = 16;                        // 4 x 4 diagonal block
+    static constexpr int LD = ((NM + 2) / 4) * 4 + 2;     // >= NM+1, = 2 mod 4 (the leading dimension of the kernel-side record)
+    static constexpr int RPM = (NM + G - 1) / G;          // row slots per lane
+    static constexpr int NXe = (NX + 1) & ~1, NMe = (NM + 2) & ~1;
+    static constexpr int SZA = LD * NX;                   // dynamics block [B'; A'] -> A Lxx in place
+    static constexpr int SZL = LD * NM;                   // L_{k+1} -> L_k (factorisation); Hessian / L_{k+1} (other sweeps)
+    static constexpr int SZU = (NM * NU + 1) & ~1;        // first nu columns of L_k (substitutions), leading dimension n
+    static constexpr int SZD = 20;                        // 4 x 4 diagonal block + 4 gradient entries
     static constexpr int MATS = SZA + SZL + SZU + SZD;
 
     // stage kinds: 0 = first (nx = 0), 1 = interior, 2 = last (nu = 0)
@@ -56,22 +63,35 @@ struct Ker
     };
 
     const FastArgs &A;
-    int li, gq;                // lane within the group, group within the warp
+    double *smem0;             // shared memory of the warp (after the two transaction barriers)
+    fk_mbar_t *bars;           // [0]: vector images, [1]: matrices
+    int li, gq, q0;            // lane within the group, group within the warp, first QP of the warp
     double *MA, *ML, *LU, *DD, *V;
-    const double *qp;
+    const double *qp, *qk;     // this group's QP record: the caller's, the kernel-side one
     double *sol, *wk;
     bool act;                  // this group's QP is being solved: global stores enabled
+    unsigned ph0, ph1;         // phase parities of the two barriers
+    unsigned tx0, tx1;         // bytes announced to them in the phase being filled
+    double nc_mask_inv;
 
-    struct View { const double *q; double *s; double *w; const int *ip; };
+    struct View { const double *q; const double *k; double *s; double *w; const int *ip; unsigned kk; };
 
-    FK_DEV Ker(const FastArgs &a, double *smem) : A(a)
+    FK_DEV Ker(const FastArgs &a, double *smem, fk_mbar_t *b, int first_qp) : A(a)
     {
         const int lane = fk_lane();
         li = lane % G;
         gq = lane / G;
+        q0 = first_qp;
+        smem0 = smem;
+        bars = b;
         double *S = smem + (size_t) gq * a.gstride;
         MA = S; ML = MA + SZA; LU = ML + SZL; DD = LU + SZU; V = DD + SZD;
-        qp = nullptr; sol = nullptr; wk = nullptr; act = false;
+        qp = nullptr; qk = nullptr; sol = nullptr; wk = nullptr; act = false;
+        ph0 = ph1 = 0; tx0 = tx1 = 0;
+        nc_mask_inv = 0.0;
+        if (lane == 0) { fk_mbar_init(bars, 1); fk_mbar_init(bars + 1, 1); }
+        fk_fence_async();
+        fk_sync();
     }
 
     template <int KIND>
@@ -80,13 +100,14 @@ struct Ker
     FK_DEV View view(int k) const
     {
         const unsigned kk = KIND == 1 ? (unsigned) (k - 1) : 0u;
-        return View{qp + kk * A.qs, sol + kk * A.ss, wk + kk * A.ws, A.ipool + (int) kk * A.is};
+        return View{qp + kk * A.qs, qk + A.kq[KIND] + kk * A.kqs, sol + kk * A.ss, wk + kk * A.ws, A.ipool + (int) kk * A.is, kk};
     }
     FK_DEV const StageDesc &sdr(int k) const { return k == 0 ? A.s0 : (k == A.N ? A.sN : A.s1); }
     FK_DEV View viewr(int k) const
     {
         const unsigned kk = (k >= 1 && k < A.N) ? (unsigned) (k - 1) : 0u;
-        return View{qp + kk * A.qs, sol + kk * A.ss, wk + kk * A.ws, A.ipool + (int) kk * A.is};
+        const int kind = k == 0 ? 0 : (k == A.N ? 2 : 1);
+        return View{qp + kk * A.qs, qk + A.kq[kind] + kk * A.kqs, sol + kk * A.ss, wk + kk * A.ws, A.ipool + (int) kk * A.is, kk};
     }
 
     // ---- group reductions ---------------------------------------------------------------------------
@@ -115,49 +136,119 @@ struct Ker
     }
     FK_DEV void st(double *p, double v) const { if (act) *p = v; }
 
-    // ---- staging ------------------------------------------------------------------------------------
-    // column-major R x C block (ld R) of a record -> shared memory (ld LD), asynchronously; fk_cp_wait() + fk_sync() complete it
-    template <int R, int C>
-    FK_DEV void stage_mat(double *dst, const double *src) const
+    // ---- staging: bulk asynchronous copies with warp-uniform operands ---------------------------------------------------
+    // One contiguous range of `nd` doubles (even) per QP of the warp, from record REC (0 kernel-side QP record, 1 solution,
+    // 2 work) at record offset `off`, to offset `soff` of each group's shared memory; BAR: 0 vector images, 1 matrices.
+    // Lane 0 issues the copies (operands depend on the warp only); every lane keeps the byte count.
+    template <int REC, int BAR>
+    FK_DEV void bulk(int soff, size_t off, int nd)
     {
-        if (R % 2 == 0)
+        if (fk_lane() == 0)
         {
-            constexpr int H = R / 2 > 0 ? R / 2 : 1, T = H * C;
-#pragma unroll 4
-            for (int e = li; e < T; e += G)
+#pragma unroll
+            for (int g = 0; g < QPW; g++)
             {
-                const int c = e / H, h = e - c * H;
-                fk_cp16(dst + LD * c + 2 * h, src + R * c + 2 * h);
+                int q = q0 + g;
+                q = q < A.nbatch ? q : A.nbatch - 1;
+                const double *src = (REC == 0 ? A.qpk + (size_t) q * A.qpk_stride : (REC == 1 ? A.sol + (size_t) q * A.sol_stride : A.work + (size_t) q * A.work_stride)) + off;
+                fk_bulk(smem0 + (size_t) g * A.gstride + soff, src, (unsigned) nd * 8u, bars + BAR);
             }
         }
-        else
-        {
-            constexpr int T = R * C, R1 = R > 0 ? R : 1;
-#pragma unroll 4
-            for (int e = li; e < T; e += G)
-            {
-                const int c = e / R1, r = e - c * R1;
-                fk_cp8(dst + LD * c + r, src + e);
-            }
-        }
+        if (BAR == 0) tx0 += (unsigned) (QPW * nd) * 8u;
+        else tx1 += (unsigned) (QPW * nd) * 8u;
     }
-    // row i of the symmetric n x n matrix H of which the lower triangle is stored (column-major, ld n), times x (shared)
-    template <int n>
-    FK_DEV double gdot_sym(const double *H, int i, const double *x) const
+    // all lanes are done with the buffers the next copies overwrite
+    FK_DEV void stage_begin() { fk_fence_async(); fk_sync(); }
+    // the copies of this stage have been issued: announce their bytes
+    FK_DEV void stage_arm()
     {
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        if (fk_lane() == 0) { fk_mbar_arrive_tx(bars, tx0); fk_mbar_arrive_tx(bars + 1, tx1); }
+        tx0 = tx1 = 0;
+    }
+    // a second batch of matrix copies inside a stage
+    FK_DEV void stage_arm_mat()
+    {
+        if (fk_lane() == 0) fk_mbar_arrive_tx(bars + 1, tx1);
+        tx1 = 0;
+    }
+    FK_DEV void wait_vec() { fk_mbar_wait(bars, ph0); ph0 ^= 1u; }
+    FK_DEV void wait_mat() { fk_mbar_wait(bars + 1, ph1); ph1 ^= 1u; }
+    FK_DEV int voff(const double *p) const { return (int) (p - (smem0 + (size_t) gq * A.gstride)); }
+
+    // ---- small dense helpers on shared memory -----------------------------------------------------------------------
+    // y[i] (+)= sum_j M[i + ld*j] * x[j], j < nc, for the rows i = li, li+G, ... < nr of this lane (row access), x broadcast
+    template <int nr, int nc>
+    FK_DEV void rows_dot(const double *M, int ld, const double *x, double (&out)[RPM > 0 ? RPM : 1]) const
+    {
+        constexpr int RP = (nr + G - 1) / G;
+#pragma unroll
+        for (int m = 0; m < RP; m++) out[m] = 0.0;
+        double o2[RPM > 0 ? RPM : 1];
+#pragma unroll
+        for (int m = 0; m < RP; m++) o2[m] = 0.0;
         int j = 0;
-#pragma unroll 2
-        for (; j + 3 < n; j += 4)
+#pragma unroll 4
+        for (; j + 1 < nc; j += 2)
         {
-            const double a0 = fk_ldg(H + (j <= i ? i + n * j : j + n * i));
-            const double a1 = fk_ldg(H + (j + 1 <= i ? i + n * (j + 1) : j + 1 + n * i));
-            const double a2 = fk_ldg(H + (j + 2 <= i ? i + n * (j + 2) : j + 2 + n * i));
-            const double a3 = fk_ldg(H + (j + 3 <= i ? i + n * (j + 3) : j + 3 + n * i));
-            s0 += a0 * x[j]; s1 += a1 * x[j + 1]; s2 += a2 * x[j + 2]; s3 += a3 * x[j + 3];
+            const double x0 = x[j], x1 = x[j + 1];
+#pragma unroll
+            for (int m = 0; m < RP; m++)
+            {
+                const int r = li + G * m;
+                const int rr = r < nr ? r : 0;
+                out[m] += M[rr + ld * j] * x0;
+                o2[m] += M[rr + ld * (j + 1)] * x1;
+            }
         }
-        for (; j < n; j++) s0 += fk_ldg(H + (j <= i ? i + n * j : j + n * i)) * x[j];
-        return (s0 + s1) + (s2 + s3);
+        if (j < nc)
+        {
+            const double x0 = x[j];
+#pragma unroll
+            for (int m = 0; m < RP; m++)
+            {
+                const int r = li + G * m;
+                const int rr = r < nr ? r : 0;
+                out[m] += M[rr + ld * j] * x0;
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < RP; m++) out[m] += o2[m];
+    }
+    // z[j] = sum_i M[i + ld*j] * w[i], i < nr, for the columns j = li, li+G, ... < nc of this lane (column access), w broadcast
+    template <int nr, int nc>
+    FK_DEV void cols_dot(const double *M, int ld, const double *w, double (&out)[RPM > 0 ? RPM : 1]) const
+    {
+        constexpr int CP = (nc + G - 1) / G;
+        double o2[RPM > 0 ? RPM : 1];
+#pragma unroll
+        for (int m = 0; m < CP; m++) { out[m] = 0.0; o2[m] = 0.0; }
+        int i = 0;
+#pragma unroll 4
+        for (; i + 1 < nr; i += 2)
+        {
+            const double w0 = w[i], w1 = w[i + 1];
+#pragma unroll
+            for (int m = 0; m < CP; m++)
+            {
+                const int c = li + G * m;
+                const int cc = c < nc ? c : 0;
+                out[m] += M[i + ld * cc] * w0;
+                o2[m] += M[i + 1 + ld * cc] * w1;
+            }
+        }
+        if (i < nr)
+        {
+            const double w0 = w[i];
+#pragma unroll
+            for (int m = 0; m < CP; m++)
+            {
+                const int c = li + G * m;
+                const int cc = c < nc ? c : 0;
+                out[m] += M[i + ld * cc] * w0;
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < CP; m++) out[m] += o2[m];
     }
 
     // ---------------------------------------------------------------------------------------------
@@ -165,6 +256,8 @@ struct Ker
     // UPDATE_VAR_QP fused (x_core_qp_ipm_aux.c:472-582: the iterate first moves by alpha_u along the step, with the
     // step shortening and the t/lam clipping) and the affine complementarity right-hand side of the next
     // iteration (res_m = lam*t - tau_min, backup lam*t; BACKUP_RES_M / COMPUTE_TAU_MIN_QP :672-781).
+    // Staged: dynamics block, symmetric Hessian, the solution and step records of the stage, ux of the next stage, the
+    // vector part of the QP record.
     // ---------------------------------------------------------------------------------------------
     struct ResAcc
     {
@@ -176,48 +269,62 @@ struct Ker
     FK_DEV void res_stage(int k, int update, double alpha_u, ResAcc &R)
     {
         constexpr int nx = KD<KIND>::nx, nu = KD<KIND>::nu, n = nx + nu, nx1 = KD<KIND>::nx1;
+        constexpr int RP = (n + G - 1) / G, CP = (nx1 + G - 1) / G;
         const StageDesc &sd = sdk<KIND>();
         const View v = view<KIND>(k);
         const int nb = sd.nb, ns = sd.ns, nc = sd.nc;
         const int *idxb = v.ip + sd.idx_off, *rev = idxb + nb;
-        double *ux = V, *x1 = ux + A.nve, *pi = x1 + evn(NX), *pim = pi + evn(NX);
-        double *lam = pim + evn(NX), *lamr = lam + A.nce, *t = lamr + A.nce, *msk = t + A.nce;
-        double *tmp0 = msk + A.nce, *tmp1 = tmp0 + A.nbe, *g_ = tmp1 + A.nbe;
-        if (nx1 > 0) stage_mat<n, nx1>(MA, v.q + sd.q_BAt);
-        // ---- vectors of this stage (optionally moved along the step) to shared memory
-        {
-            double *gu = v.s + sd.sol.ux;
-            const double *du = v.w + sd.step.ux;
-            for (int i = li; i < n + 2 * ns; i += G)
-            {
-                double x = gu[i];
-                if (update) { x += alpha_u * du[i]; st(gu + i, x); }
-                ux[i] = x;
-            }
-        }
+        const int nu1 = (nx1 > 0 && k + 1 < A.N) ? NU : 0, n1e = (nx1 + nu1 + 1) & ~1;
+        // images
+        const int solN = (int) (sd.sol.t - sd.sol.ux) + evn(nc), stpN = (int) (sd.step.t - sd.step.ux) + evn(nc);
+        const int qvN = (int) ((sd.q_stage + sd.q_stage_bytes / 8u) - sd.q_b);
+        double *SOL = V, *STP = SOL + (A.nve + NXe + 2 * A.nce), *SOLN = STP + (A.nve + NXe + 2 * A.nce), *STPN = SOLN + NMe;
+        double *QV = STPN + NMe, *tmp0 = QV + (NXe + NMe + 2 * A.nce + 2 * A.ns2e), *tmp1 = tmp0 + A.nbe, *g_ = tmp1 + A.nbe, *pim = g_ + A.nve;
+        double *x1 = pim + NXe;
+        stage_begin();
+        bulk<1, 0>(voff(SOL), (size_t) v.kk * A.ss + sd.sol.ux, solN);
+        if (update) bulk<2, 0>(voff(STP), (size_t) v.kk * A.ws + sd.step.ux, stpN);
+        bulk<0, 0>(voff(QV), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kV[KIND], evn(qvN));
         if (nx1 > 0)
         {
             const StageDesc &s1 = sdr(k + 1);
             const View v1 = viewr(k + 1);
-            const double *gu1 = v1.s + s1.sol.ux + s1.nu, *du1 = v1.w + s1.step.ux + s1.nu, *dp = v.w + sd.step.pi;
-            double *gp = v.s + sd.sol.pi;
+            bulk<1, 0>(voff(SOLN), (size_t) v1.kk * A.ss + s1.sol.ux, n1e);
+            if (update) bulk<2, 0>(voff(STPN), (size_t) v1.kk * A.ws + s1.step.ux, n1e);
+            bulk<0, 1>(voff(MA), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs, evn(LD * nx1));
+        }
+        bulk<0, 1>(voff(ML), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kH[KIND], LD * n);
+        stage_arm();
+        wait_vec();
+        double *ux = SOL, *pi = SOL + (sd.sol.pi - sd.sol.ux), *lam = SOL + (sd.sol.lam - sd.sol.ux), *t = SOL + (sd.sol.t - sd.sol.ux);
+        const double *du = STP, *dp = STP + (sd.step.pi - sd.step.ux), *dl = STP + (sd.step.lam - sd.step.ux), *dtt = STP + (sd.step.t - sd.step.ux);
+        const double *qb = QV, *qrq = QV + (sd.q_rq - sd.q_b), *qd = QV + (sd.q_d - sd.q_b), *msk = QV + (sd.q_dmask - sd.q_b);
+        const double *qZ = QV + (sd.q_Z - sd.q_b), *qz = QV + (sd.q_z - sd.q_b);
+        // ---- move along the step (in the images; the new iterate goes back to the solution record)
+        if (update)
+        {
+            double *gu = v.s + sd.sol.ux, *gp = v.s + sd.sol.pi;
+            for (int i = li; i < n + 2 * ns; i += G)
+            {
+                const double x = ux[i] + alpha_u * du[i];
+                ux[i] = x;
+                st(gu + i, x);
+            }
             for (int j = li; j < nx1; j += G)
             {
-                double x = gu1[j], p = gp[j];
-                if (update) { x += alpha_u * du1[j]; p += alpha_u * dp[j]; st(gp + j, p); }
-                x1[j] = x;
+                const double p = pi[j] + alpha_u * dp[j];
                 pi[j] = p;
+                st(gp + j, p);
             }
         }
+        for (int j = li; j < nx1; j += G) x1[j] = update ? SOLN[nu1 + j] + alpha_u * STPN[nu1 + j] : SOLN[nu1 + j];
         {
             double *gl = v.s + sd.sol.lam, *gt = v.s + sd.sol.t;
-            const double *gm = v.q + sd.q_dmask, *dl = v.w + sd.step.lam, *dtt = v.w + sd.step.t;
-            double *bl = wk + A.w_bkp + (sd.sol.lam + (KIND == 1 ? (unsigned) (k - 1) * A.ss : 0u));
-            double *bt = wk + A.w_bkp + (sd.sol.t + (KIND == 1 ? (unsigned) (k - 1) * A.ss : 0u));
+            double *bl = wk + A.w_bkp + (sd.sol.lam + v.kk * A.ss), *bt = wk + A.w_bkp + (sd.sol.t + v.kk * A.ss);
             for (int i = li; i < nc; i += G)
             {
-                double l = gl[i], tt = gt[i];
-                const double mk = fk_ldg(gm + i);
+                double l = lam[i], tt = t[i];
+                const double mk = msk[i];
                 if (update)
                 {
                     // iterate of the factorisation just used (UPDATE_VAR_QP backups, x_core_qp_ipm_aux.c:534-575): the point the
@@ -235,60 +342,54 @@ struct Ker
                     st(gl + i, l);
                     st(gt + i, tt);
                 }
-                lamr[i] = l;
                 lam[i] = l * mk;
                 t[i] = tt;
-                msk[i] = mk;
             }
         }
-        fk_cp_wait();
         fk_sync();
         for (int i = li; i < nb; i += G) tmp0[i] = lam[nb + i] - lam[i];
+        wait_mat();
         fk_sync();
         // ---- rows of res_g (lane = row), res_b (lane = column)
-        const double *Hg = v.q + sd.q_RSQ;
         {
-            const double *gvec = v.q + sd.q_rq;
-            for (int i = li; i < n; i += G)
+            double hx[RPM > 0 ? RPM : 1], ap[RPM > 0 ? RPM : 1];
+            rows_dot<n, n>(ML, LD, ux, hx);
+            if (nx1 > 0) rows_dot<n, nx1>(MA, LD, pi, ap);
+#pragma unroll
+            for (int m = 0; m < RP; m++)
             {
-                const double acc = gdot_sym<n>(Hg, i, ux);
-                const double gv = fk_ldg(gvec + i);
-                double r = acc + 2.0 * gv;
-                R.a_obj += 0.5 * r * ux[i];
-                r -= gv;
-                R.a_gap += r * ux[i];
-                if (nx > 0 && i >= nu) r -= pim[i - nu];
-                if (nx1 > 0)
+                const int i = li + G * m;
+                if (i < n)
                 {
-                    double s0 = 0.0, s1 = 0.0;
-                    const double *arow = MA + i;
-                    int j = 0;
-#pragma unroll 4
-                    for (; j + 1 < nx1; j += 2) { s0 += arow[LD * j] * pi[j]; s1 += arow[LD * (j + 1)] * pi[j + 1]; }
-                    if (j < nx1) s0 += arow[LD * j] * pi[j];
-                    r += s0 + s1;
+                    const double gv = qrq[i];
+                    double r = hx[m] + 2.0 * gv;
+                    R.a_obj += 0.5 * r * ux[i];
+                    r -= gv;
+                    R.a_gap += r * ux[i];
+                    if (nx > 0 && i >= nu) r -= pim[i - nu];
+                    if (nx1 > 0) r += ap[m];
+                    g_[i] = r;
                 }
-                g_[i] = r;
             }
             if (nx1 > 0)
             {
-                const double *bvec = v.q + sd.q_b;
+                double au[RPM > 0 ? RPM : 1];
+                cols_dot<n, nx1>(MA, LD, ux, au);
                 double *ob = v.w + sd.res.b;
-                for (int j = li; j < nx1; j += G)
+#pragma unroll
+                for (int m = 0; m < CP; m++)
                 {
-                    double s0 = 0.0, s1 = 0.0;
-                    const double *acol = MA + LD * j;
-                    int i = 0;
-#pragma unroll 4
-                    for (; i + 1 < n; i += 2) { s0 += acol[i] * ux[i]; s1 += acol[i + 1] * ux[i + 1]; }
-                    if (i < n) s0 += acol[i] * ux[i];
-                    const double bv = fk_ldg(bvec + j);
-                    const double r = bv - x1[j] + (s0 + s1);
-                    st(ob + j, r);
-                    const double a = fabs(r);
-                    R.m1 = fmax(R.m1, a);
-                    R.f1 |= (a != a);
-                    R.a_gap -= bv * pi[j];
+                    const int j = li + G * m;
+                    if (j < nx1)
+                    {
+                        const double bv = qb[j];
+                        const double r = bv - x1[j] + au[m];
+                        st(ob + j, r);
+                        const double a = fabs(r);
+                        R.m1 = fmax(R.m1, a);
+                        R.f1 |= (a != a);
+                        R.a_gap -= bv * pi[j];
+                    }
                 }
             }
         }
@@ -302,11 +403,10 @@ struct Ker
         }
         if (ns > 0)
         {
-            const double *Z = v.q + sd.q_Z, *zvec = v.q + sd.q_z;
             for (int j = li; j < 2 * ns; j += G)
             {
-                const double sj = ux[n + j], zz = fk_ldg(zvec + j);
-                double r = fk_ldg(Z + j) * sj + 2.0 * zz;
+                const double sj = ux[n + j], zz = qz[j];
+                double r = qZ[j] * sj + 2.0 * zz;
                 R.a_obj += 0.5 * r * sj;
                 r -= zz;
                 R.a_gap += r * sj;
@@ -320,11 +420,10 @@ struct Ker
         fk_sync();
         // ---- res_d, res_m
         {
-            const double *dvec = v.q + sd.q_d;
             double *od = v.w + sd.res.d, *om = v.w + sd.res.m, *obk = v.w + sd.w_rmb;
             for (int i = li; i < nc; i += G)
             {
-                const double dv = fk_ldg(dvec + i);
+                const double dv = qd[i];
                 double r;
                 if (i < 2 * nb)
                 {
@@ -365,9 +464,7 @@ struct Ker
                 R.f0 |= (a != a);
             }
         }
-        fk_sync();
         for (int j = li; j < nx1; j += G) pim[j] = pi[j];      // pi_k is "pi_{k-1}" of the next stage
-        fk_sync();
     }
 
     FK_DEV void res_pass(int update, double alpha_u, QpState &Q)
@@ -376,7 +473,6 @@ struct Ker
         R.a_mu = R.a_obj = R.a_gap = R.m0 = R.m1 = R.m2 = R.m3 = R.m4 = 0.0;
         R.f0 = R.f1 = R.f2 = R.f3 = R.f4 = 0;
         if (update && alpha_u < 1.0) alpha_u = alpha_u * ((1.0 - alpha_u) * 0.99 + alpha_u * 0.9999999);
-        fk_sync();
         res_stage<0>(0, update, alpha_u, R);
         for (int k = 1; k < A.N; k++) res_stage<1>(k, update, alpha_u, R);
         res_stage<2>(A.N, update, alpha_u, R);
@@ -401,7 +497,7 @@ struct Ker
         {
             const int jj = j < ns ? j : j - ns, offc = j < ns ? 0 : nb;
             double zi = 0.0, d = rgs[j] + gam[2 * nb + j];
-            if (fact) zi = fk_ldg(Z + j) + A.o.reg_prim + Gam[2 * nb + j];
+            if (fact) zi = Z[j] + A.o.reg_prim + Gam[2 * nb + j];
             for (int i = 0; i < nb; i++)
                 if (rev[i] == jj)
                 {
@@ -433,13 +529,17 @@ struct Ker
     }
 
     // ---------------------------------------------------------------------------------------------
-    // 4-column panel of the left-looking Cholesky: x[m][0..3] hold the raw (updated) entries of columns j0..j0+3 of
-    // this lane's rows; the 4 x 4 diagonal block is published through DD, factorised redundantly by every lane (pivot
-    // rule blasfeo_ref/x_lapack_ref.c:84-91: a non-positive pivot gives a zero column), the rows below are scaled.
-    // Results stay in x, go to ML (final columns of L) and to the work record (lower part; row n -> lrow).
+    // 4-column panel of the left-looking Cholesky: x[m][xo..xo+3] hold the raw (updated) entries of columns j0..j0+3 of
+    // this lane's rows, hh[m] the gradient entries of those rows.  The 4 x 4 diagonal block and the 4 gradient entries are
+    // published through DD, the block is factorised redundantly by every lane (pivot rule blasfeo_ref/x_lapack_ref.c:84-91:
+    // a non-positive pivot gives a zero column), the rows below are scaled; the gradient takes one step of the forward
+    // substitution l = L^{-1} h (its entries j0..j0+3 become final, the entries of the rows below are updated).
+    // Results: x (kept for the update of the second half of the tile), ML (final columns of L), the work record (lower
+    // part), lvec / lrow (gradient), Linv.
     // ---------------------------------------------------------------------------------------------
     template <int n, int RP, int W4>
-    FK_DEV void panel4(int j0, int m0, double (&x)[RPM][8], int xo, double *Lg, double *lrow, double *Linv)
+    FK_DEV void panel4(int j0, int m0, double (&x)[RPM > 0 ? RPM : 1][8], int xo, double (&hh)[RPM > 0 ? RPM : 1], double *Lg, double *lrow,
+                       double *lvec, double *Linv)
     {
 #pragma unroll
         for (int m = 0; m < RP; m++)
@@ -450,13 +550,15 @@ struct Ker
             {
 #pragma unroll
                 for (int q = 0; q < W4; q++) DD[rr + 4 * q] = x[m][xo + q];
+                DD[16 + rr] = hh[m];
             }
         }
         fk_sync();
         double d00 = DD[0], d10 = 0, d20 = 0, d30 = 0, d11 = 0, d21 = 0, d31 = 0, d22 = 0, d32 = 0, d33 = 0;
-        if (W4 > 1) { d10 = DD[1]; d11 = DD[5]; }
-        if (W4 > 2) { d20 = DD[2]; d21 = DD[6]; d22 = DD[10]; }
-        if (W4 > 3) { d30 = DD[3]; d31 = DD[7]; d32 = DD[11]; d33 = DD[15]; }
+        double h0 = DD[16], h1 = 0, h2 = 0, h3 = 0;
+        if (W4 > 1) { d10 = DD[1]; d11 = DD[5]; h1 = DD[17]; }
+        if (W4 > 2) { d20 = DD[2]; d21 = DD[6]; d22 = DD[10]; h2 = DD[18]; }
+        if (W4 > 3) { d30 = DD[3]; d31 = DD[7]; d32 = DD[11]; d33 = DD[15]; h3 = DD[19]; }
         const double i0 = d00 > 0.0 ? fk_rsqrt(d00) : 0.0;
         const double l10 = d10 * i0, l20 = d20 * i0, l30 = d30 * i0;
         d11 -= l10 * l10;
@@ -467,6 +569,11 @@ struct Ker
         const double l32 = (d32 - l30 * l20 - l31 * l21) * i2;
         d33 -= l30 * l30 + l31 * l31 + l32 * l32;
         const double i3 = d33 > 0.0 ? fk_rsqrt(d33) : 0.0;
+        // gradient entries of the block
+        const double g0 = h0 * i0;
+        const double g1 = W4 > 1 ? (h1 - l10 * g0) * i1 : 0.0;
+        const double g2 = W4 > 2 ? (h2 - l20 * g0 - l21 * g1) * i2 : 0.0;
+        const double g3 = W4 > 3 ? (h3 - l30 * g0 - l31 * g1 - l32 * g2) * i3 : 0.0;
 #pragma unroll
         for (int m = 0; m < RP; m++)
         {
@@ -481,7 +588,8 @@ struct Ker
             if (W4 > 1) x[m][xo + 1] = x1;
             if (W4 > 2) x[m][xo + 2] = x2;
             if (W4 > 3) x[m][xo + 3] = x3;
-            if (rr >= 0 && r <= n)
+            if (rr >= W4) hh[m] -= x0 * g0 + x1 * g1 + x2 * g2 + x3 * g3;
+            if (rr >= 0 && r < n)
             {
                 double *mr = ML + r + LD * j0;
                 mr[0] = x0;
@@ -490,69 +598,65 @@ struct Ker
                 if (W4 > 3) mr[3 * LD] = x3;
                 if (act)
                 {
-                    if (r < n)
-                    {
-                        double *gr = Lg + r + n * j0;
-                        gr[0] = x0;
-                        if (W4 > 1 && rr >= 1) gr[n] = x1;
-                        if (W4 > 2 && rr >= 2) gr[2 * n] = x2;
-                        if (W4 > 3 && rr >= 3) gr[3 * n] = x3;
-                    }
-                    else
-                    {
-                        lrow[j0] = x0;
-                        if (W4 > 1) lrow[j0 + 1] = x1;
-                        if (W4 > 2) lrow[j0 + 2] = x2;
-                        if (W4 > 3) lrow[j0 + 3] = x3;
-                    }
+                    double *gr = Lg + r + n * j0;
+                    gr[0] = x0;
+                    if (W4 > 1 && rr >= 1) gr[n] = x1;
+                    if (W4 > 2 && rr >= 2) gr[2 * n] = x2;
+                    if (W4 > 3 && rr >= 3) gr[3 * n] = x3;
                 }
             }
         }
         if (li == 0)
         {
-            Linv[j0] = i0;
-            if (W4 > 1) Linv[j0 + 1] = i1;
-            if (W4 > 2) Linv[j0 + 2] = i2;
-            if (W4 > 3) Linv[j0 + 3] = i3;
+            Linv[j0] = i0; lvec[j0] = g0;
+            if (W4 > 1) { Linv[j0 + 1] = i1; lvec[j0 + 1] = g1; }
+            if (W4 > 2) { Linv[j0 + 2] = i2; lvec[j0 + 2] = g2; }
+            if (W4 > 3) { Linv[j0 + 3] = i3; lvec[j0 + 3] = g3; }
+            if (act)
+            {
+                lrow[j0] = g0;
+                if (W4 > 1) lrow[j0 + 1] = g1;
+                if (W4 > 2) lrow[j0 + 2] = g2;
+                if (W4 > 3) lrow[j0 + 3] = g3;
+            }
         }
         fk_sync();
     }
 
     // ---------------------------------------------------------------------------------------------
     // one stage of the backward Riccati sweep with factorisation (OCP_QP_FACT_SOLVE_KKT_STEP, x_ocp_qp_kkt.c:880-966),
-    // right-hand side = residual set 0.  ML holds L_{k+1} (row n1 = its gradient row) on entry and L_k on exit.
-    //   [A; b'] -> MA, in place  AL = [A; b'] * Lxx_{k+1}                              (TRMM_RLNN)
+    // right-hand side = residual set 0.  ML holds L_{k+1} on entry and L_k on exit, lprev the x part of the gradient
+    // vector of stage k+1.
+    //   A -> MA (bulk copy), in place  AL = A * Lxx_{k+1}                               (TRMM_RLNN)
+    //   gradient:  alb = Lxx' b + l_{k+1,x},  h = g + AL alb                             (the (n+1)-th row of the reference's block)
     //   8-column tiles:  acc = H + diag + AL AL' - (columns already factorised)         (SYRK + left-looking POTRF)
     // ---------------------------------------------------------------------------------------------
     template <int KIND>
     FK_DEV void fact_stage(int k)
     {
         constexpr int nx = KD<KIND>::nx, nu = KD<KIND>::nu, n = nx + nu, nx1 = KD<KIND>::nx1;
-        constexpr int RP = (n + 1 + G - 1) / G;
+        constexpr int RP = (n + G - 1) / G, CP = (nx1 + G - 1) / G;
         const StageDesc &sd = sdk<KIND>();
         const View v = view<KIND>(k);
         const int nb = sd.nb, ns = sd.ns, nc = sd.nc;
         const int *idxb = v.ip + sd.idx_off, *rev = idxb + nb;
-        const int nu1 = (nx1 > 0 && k + 1 < A.N) ? NU : 0, n1 = nx1 + nu1;
-        double *Gam = V, *gam = Gam + A.nce, *tmp0 = gam + A.nce, *tmp1 = tmp0 + A.nbe;
-        double *dadd = tmp1 + A.nbe, *rowv = dadd + evn(NM + 1), *Linv = rowv + evn(NM + 1);
-        double *Zi = Linv + evn(NM + 1), *ds = Zi + A.ns2e, *lnx = ds + A.ns2e;
-        // ---- stage inputs: [A; b'] into MA (asynchronous), gradient, constraint quantities
-        if (nx1 > 0)
-        {
-            stage_mat<n, nx1>(MA, v.q + sd.q_BAt);
-            const double *b_ = v.w + sd.res.b;
-            for (int j = li; j < nx1; j += G) fk_cp8(MA + n + LD * j, b_ + j);
-            // gradient row of L_{k+1} (x part) before ML is overwritten
-            for (int j = li; j < nx1; j += G) lnx[j] = ML[n1 + LD * (nu1 + j)];
-        }
-        {
-            const double *g0 = v.w + sd.res.g;
-            for (int i = li; i < n; i += G) { rowv[i] = g0[i]; dadd[i] = A.o.reg_prim; }
-        }
+        const int nu1 = (nx1 > 0 && k + 1 < A.N) ? NU : 0;
+        const int resN = (int) (sd.res.m - sd.res.g) + evn(nc), ltN = (int) (sd.sol.t - sd.sol.lam) + evn(nc);
+        double *RES = V, *LT = RES + (A.nve + NXe + 2 * A.nce), *ZQ = LT + 2 * A.nce, *Gam = ZQ + A.ns2e, *gam = Gam + A.nce;
+        double *tmp0 = gam + A.nce, *tmp1 = tmp0 + A.nbe, *dadd = tmp1 + A.nbe, *Linv = dadd + NMe, *Zi = Linv + NMe, *ds = Zi + A.ns2e;
+        double *alb = ds + A.ns2e, *lvec = alb + NXe, *lprev = lvec + NMe;
+        stage_begin();
+        bulk<2, 0>(voff(RES), (size_t) v.kk * A.ws + sd.res.g, resN);
+        bulk<1, 0>(voff(LT), (size_t) v.kk * A.ss + sd.sol.lam, ltN);
+        if (ns > 0) bulk<0, 0>(voff(ZQ), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kV[KIND] + (sd.q_Z - sd.q_b), evn(2 * ns));
+        if (nx1 > 0) bulk<0, 1>(voff(MA), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs, evn(LD * nx1));
+        stage_arm();
+        wait_vec();
+        double *rowv = RES;
+        const double *rb = RES + (sd.res.b - sd.res.g), *rd = RES + (sd.res.d - sd.res.g), *rm = RES + (sd.res.m - sd.res.g);
+        const double *gl = LT, *gt = LT + (sd.sol.t - sd.sol.lam);
         {
             // Gamma, gamma (COMPUTE_GAMMA_GAMMA_QP, x_core_qp_ipm_aux.c:38-86)
-            const double *gl = v.s + sd.sol.lam, *gt = v.s + sd.sol.t, *grd = v.w + sd.res.d, *grm = v.w + sd.res.m;
             const double t_min_inv = A.o.t_min > 0 ? 1.0 / A.o.t_min : 1e30;
             for (int i = li; i < nc; i += G)
             {
@@ -561,13 +665,14 @@ struct Ker
                     Gam[i] = (tt < A.o.t_min ? t_min_inv : ti) * (l < A.o.lam_min ? A.o.lam_min : l);
                 else
                     Gam[i] = ti * l;
-                gam[i] = ti * (grm[i] - l * grd[i]);
+                gam[i] = ti * (rm[i] - l * rd[i]);
             }
+            for (int i = li; i < n; i += G) dadd[i] = A.o.reg_prim;
         }
         fk_sync();
         if (ns > 0)
         {
-            cond_slacks(nb, ns, rev, v.q + sd.q_Z, 1, Gam, gam, v.w + sd.res.g + n, Zi, ds, tmp0, tmp1);
+            cond_slacks(nb, ns, rev, ZQ, 1, Gam, gam, rowv + n, Zi, ds, tmp0, tmp1);
             fk_sync();
             for (int j = li; j < 2 * ns; j += G)
             {
@@ -590,17 +695,54 @@ struct Ker
             dadd[ix] += tmp0[i];
             rowv[ix] += tmp1[i];
         }
-        fk_cp_wait();
+        wait_mat();
         fk_sync();
+        double hh[RPM > 0 ? RPM : 1];
+#pragma unroll
+        for (int m = 0; m < RP; m++) hh[m] = rowv[(li + G * m) < n ? li + G * m : 0];
         if (nx1 > 0)
         {
-            // ---- in place: AL = [A; b'] * Lxx   (row slots x 8-column tiles; Lxx(c, j) = Lx[c + LD*j], lower triangular)
-            const double *Lx = ML + nu1 + LD * nu1;
+            const double *Lx = ML + nu1 + LD * nu1;                 // Lxx(c, j) = Lx[c + LD*j], lower triangular
+            // ---- gradient: alb = Lxx' b (lane = column), Pb = Lxx alb (lane = row), then alb += l_{k+1,x}
+#pragma unroll
+            for (int m = 0; m < CP; m++)
+            {
+                const int j = li + G * m;
+                if (j < nx1)
+                {
+                    double s0 = 0.0, s1 = 0.0;
+                    const double *lcol = Lx + LD * j;
+                    int c = j;
+                    for (; c + 1 < nx1; c += 2) { s0 += lcol[c] * rb[c]; s1 += lcol[c + 1] * rb[c + 1]; }
+                    if (c < nx1) s0 += lcol[c] * rb[c];
+                    alb[j] = s0 + s1;
+                }
+            }
+            fk_sync();
+            {
+                double *Pb = v.w + sd.w_Pb;
+#pragma unroll
+                for (int m = 0; m < CP; m++)
+                {
+                    const int i = li + G * m;
+                    if (i < nx1)
+                    {
+                        double s0 = 0.0, s1 = 0.0;
+                        int c = 0;
+                        for (; c + 1 <= i; c += 2) { s0 += Lx[i + LD * c] * alb[c]; s1 += Lx[i + LD * (c + 1)] * alb[c + 1]; }
+                        if (c <= i) s0 += Lx[i + LD * c] * alb[c];
+                        st(Pb + i, s0 + s1);
+                    }
+                }
+            }
+            fk_sync();
+            for (int j = li; j < nx1; j += G) alb[j] += lprev[j];
+            // ---- in place: AL = A * Lxx   (row slots x 8-column tiles)
 #pragma unroll
             for (int jt = 0; jt < nx1; jt += 8)
             {
                 const int w = nx1 - jt < 8 ? nx1 - jt : 8;
-                double acc[RPM][8];
+                double acc[RPM > 0 ? RPM : 1][8];
 #pragma unroll
                 for (int m = 0; m < RP; m++)
 #pragma unroll
@@ -611,9 +753,9 @@ struct Ker
                 {
                     if (h >= w) continue;
                     const int c = jt + h;
-                    double a[RPM];
+                    double a[RPM > 0 ? RPM : 1];
 #pragma unroll
-                    for (int m = 0; m < RP; m++) a[m] = MA[li + G * m + LD * c];
+                    for (int m = 0; m < RP; m++) a[m] = MA[(li + G * m < n ? li + G * m : 0) + LD * c];
 #pragma unroll
                     for (int q = 0; q <= h; q++)
                     {
@@ -625,9 +767,9 @@ struct Ker
 #pragma unroll 2
                 for (int c = jt + 8; c < nx1; c++)
                 {
-                    double a[RPM];
+                    double a[RPM > 0 ? RPM : 1];
 #pragma unroll
-                    for (int m = 0; m < RP; m++) a[m] = MA[li + G * m + LD * c];
+                    for (int m = 0; m < RP; m++) a[m] = MA[(li + G * m < n ? li + G * m : 0) + LD * c];
 #pragma unroll
                     for (int q = 0; q < 8; q++)
                     {
@@ -640,7 +782,7 @@ struct Ker
                 for (int m = 0; m < RP; m++)
                 {
                     const int r = li + G * m;
-                    if (r <= n)
+                    if (r < n)
                     {
 #pragma unroll
                         for (int q = 0; q < 8; q++)
@@ -649,32 +791,17 @@ struct Ker
                 }
             }
             fk_sync();
-            // Pb = Lxx * (Lxx' b)  (row n of AL is Lxx' b at this point), then the gradient row gets l_{k+1}
-            {
-                double *Pb = v.w + sd.w_Pb;
-                for (int i = li; i < nx1; i += G)
-                {
-                    double s0 = 0.0, s1 = 0.0;
-                    int c = 0;
-                    for (; c + 1 <= i; c += 2) { s0 += Lx[i + LD * c] * MA[n + LD * c]; s1 += Lx[i + LD * (c + 1)] * MA[n + LD * (c + 1)]; }
-                    if (c <= i) s0 += Lx[i + LD * c] * MA[n + LD * c];
-                    st(Pb + i, s0 + s1);
-                }
-            }
-            fk_sync();
-            for (int j = li; j < nx1; j += G) MA[n + LD * j] += lnx[j];
-            fk_sync();
         }
-        // ---- column tiles: SYRK + left-looking Cholesky, rows r >= jt (row n = gradient row)
-        const double *Hg = v.q + sd.q_RSQ;
+        // ---- column tiles: SYRK + left-looking Cholesky, rows r >= jt; gradient h = g + AL alb in the first tile
+        const double *Hk = v.k + A.kH[KIND];
         double *Lg = v.w + sd.w_L, *lrow = v.w + sd.w_lrow;
 #pragma unroll
         for (int jt = 0; jt < n; jt += 8)
         {
             const int w = n - jt < 8 ? n - jt : 8;
             const int m0 = jt / G;                      // first row slot that reaches into the tile
-            double acc[RPM][8], h[RPM][8];
-            // H (lower, from global; issued first so that the loads overlap the products), diagonal additions, gradient
+            double acc[RPM > 0 ? RPM : 1][8], h[RPM > 0 ? RPM : 1][8];
+            // H (lower; issued first so that the loads overlap the products)
 #pragma unroll
             for (int m = 0; m < RP; m++)
             {
@@ -684,14 +811,7 @@ struct Ker
                 for (int q = 0; q < 8; q++)
                 {
                     acc[m][q] = 0.0;
-                    double hv = 0.0;
-                    if (q < w)
-                    {
-                        if (r < n) { if (r >= jt + q) hv = fk_ldg(Hg + r + n * (jt + q)); }
-                        else if (r == n) hv = rowv[jt + q];
-                        if (r == jt + q) hv += dadd[r];
-                    }
-                    h[m][q] = hv;
+                    h[m][q] = (q < w && r < n && r >= jt + q) ? fk_ldg(Hk + r + LD * (jt + q)) : 0.0;
                 }
             }
             if (nx1 > 0)
@@ -699,9 +819,9 @@ struct Ker
 #pragma unroll 3
                 for (int c = 0; c < nx1; c++)
                 {
-                    double a[RPM], b[8];
+                    double a[RPM > 0 ? RPM : 1], b[8];
 #pragma unroll
-                    for (int m = 0; m < RP; m++) a[m] = m >= m0 ? MA[li + G * m + LD * c] : 0.0;
+                    for (int m = 0; m < RP; m++) a[m] = m >= m0 ? MA[(li + G * m < n ? li + G * m : 0) + LD * c] : 0.0;
 #pragma unroll
                     for (int q = 0; q < 8; q++) b[q] = q < w ? MA[jt + q + LD * c] : 0.0;
 #pragma unroll
@@ -709,14 +829,20 @@ struct Ker
                         if (m >= m0)
 #pragma unroll
                             for (int q = 0; q < 8; q++) acc[m][q] += a[m] * b[q];
+                    if (jt == 0)
+                    {
+                        const double ab = alb[c];
+#pragma unroll
+                        for (int m = 0; m < RP; m++) hh[m] += a[m] * ab;
+                    }
                 }
             }
 #pragma unroll 2
             for (int c = 0; c < jt; c++)
             {
-                double a[RPM], b[8];
+                double a[RPM > 0 ? RPM : 1], b[8];
 #pragma unroll
-                for (int m = 0; m < RP; m++) a[m] = m >= m0 ? ML[li + G * m + LD * c] : 0.0;
+                for (int m = 0; m < RP; m++) a[m] = m >= m0 ? ML[(li + G * m < n ? li + G * m : 0) + LD * c] : 0.0;
 #pragma unroll
                 for (int q = 0; q < 8; q++) b[q] = q < w ? ML[jt + q + LD * c] : 0.0;
 #pragma unroll
@@ -728,13 +854,20 @@ struct Ker
 #pragma unroll
             for (int m = 0; m < RP; m++)
                 if (m >= m0)
+                {
+                    const int r = li + G * m;
 #pragma unroll
-                    for (int q = 0; q < 8; q++) acc[m][q] += h[m][q];
+                    for (int q = 0; q < 8; q++)
+                    {
+                        acc[m][q] += h[m][q];
+                        if (q < w && r == jt + q) acc[m][q] += dadd[r < n ? r : 0];
+                    }
+                }
             // ---- first half of the tile
-            if (w >= 4) panel4<n, RP, 4>(jt, m0, acc, 0, Lg, lrow, Linv);
-            else if (w == 3) panel4<n, RP, 3>(jt, m0, acc, 0, Lg, lrow, Linv);
-            else if (w == 2) panel4<n, RP, 2>(jt, m0, acc, 0, Lg, lrow, Linv);
-            else panel4<n, RP, 1>(jt, m0, acc, 0, Lg, lrow, Linv);
+            if (w >= 4) panel4<n, RP, 4>(jt, m0, acc, 0, hh, Lg, lrow, lvec, Linv);
+            else if (w == 3) panel4<n, RP, 3>(jt, m0, acc, 0, hh, Lg, lrow, lvec, Linv);
+            else if (w == 2) panel4<n, RP, 2>(jt, m0, acc, 0, hh, Lg, lrow, lvec, Linv);
+            else panel4<n, RP, 1>(jt, m0, acc, 0, hh, Lg, lrow, lvec, Linv);
             if (w > 4)
             {
                 // ---- second half: update with the four columns just finished, then its own panel
@@ -751,22 +884,21 @@ struct Ker
 #pragma unroll
                             for (int q = 0; q < 4; q++) acc[m][4 + q] -= acc[m][c] * b[q];
                 }
-                if (w >= 8) panel4<n, RP, 4>(jt + 4, m1, acc, 4, Lg, lrow, Linv);
-                else if (w == 7) panel4<n, RP, 3>(jt + 4, m1, acc, 4, Lg, lrow, Linv);
-                else if (w == 6) panel4<n, RP, 2>(jt + 4, m1, acc, 4, Lg, lrow, Linv);
-                else panel4<n, RP, 1>(jt + 4, m1, acc, 4, Lg, lrow, Linv);
+                if (w >= 8) panel4<n, RP, 4>(jt + 4, m1, acc, 4, hh, Lg, lrow, lvec, Linv);
+                else if (w == 7) panel4<n, RP, 3>(jt + 4, m1, acc, 4, hh, Lg, lrow, lvec, Linv);
+                else if (w == 6) panel4<n, RP, 2>(jt + 4, m1, acc, 4, hh, Lg, lrow, lvec, Linv);
+                else panel4<n, RP, 1>(jt + 4, m1, acc, 4, hh, Lg, lrow, lvec, Linv);
             }
         }
         {
             double *li_ = v.w + sd.w_Linv;
             for (int j = li; j < n; j += G) st(li_ + j, Linv[j]);
+            for (int j = li; j < nx; j += G) lprev[j] = lvec[nu + j];
         }
-        fk_sync();
     }
 
     FK_DEV void fact_backward()
     {
-        fk_sync();
         fact_stage<2>(A.N);
         for (int k = A.N - 1; k >= 1; k--) fact_stage<1>(k);
         fact_stage<0>(0);
@@ -783,46 +915,51 @@ struct Ker
     {
         constexpr int nx = KD<KIND>::nx, nu = KD<KIND>::nu, n = nx + nu, nx1 = KD<KIND>::nx1;
         constexpr int nsolve = nu;                  // stage 0 has nx = 0: n = nu
+        constexpr int RP = (n + G - 1) / G;
         const StageDesc &sd = sdk<KIND>();
         const View v = view<KIND>(k);
         const int nb = sd.nb, ns = sd.ns, nc = sd.nc;
         const int *idxb = v.ip + sd.idx_off, *rev = idxb + nb;
-        double *vv = V, *gam = vv + A.nve, *Gam = gam + A.nce, *tmp0 = Gam + A.nce, *tmp1 = tmp0 + A.nbe;
-        double *Zi = tmp1 + A.nbe, *ds = Zi + A.ns2e, *xprev = ds + A.ns2e, *tmpx = xprev + evn(NX);
-        double *Lis = tmpx + evn(NX), *pbs = Lis + evn(NM + 1);
+        const int resN = (int) (sd.res.m - sd.res.g) + evn(nc), ltN = (int) (sd.sol.t - sd.sol.lam) + evn(nc);
+        const int fvN = (int) (sd.w_Zsi - sd.w_Linv) + evn(2 * ns), stN = (int) (sd.step.t - sd.step.lam) + evn(nc);
+        const int qmN = (int) (sd.q_Z - sd.q_dmask) + evn(2 * ns);
+        double *RES = V, *LT = RES + (A.nve + NXe + 2 * A.nce), *FV = LT + 2 * A.nce, *RMB = FV + (2 * NMe + NXe + A.ns2e), *STL = RMB + A.nce;
+        double *QM = STL + 2 * A.nce, *Gam = QM + (A.nce + A.ns2e), *gam = Gam + A.nce, *tmp0 = gam + A.nce, *tmp1 = tmp0 + A.nbe;
+        double *ds = tmp1 + A.nbe, *xprev = ds + A.ns2e, *tmpx = xprev + NXe;
         const bool so = act && stw;
-        if (nx1 > 0) stage_mat<n, nx1>(MA, v.q + sd.q_BAt);
+        stage_begin();
+        bulk<2, 0>(voff(RES), (size_t) v.kk * A.ws + sd.res.g, resN);
+        bulk<1, 0>(voff(LT), (size_t) v.kk * A.ss + sd.sol.lam, ltN);
+        bulk<2, 0>(voff(FV), (size_t) v.kk * A.ws + sd.w_Linv, fvN);
+        bulk<2, 0>(voff(RMB), (size_t) v.kk * A.ws + sd.w_rmb, evn(nc));
+        bulk<2, 0>(voff(STL), (size_t) v.kk * A.ws + sd.step.lam, stN);
+        bulk<0, 0>(voff(QM), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kV[KIND] + (sd.q_dmask - sd.q_b), qmN);
+        if (nx1 > 0) bulk<0, 1>(voff(MA), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs, evn(LD * nx1));
+        if (nsolve > 0) bulk<2, 1>(voff(LU), (size_t) v.kk * A.ws + sd.w_L, evn(n * nsolve));
+        stage_arm();
+        wait_vec();
+        double *vv = RES;
+        const double *rd = RES + (sd.res.d - sd.res.g), *gl = LT, *gt = LT + (sd.sol.t - sd.sol.lam);
+        const double *Lis = FV, *pbs = FV + (sd.w_Pb - sd.w_Linv), *Zi = FV + (sd.w_Zsi - sd.w_Linv);
+        const double *dl = STL, *dtt = STL + (sd.step.t - sd.step.lam), *gm = QM, *qZ = QM + (sd.q_Z - sd.q_dmask);
         {
-            const double *Lg = v.w + sd.w_L;
-            for (int e = li; e < n * nsolve; e += G)
-            {
-                const int c = e / (n > 0 ? n : 1), r = e - c * n;
-                fk_cp8(LU + r + LD * c, Lg + e);
-            }
-            const double *g0 = v.w + sd.res.g, *Li = v.w + sd.w_Linv, *zs = v.w + sd.w_Zsi, *pb = v.w + sd.w_Pb;
-            for (int i = li; i < n; i += G) vv[i] = g0[i];
-            for (int i = li; i < nsolve; i += G) Lis[i] = Li[i];
-            for (int j = li; j < 2 * ns; j += G) Zi[j] = zs[j];
-            for (int j = li; j < nx1; j += G) pbs[j] = pb[j];
-            const double *gl = v.s + sd.sol.lam, *gt = v.s + sd.sol.t, *grd = v.w + sd.res.d, *gm = v.q + sd.q_dmask;
             double *grm = v.w + sd.res.m;
-            const double *bk = v.w + sd.w_rmb, *dl = v.w + sd.step.lam, *dtt = v.w + sd.step.t;
             const double t_min_inv = A.o.t_min > 0 ? 1.0 / A.o.t_min : 1e30;
             for (int i = li; i < nc; i += G)
             {
                 const double l = gl[i], tt = gt[i], ti = 1.0 / tt;
-                double m = rm_mode == 1 ? bk[i] + dtt[i] * dl[i] - sigma_mu : bk[i] - sigma_mu;
-                m *= fk_ldg(gm + i);
+                double m = rm_mode == 1 ? RMB[i] + dtt[i] * dl[i] - sigma_mu : RMB[i] - sigma_mu;
+                m *= gm[i];
                 if (so) grm[i] = m;
                 // the slack elimination needs the Gamma of the factorisation (clipped when t_lam_min==1)
                 Gam[i] = (ns > 0 && A.o.t_lam_min == 1) ? (tt < A.o.t_min ? t_min_inv : ti) * (l < A.o.lam_min ? A.o.lam_min : l) : ti * l;
-                gam[i] = ti * (m - l * grd[i]);
+                gam[i] = ti * (m - l * rd[i]);
             }
         }
         fk_sync();
         if (ns > 0)
         {
-            cond_slacks(nb, ns, rev, v.q + sd.q_Z, 0, Gam, gam, v.w + sd.res.g + n, Zi, ds, tmp0, tmp1);
+            cond_slacks(nb, ns, rev, qZ, 0, Gam, gam, vv + n, const_cast<double *>(Zi), ds, tmp0, tmp1);
             fk_sync();
             double *o_ = v.w + sd.step.ux + n;
             for (int j = li; j < 2 * ns; j += G)
@@ -835,20 +972,21 @@ struct Ker
         }
         for (int i = li; i < nb; i += G) vv[idxb[i]] += tmp1[i];
         for (int j = li; j < nx1; j += G) tmpx[j] = xprev[j] + pbs[j];
-        fk_cp_wait();
+        wait_mat();
         fk_sync();
+        double x[RPM > 0 ? RPM : 1];
+#pragma unroll
+        for (int m = 0; m < RP; m++) x[m] = vv[(li + G * m) < n ? li + G * m : 0];
         if (nx1 > 0)
         {
-            for (int i = li; i < n; i += G)
-            {
-                double s0 = 0.0, s1 = 0.0;
-                const double *arow = MA + i;
-                int j = 0;
-#pragma unroll 4
-                for (; j + 1 < nx1; j += 2) { s0 += arow[LD * j] * tmpx[j]; s1 += arow[LD * (j + 1)] * tmpx[j + 1]; }
-                if (j < nx1) s0 += arow[LD * j] * tmpx[j];
-                vv[i] += s0 + s1;
-            }
+            double ap[RPM > 0 ? RPM : 1];
+            rows_dot<n, nx1>(MA, LD, tmpx, ap);
+#pragma unroll
+            for (int m = 0; m < RP; m++) x[m] += ap[m];
+            fk_sync();
+#pragma unroll
+            for (int m = 0; m < RP; m++)
+                if (li + G * m < nsolve) vv[li + G * m] = x[m];
             fk_sync();
         }
         // TRSV_LNN(_MN): forward substitution on the first nsolve unknowns (redundantly by every lane), then the rows below
@@ -859,37 +997,39 @@ struct Ker
             {
                 double part = 0.0;
 #pragma unroll
-                for (int c = 0; c < j; c++) part += LU[j + LD * c] * u[c];
+                for (int c = 0; c < j; c++) part += LU[j + n * c] * u[c];
                 u[j] = (vv[j] - part) * Lis[j];
             }
             fk_sync();
-            for (int i = li; i < n; i += G)
+#pragma unroll
+            for (int m = 0; m < RP; m++)
             {
-                double x = vv[i];
-                if (i < nsolve)
+                const int i = li + G * m;
+                if (i < n)
                 {
+                    double xi = x[m];
+                    if (i < nsolve)
+                    {
 #pragma unroll
-                    for (int j = 0; j < nsolve; j++)
-                        if (i == j) x = u[j];
-                }
-                else
-                {
-                    double part = 0.0;
+                        for (int j = 0; j < nsolve; j++)
+                            if (i == j) xi = u[j];
+                    }
+                    else
+                    {
+                        double part = 0.0;
 #pragma unroll
-                    for (int c = 0; c < nsolve; c++) part += LU[i + LD * c] * u[c];
-                    x -= part;
+                        for (int c = 0; c < nsolve; c++) part += LU[i + n * c] * u[c];
+                        xi -= part;
+                    }
+                    if (so) (v.w + sd.step.ux)[i] = xi;
+                    if (i >= nu) xprev[i - nu] = xi;
                 }
-                vv[i] = x;
-                if (so) (v.w + sd.step.ux)[i] = x;
-                if (i >= nu) xprev[i - nu] = x;
             }
         }
-        fk_sync();
     }
 
     FK_DEV void solve_backward(int rm_mode, double sigma_mu, bool stw)
     {
-        fk_sync();
         solve_stage<2>(A.N, rm_mode, sigma_mu, stw);
         for (int k = A.N - 1; k >= 1; k--) solve_stage<1>(k, rm_mode, sigma_mu, stw);
         solve_stage<0>(0, rm_mode, sigma_mu, stw);
@@ -901,6 +1041,7 @@ struct Ker
     // (COMPUTE_ALPHA_QP :375-398) + the residual of the linear system (OCP_QP_RES_COMPUTE_LIN) -> residual set 1.
     // after_fact: start from -lrow, pi = P x + p with p from lrow; else: start from the backward quantities stored in
     // the step, pi = p_backward + P x.
+    // ML first holds the Hessian (for the residual of the linear system), then the factor of the next stage.
     // ---------------------------------------------------------------------------------------------
     struct FwdAcc
     {
@@ -913,57 +1054,50 @@ struct Ker
     {
         constexpr int nx = KD<KIND>::nx, nu = KD<KIND>::nu, n = nx + nu, nx1 = KD<KIND>::nx1;
         constexpr int nsolve = nu;
+        constexpr int RP = (n + G - 1) / G, CP = (nx1 + G - 1) / G;
         const StageDesc &sd = sdk<KIND>();
         const View v = view<KIND>(k);
         const int nb = sd.nb, ns = sd.ns, nc = sd.nc;
         const int *idxb = v.ip + sd.idx_off, *rev = idxb + nb;
-        const int nu1 = (nx1 > 0 && k + 1 < A.N) ? NU : 0;
-        const int NXe = evn(NX);
-        double *vv = V, *x1 = vv + A.nve, *tmp = x1 + NXe, *p1 = tmp + NXe, *pik = p1 + NXe, *pim = pik + NXe;
-        double *Gam = pim + NXe, *dt = Gam + A.nce, *lam = dt + A.nce, *dlm = lam + A.nce;
-        double *Zi = dlm + A.nce, *ds = Zi + A.ns2e, *g_ = ds + A.ns2e, *tmp0 = g_ + A.nve;
-        double *Lis = tmp0 + A.nbe, *bs = Lis + evn(NM + 1), *ts = bs + NXe, *rds = ts + A.nce, *rms = rds + A.nce, *mks = rms + A.nce;
+        const int nu1 = (nx1 > 0 && k + 1 < A.N) ? NU : 0, n1 = nx1 + nu1, n1e = (n1 + 1) & ~1;
+        const int resN = (int) (sd.res.m - sd.res.g) + evn(nc), ltN = (int) (sd.sol.t - sd.sol.lam) + evn(nc);
+        const int fvN = (int) (sd.w_Zsi - sd.w_Linv) + evn(2 * ns), qmN = (int) (sd.q_Z - sd.q_dmask) + evn(2 * ns);
+        double *RES = V, *LT = RES + (A.nve + NXe + 2 * A.nce), *FV = LT + 2 * A.nce, *SUX = FV + (2 * NMe + NXe + A.ns2e), *P1 = SUX + A.nve;
+        double *QM = P1 + NMe, *vv = QM + (A.nce + A.ns2e), *x1 = vv + A.nve, *tg = x1 + NXe, *pik = tg + A.nve, *pim = pik + NXe;
+        double *dt = pim + NXe, *dlm = dt + A.nce, *dsv = dlm + A.nce, *tmp0 = dsv + A.ns2e;
+        double *tmp = tg, *g_ = tg;                 // tmp (Lxx' x) is dead when g_ (residual rows) is written
         const bool so = act && stw;
-        // ---- staging: BAt, first nsolve columns of L_k, L_{k+1}, vectors
+        View v1 = v;
+        const StageDesc *s1p = &sd;
+        if (nx1 > 0) { s1p = &sdr(k + 1); v1 = viewr(k + 1); }
+        stage_begin();
+        bulk<2, 0>(voff(RES), (size_t) v.kk * A.ws + sd.res.g, resN);
+        bulk<1, 0>(voff(LT), (size_t) v.kk * A.ss + sd.sol.lam, ltN);
+        bulk<2, 0>(voff(FV), (size_t) v.kk * A.ws + sd.w_Linv, fvN);
+        bulk<2, 0>(voff(SUX), (size_t) v.kk * A.ws + sd.step.ux, evn(n + 2 * ns));
+        bulk<0, 0>(voff(QM), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kV[KIND] + (sd.q_dmask - sd.q_b), qmN);
         if (nx1 > 0)
         {
-            stage_mat<n, nx1>(MA, v.q + sd.q_BAt);
-            const StageDesc &s1 = sdr(k + 1);
-            const View v1 = viewr(k + 1);
-            const double *L1 = v1.w + s1.w_L;
-            if (nu1 > 0) stage_mat<NX + NU, NX + NU>(ML, L1);
-            else stage_mat<NX, NX>(ML, L1);
-            const double *ps = after_fact ? v1.w + s1.w_lrow + nu1 : v1.w + s1.step.ux + nu1;   // p part / backward value of x_{k+1}
-            for (int j = li; j < nx1; j += G) p1[j] = ps[j];
-            const double *b_ = v.w + sd.res.b;
-            for (int j = li; j < nx1; j += G) bs[j] = b_[j];
+            // p part (gradient vector of stage k+1) / backward value of x_{k+1}
+            bulk<2, 0>(voff(P1), (size_t) v1.kk * A.ws + (after_fact ? s1p->w_lrow : s1p->step.ux), n1e);
+            bulk<0, 1>(voff(MA), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs, evn(LD * nx1));
         }
+        if (nsolve > 0) bulk<2, 1>(voff(LU), (size_t) v.kk * A.ws + sd.w_L, evn(n * nsolve));
+        if (do_lin) bulk<0, 1>(voff(ML), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kH[KIND], LD * n);
+        else if (nx1 > 0) bulk<2, 1>(voff(ML), (size_t) v1.kk * A.ws + s1p->w_L, evn(n1 * n1));
+        stage_arm();
+        wait_vec();
+        const double *gv = RES, *bs = RES + (sd.res.b - sd.res.g), *rds = RES + (sd.res.d - sd.res.g), *rms = RES + (sd.res.m - sd.res.g);
+        const double *lam = LT, *ts = LT + (sd.sol.t - sd.sol.lam);
+        const double *Lis = FV, *lrow_ = FV + (sd.w_lrow - sd.w_Linv), *Zi = FV + (sd.w_Zsi - sd.w_Linv);
+        const double *mks = QM, *qZ = QM + (sd.q_Z - sd.q_dmask);
         {
-            const double *Lg = v.w + sd.w_L;
-            for (int e = li; e < n * nsolve; e += G)
-            {
-                const int c = e / (n > 0 ? n : 1), r = e - c * n;
-                fk_cp8(LU + r + LD * c, Lg + e);
-            }
-            const double *src = after_fact ? v.w + sd.w_lrow : v.w + sd.step.ux, *Li = v.w + sd.w_Linv;
-            for (int i = li; i < nsolve; i += G) { vv[i] = -src[i]; Lis[i] = Li[i]; }
+            const double *src = after_fact ? lrow_ : SUX;
+            for (int i = li; i < nsolve; i += G) vv[i] = -src[i];
             // x part (k>0) was written into vv by the previous stage
-            if (ns > 0)
-            {
-                const double *z_ = v.w + sd.w_Zsi, *d_ = v.w + sd.step.ux + n;
-                for (int j = li; j < 2 * ns; j += G) { Zi[j] = z_[j]; ds[j] = d_[j]; }
-            }
-            const double *gl = v.s + sd.sol.lam, *gt = v.s + sd.sol.t, *grd = v.w + sd.res.d, *grm = v.w + sd.res.m, *gm = v.q + sd.q_dmask;
-            for (int i = li; i < nc; i += G)
-            {
-                lam[i] = gl[i];
-                ts[i] = gt[i];
-                rds[i] = grd[i];
-                rms[i] = grm[i];
-                mks[i] = fk_ldg(gm + i);
-            }
+            for (int j = li; j < 2 * ns; j += G) dsv[j] = SUX[n + j];
         }
-        fk_cp_wait();
+        wait_mat();
         fk_sync();
         // ---- TRSV_LTN(_MN): u = -Luu^{-T} (l_u + Lxu' x): the dot products over the x rows by the group, the small triangle
         // redundantly by every lane
@@ -974,7 +1108,7 @@ struct Ker
             for (int j = 0; j < nsolve; j++)
             {
                 double part = 0.0;
-                for (int i = nsolve + li; i < n; i += G) part += LU[i + LD * j] * vv[i];
+                for (int i = nsolve + li; i < n; i += G) part += LU[i + n * j] * vv[i];
                 if (n > nsolve) part = gsum(part);
                 wv[j] = vv[j] - part;
             }
@@ -983,7 +1117,7 @@ struct Ker
             {
                 double part = 0.0;
 #pragma unroll
-                for (int i = j + 1; i < nsolve; i++) part += LU[i + LD * j] * wv[i];
+                for (int i = j + 1; i < nsolve; i++) part += LU[i + n * j] * wv[i];
                 wv[j] = (wv[j] - part) * Lis[j];
             }
             fk_sync();
@@ -997,65 +1131,46 @@ struct Ker
             for (int i = li; i < n; i += G)
                 if (so) o_[i] = vv[i];
         }
+        // ---- H v (for the residual of the linear system) while ML holds the Hessian, then ML <- L_{k+1}
+        double hx[RPM > 0 ? RPM : 1];
+        if (do_lin)
+        {
+            rows_dot<n, n>(ML, LD, vv, hx);
+            if (nx1 > 0)
+            {
+                stage_begin();
+                bulk<2, 1>(voff(ML), (size_t) v1.kk * A.ws + s1p->w_L, evn(n1 * n1));
+                stage_arm_mat();
+            }
+        }
+        // ---- x+ = A' v + b
         if (nx1 > 0)
         {
-            const double *Lx = ML + nu1 + LD * nu1;                          // Lxx of stage k+1
+            double av[RPM > 0 ? RPM : 1];
+            cols_dot<n, nx1>(MA, LD, vv, av);
             double *ob = v.w + sd.ires.b;
-            for (int j = li; j < nx1; j += G)
+#pragma unroll
+            for (int m = 0; m < CP; m++)
             {
-                double s0 = 0.0, s1 = 0.0;
-                const double *acol = MA + LD * j;
-                int i = 0;
-#pragma unroll 4
-                for (; i + 1 < n; i += 2) { s0 += acol[i] * vv[i]; s1 += acol[i + 1] * vv[i + 1]; }
-                if (i < n) s0 += acol[i] * vv[i];
-                const double acc = s0 + s1, bv = bs[j];
-                const double xj = bv + acc;
-                x1[j] = xj;
-                if (do_lin)
+                const int j = li + G * m;
+                if (j < nx1)
                 {
-                    const double r = bv - xj + acc;
-                    if (so) ob[j] = r;
-                    const double a = fabs(r);
-                    F.m1 = fmax(F.m1, a);
-                    F.f1 |= (a != a);
+                    const double acc = av[m], bv = bs[j];
+                    const double xj = bv + acc;
+                    x1[j] = xj;
+                    if (do_lin)
+                    {
+                        const double r = bv - xj + acc;
+                        if (so) ob[j] = r;
+                        const double a = fabs(r);
+                        F.m1 = fmax(F.m1, a);
+                        F.f1 |= (a != a);
+                    }
                 }
-            }
-            fk_sync();
-            for (int j = li; j < nx1; j += G)
-            {
-                double s0 = 0.0, s1 = 0.0;
-                const double *lcol = Lx + LD * j;
-                int i = j;
-                for (; i + 1 < nx1; i += 2) { s0 += lcol[i] * x1[i]; s1 += lcol[i + 1] * x1[i + 1]; }
-                if (i < nx1) s0 += lcol[i] * x1[i];
-                const double acc = s0 + s1;
-                tmp[j] = after_fact ? acc + p1[j] : acc;
-            }
-            fk_sync();
-            double *pi = v.w + sd.step.pi;
-            for (int i = li; i < nx1; i += G)
-            {
-                double s0 = 0.0, s1 = 0.0;
-                const double *lrow_ = Lx + i;
-                int c = 0;
-                for (; c + 1 <= i; c += 2) { s0 += lrow_[LD * c] * tmp[c]; s1 += lrow_[LD * (c + 1)] * tmp[c + 1]; }
-                if (c <= i) s0 += lrow_[LD * c] * tmp[c];
-                const double acc = s0 + s1;
-                const double pv = after_fact ? acc : acc + p1[i];
-                if (so) pi[i] = pv;
-                pik[i] = pv;
             }
         }
         // ---- constraint part of the step at this stage
         {
-            const double t_min_inv = A.o.t_min > 0 ? 1.0 / A.o.t_min : 1e30;
-            for (int i = li; i < nc; i += G)
-            {
-                const double l = lam[i], tt = ts[i];
-                Gam[i] = (ns > 0 && A.o.t_lam_min == 1) ? (tt < A.o.t_min ? t_min_inv : 1.0 / tt) * (l < A.o.lam_min ? A.o.lam_min : l)
-                                                      : (1.0 / tt) * l;
-            }
             for (int i = li; i < nb; i += G)
             {
                 const double a = vv[idxb[i]];
@@ -1065,25 +1180,31 @@ struct Ker
             if (ns > 0)
             {
                 fk_sync();
+                const double t_min_inv = A.o.t_min > 0 ? 1.0 / A.o.t_min : 1e30;
                 for (int j = li; j < 2 * ns; j += G)
                 {
                     const int jj = j < ns ? j : j - ns, offc = j < ns ? 0 : nb;
-                    double d = ds[j];
+                    double d = dsv[j];
                     for (int i = 0; i < nb; i++)
-                        if (rev[i] == jj) d += Gam[offc + i] * dt[offc + i];
+                        if (rev[i] == jj)
+                        {
+                            const double l = lam[offc + i], tt = ts[offc + i];
+                            const double Gm = A.o.t_lam_min == 1 ? (tt < A.o.t_min ? t_min_inv : 1.0 / tt) * (l < A.o.lam_min ? A.o.lam_min : l) : (1.0 / tt) * l;
+                            d += Gm * dt[offc + i];
+                        }
                     d = -Zi[j] * d;
-                    ds[j] = d;
+                    dsv[j] = d;
                     dt[2 * nb + j] = d;
                 }
                 fk_sync();
                 for (int i = li; i < 2 * nb; i += G)
                 {
                     const int up = i >= nb, ii = up ? i - nb : i;
-                    if (rev[ii] >= 0) dt[i] += ds[(up ? ns : 0) + rev[ii]];
+                    if (rev[ii] >= 0) dt[i] += dsv[(up ? ns : 0) + rev[ii]];
                 }
                 double *o_ = v.w + sd.step.ux + n;
                 for (int j = li; j < 2 * ns; j += G)
-                    if (so) o_[j] = ds[j];
+                    if (so) o_[j] = dsv[j];
             }
             fk_sync();
             double *odl = v.w + sd.step.lam, *odt = v.w + sd.step.t, *ld_ = v.w + sd.ires.d, *lm_ = v.w + sd.ires.m;
@@ -1119,37 +1240,74 @@ struct Ker
                 }
             }
         }
+        // ---- pi = P x+ + p with the factor of the next stage
+        if (nx1 > 0)
+        {
+            if (do_lin) wait_mat();
+            fk_sync();
+            const double *Lx = ML + nu1 + n1 * nu1;                          // Lxx of stage k+1, leading dimension n1
+#pragma unroll
+            for (int m = 0; m < CP; m++)
+            {
+                const int j = li + G * m;
+                if (j < nx1)
+                {
+                    double s0 = 0.0, s1 = 0.0;
+                    const double *lcol = Lx + n1 * j;
+                    int i = j;
+                    for (; i + 1 < nx1; i += 2) { s0 += lcol[i] * x1[i]; s1 += lcol[i + 1] * x1[i + 1]; }
+                    if (i < nx1) s0 += lcol[i] * x1[i];
+                    const double acc = s0 + s1;
+                    tmp[j] = after_fact ? acc + P1[nu1 + j] : acc;
+                }
+            }
+            fk_sync();
+            double *pi = v.w + sd.step.pi;
+#pragma unroll
+            for (int m = 0; m < CP; m++)
+            {
+                const int i = li + G * m;
+                if (i < nx1)
+                {
+                    double s0 = 0.0, s1 = 0.0;
+                    const double *lr = Lx + i;
+                    int c = 0;
+                    for (; c + 1 <= i; c += 2) { s0 += lr[n1 * c] * tmp[c]; s1 += lr[n1 * (c + 1)] * tmp[c + 1]; }
+                    if (c <= i) s0 += lr[n1 * c] * tmp[c];
+                    const double acc = s0 + s1;
+                    const double pv = after_fact ? acc : acc + P1[nu1 + i];
+                    if (so) pi[i] = pv;
+                    pik[i] = pv;
+                }
+            }
+        }
         fk_sync();
         if (do_lin)
         {
             // ---- res_g of the linear system (lane = row): H dux + rhs_g - dpi_{k-1} + A dpi_k + constraint multipliers
-            const double *Hg = v.q + sd.q_RSQ, *gv = v.w + sd.res.g;
             for (int i = li; i < nb; i += G) tmp0[i] = dlm[nb + i] - dlm[i];
-            fk_sync();
-            for (int i = li; i < n; i += G)
+            double ap[RPM > 0 ? RPM : 1];
+            if (nx1 > 0) rows_dot<n, nx1>(MA, LD, pik, ap);
+#pragma unroll
+            for (int m = 0; m < RP; m++)
             {
-                double r = gdot_sym<n>(Hg, i, vv) + gv[i];
-                if (nx > 0 && i >= nu) r -= pim[i - nu];
-                if (nx1 > 0)
+                const int i = li + G * m;
+                if (i < n)
                 {
-                    double s0 = 0.0, s1 = 0.0;
-                    const double *arow = MA + i;
-                    int j = 0;
-#pragma unroll 4
-                    for (; j + 1 < nx1; j += 2) { s0 += arow[LD * j] * pik[j]; s1 += arow[LD * (j + 1)] * pik[j + 1]; }
-                    if (j < nx1) s0 += arow[LD * j] * pik[j];
-                    r += s0 + s1;
+                    double r = hx[m] + gv[i];
+                    if (nx > 0 && i >= nu) r -= pim[i - nu];
+                    if (nx1 > 0) r += ap[m];
+                    g_[i] = r;
                 }
-                g_[i] = r;
             }
             fk_sync();
             for (int i = li; i < nb; i += G) g_[idxb[i]] += tmp0[i];
             if (ns > 0)
             {
-                const double *Z = v.q + sd.q_Z, *zv = v.w + sd.res.g + n;
+                const double *zv = gv + n;
                 for (int j = li; j < 2 * ns; j += G)
                 {
-                    double r = fk_ldg(Z + j) * ds[j] + zv[j] - dlm[2 * nb + j];
+                    double r = qZ[j] * dsv[j] + zv[j] - dlm[2 * nb + j];
                     const int jj = j < ns ? j : j - ns, offl = j < ns ? 0 : nb;
                     for (int i = 0; i < nb; i++)
                         if (rev[i] == jj) r -= dlm[offl + i];
@@ -1175,7 +1333,6 @@ struct Ker
                 pim[j] = pik[j];
             }
         }
-        fk_sync();
     }
 
     // returns the step length; lin_nrm = inf-norms of the residual of the linear system (do_lin)
@@ -1185,7 +1342,6 @@ struct Ker
         F.alpha = 1.0;
         F.m0 = F.m1 = F.m2 = F.m3 = 0.0;
         F.f0 = F.f1 = F.f2 = F.f3 = 0;
-        fk_sync();
         fwd_stage<0>(0, after_fact, do_lin, stw, F);
         for (int k = 1; k < A.N; k++) fwd_stage<1>(k, after_fact, do_lin, stw, F);
         fwd_stage<2>(A.N, after_fact, do_lin, stw, F);
@@ -1313,8 +1469,6 @@ struct Ker
         fk_sync();
     }
 
-    double nc_mask_inv;
-
     // ---------------------------------------------------------------------------------------------
     // driver (OCP_QP_IPM_SOLVE x_ocp_qp_ipm.c:2684-3120 + OCP_QP_IPM_DELTA_STEP :2208-2682) for the QPs of this warp;
     // q = index of this group's QP (clamped to a valid one; valid = it exists)
@@ -1324,6 +1478,7 @@ struct Ker
         const int N = A.N;
         const int SM = CUIPM_STAT_M;
         qp = A.qp + (size_t) q * A.qp_stride;
+        qk = A.qpk + (size_t) q * A.qpk_stride;
         sol = A.sol + (size_t) q * A.sol_stride;
         wk = A.work + (size_t) q * A.work_stride;
         act = valid;
@@ -1474,14 +1629,15 @@ struct Ker
     }
 };
 
-// doubles of the per-QP vector pool the sweeps carve out of shared memory
+// doubles of the per-QP vector pool the sweeps carve out of shared memory (record images + scratch)
 inline int vector_pool_doubles(int NX, int NM, int nce, int nbe, int ns2e, int nve)
 {
     const int nxe = (NX + 1) & ~1, nme = (NM + 2) & ~1;
-    const int v_res = 2 * nve + 3 * nxe + 4 * nce + 2 * nbe;
-    const int v_fact = 2 * nce + 2 * nbe + 3 * nme + 2 * ns2e + nxe;
-    const int v_slv = nve + 2 * nce + 2 * nbe + 2 * ns2e + 2 * nxe + nme + nxe;
-    const int v_fwd = 2 * nve + 6 * nxe + 8 * nce + 2 * ns2e + nbe + nme;
+    const int img = nve + nxe + 2 * nce;                                  // image of a (ux|g, pi|b, lam|d, t|m) record range
+    const int v_res = 2 * img + 2 * nme + (nxe + nme + 2 * nce + 2 * ns2e) + 2 * nbe + nve + 2 * nxe;
+    const int v_fact = img + 2 * nce + ns2e + 2 * nce + 2 * nbe + 2 * nme + 2 * ns2e + nxe + nme + nxe;
+    const int v_slv = img + 2 * nce + (2 * nme + nxe + ns2e) + nce + 2 * nce + (nce + ns2e) + 2 * nce + 2 * nbe + ns2e + 2 * nxe;
+    const int v_fwd = img + 2 * nce + (2 * nme + nxe + ns2e) + nve + nme + (nce + ns2e) + nve + nxe + nve + 2 * nxe + 2 * nce + ns2e + nbe;
     const int v_init = nve + nce;
     int m = v_res;
     if (v_fact > m) m = v_fact;

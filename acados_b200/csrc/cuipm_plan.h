@@ -148,7 +148,46 @@ inline bool fast_plan(const std::vector<StageDesc> &sd, const ProbDesc &P, FastA
     F.qp_stride = P.qp_stride; F.sol_stride = P.sol_stride; F.work_stride = P.work_stride; F.w_bkp = P.w_bkp;
     auto e = [](int n) { return (n + 1) & ~1; };
     F.nce = e(P.ncmax); F.nbe = e(P.nbgmax); F.ns2e = e(2 * P.nsmax); F.nve = e(P.nvsmax);
+    // kernel-side record: leading dimension >= nu+nx+1, = 2 (mod 4): row and column accesses in shared memory are both
+    // bank-conflict free and every column starts on a 16-byte boundary
+    const int NM = a.nx + a.nu;
+    F.ld = ((NM + 2) / 4) * 4 + 2;
+    unsigned o = 0;
+    const StageDesc *three[3] = {&sd[0], &sd[1], &sd[N]};
+    unsigned size[3];
+    for (int t = 0; t < 3; t++)
+    {
+        const StageDesc &d = *three[t];
+        const unsigned szA = (unsigned) e(F.ld * d.nx1), szH = (unsigned) (F.ld * d.n);
+        const unsigned szV = (d.q_stage + (unsigned) (d.q_stage_bytes / sizeof(double))) - d.q_b;
+        F.kH[t] = szA; F.kV[t] = szA + szH;
+        size[t] = szA + szH + (unsigned) e((int) szV);
+    }
+    F.kq[0] = 0; F.kq[1] = size[0]; F.kqs = size[1]; F.kq[2] = size[0] + (unsigned) (N - 1) * size[1];
+    o = F.kq[2] + size[2];
+    F.qpk_stride = (size_t) e((int) o);
     return true;
+}
+
+// Caller's QP record -> kernel-side QP record of the throughput kernel (host version of the repack pass; the device version is
+// in cuipm_fast.cu): dynamics block with leading dimension F.ld, Hessian as a full symmetric matrix with leading dimension
+// F.ld, the vector part verbatim.
+inline void repack_host(const FastArgs &F, const std::vector<StageDesc> &sd, const double *qp, double *qpk)
+{
+    const int N = F.N, ld = F.ld;
+    for (int k = 0; k <= N; k++)
+    {
+        const StageDesc &d = sd[k];
+        const int kind = k == 0 ? 0 : (k == N ? 2 : 1);
+        double *o = qpk + F.kq[kind] + (kind == 1 ? (size_t) (k - 1) * F.kqs : 0);
+        for (int c = 0; c < d.nx1; c++)
+            for (int r = 0; r < d.n; r++) o[r + ld * c] = qp[d.q_BAt + r + d.n * c];
+        double *H = o + F.kH[kind];
+        for (int j = 0; j < d.n; j++)
+            for (int i = 0; i < d.n; i++) H[i + ld * j] = i >= j ? qp[d.q_RSQ + i + d.n * j] : qp[d.q_RSQ + j + d.n * i];
+        const unsigned nv = d.q_stage + (unsigned) (d.q_stage_bytes / sizeof(double)) - d.q_b;
+        for (unsigned i = 0; i < nv; i++) o[F.kV[kind] + i] = qp[d.q_b + i];
+    }
 }
 
 }  // namespace cuipm

@@ -17,13 +17,12 @@ static inline void fk_sync() { simt::sync(); }
 static inline double fk_shfl_xor(double v, int m) { return simt::shfl(v, simt::lane() ^ m); }
 static inline int fk_shfl_xor_i(int v, int m) { return simt::shfl_i(v, simt::lane() ^ m); }
 static inline bool fk_any(bool p) { return simt::ballot(p) != 0u; }
-static inline void fk_cp16(double *dst, const double *src)
-{
-    if (((size_t) dst & 15) || ((size_t) src & 15)) { std::fprintf(stderr, "fast_emul: misaligned 16-byte copy\n"); std::abort(); }
-    simt::cp_async(dst, src, 16);
-}
-static inline void fk_cp8(double *dst, const double *src) { simt::cp_async(dst, src, 8); }
-static inline void fk_cp_wait() { simt::cp_wait(); }
+typedef simt::MBar fk_mbar_t;
+static inline void fk_mbar_init(fk_mbar_t *b, int count) { simt::mbar_init(b, count); }
+static inline void fk_bulk(double *dst, const double *src, unsigned bytes, fk_mbar_t *b) { simt::bulk_copy(b, dst, src, (int) bytes); }
+static inline void fk_mbar_arrive_tx(fk_mbar_t *b, unsigned bytes) { simt::mbar_arrive_tx(b, (int) bytes); }
+static inline void fk_mbar_wait(fk_mbar_t *b, unsigned parity) { simt::mbar_wait(b, (int) parity); }
+static inline void fk_fence_async() {}
 static inline double fk_ldg(const double *p) { return *p; }
 static inline double fk_rsqrt(double x) { return 1.0 / std::sqrt(x); }
 static inline int fk_atomic_inc(int *p) { return (*p)++; }
@@ -53,8 +52,9 @@ int run(cuipm::FastArgs F, int order)
     for (int w = 0; w < nwarp; w++)
     {
         for (double &x : smem) x = std::nan("");      // uninitialised shared memory
+        simt::MBar bars[2];
         simt::run_warp([&]() {
-            K k(F, base);
+            K k(F, base, bars, w * K::QPW);
             int q = w * K::QPW + k.gq;
             const bool valid = q < F.nbatch;
             if (!valid) q = F.nbatch - 1;
@@ -86,6 +86,9 @@ extern "C" int fast_emul_solve(const cuipm_shape *sh, int nbatch, const double *
     F.ipool = ipool.data(); F.qp = qp; F.sol = sol; F.work = work.data(); F.info = info; F.stat = stat;
     F.redo_list = redo; F.redo_count = nredo; F.o = *opts;
     *nredo = 0;
+    std::vector<double> qpk((size_t) F.qpk_stride * nbatch, 0.0);
+    for (int i = 0; i < nbatch; i++) cuipm::repack_host(F, sd, qp + (size_t) i * P.qp_stride, qpk.data() + (size_t) i * F.qpk_stride);
+    F.qpk = qpk.data();
     const int nx = F.s1.nx, nu = F.s1.nu;
     int rc = -2;
 #define INST(NX_, NU_, G_) if (nx == NX_ && nu == NU_ && g == G_) rc = run<NX_, NU_, G_>(F, order);

@@ -38,6 +38,18 @@ struct Warp
     std::vector<PendingCopy> pend[NL];
     std::function<void()> body;
     long barriers = 0;
+    long events = 0;               // progress other than barriers (transaction barriers completing)
+};
+
+// emulation of an mbarrier with transaction count (bulk asynchronous copies): the copies are queued and performed by
+// the first lane that observes the completed phase, so that a lane reading a block before its wait sees stale data
+struct MBar
+{
+    int phase = 0;                 // parity of the phase being filled
+    long tx = 0;                   // bytes expected minus bytes announced by copies
+    int pending_arrivals = 1;
+    bool armed = false;
+    std::vector<PendingCopy> copies;
 };
 
 inline Warp *&cur_warp()
@@ -108,6 +120,34 @@ inline void cp_wait()
     w->pend[w->cur].clear();
 }
 
+inline void mbar_init(MBar *b, int count) { *b = MBar(); b->pending_arrivals = count; }
+inline void bulk_copy(MBar *b, void *dst, const void *src, int bytes)
+{
+    if (((size_t) dst & 15) || ((size_t) src & 15) || (bytes & 15)) { std::fprintf(stderr, "simt_emul: misaligned bulk copy\n"); std::abort(); }
+    b->copies.push_back({dst, src, bytes});
+    b->tx -= bytes;
+}
+// arrive (one of `count` arrivals) and expect `bytes` more bytes of copies
+inline void mbar_arrive_tx(MBar *b, int bytes)
+{
+    b->tx += bytes;
+    b->pending_arrivals--;
+    cur_warp()->events++;
+}
+// waits for the phase of parity `parity` to complete (all arrivals in, all announced bytes delivered)
+inline void mbar_wait(MBar *b, int parity)
+{
+    while (b->phase == parity && !(b->pending_arrivals == 0 && b->tx == 0)) yield_();
+    if (b->phase == parity)
+    {   // first lane to observe completion: deliver the data, open the next phase
+        for (const PendingCopy &c : b->copies) std::memcpy(c.dst, c.src, (size_t) c.bytes);
+        b->copies.clear();
+        b->phase ^= 1;
+        b->pending_arrivals = 1;
+        cur_warp()->events++;
+    }
+}
+
 inline void trampoline_()
 {
     Warp *w = cur_warp();
@@ -138,6 +178,7 @@ inline long run_warp(const std::function<void()> &body, int order = 0, size_t st
     {
         bool all = true;
         const int g0 = w.gen, a0 = w.arrived;
+        const long e0 = w.events;
         int ndone0 = 0;
         for (int i = 0; i < Warp::NL; i++) ndone0 += w.done[i];
         for (int s = 0; s < Warp::NL; s++)
@@ -151,7 +192,7 @@ inline long run_warp(const std::function<void()> &body, int order = 0, size_t st
         if (all) break;
         int ndone1 = 0;
         for (int i = 0; i < Warp::NL; i++) ndone1 += w.done[i];
-        if (w.gen == g0 && ndone1 == ndone0 && w.arrived == a0)
+        if (w.gen == g0 && ndone1 == ndone0 && w.arrived == a0 && w.events == e0)
         {
             std::fprintf(stderr, "simt_emul: no progress (divergent barrier: %d lanes wait, %d finished)\n", w.arrived, ndone1);
             std::abort();

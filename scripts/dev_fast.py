@@ -50,6 +50,20 @@ if __name__ == "__main__":
         sh = problems.random_shape(12, 8, 3, nbx=4, ns=2)
         parity(problems.random_qp(sh, 64, seed=5, mask_frac=0.3), "rand_soft_mask")
         parity(problems.chain_mass(64, N=40, seed=5), "c2 lq0", lq_fact=0)
+    if what == "ncu":
+        # one launch per kernel for a profiler: python scripts/dev_fast.py ncu <config> <batch>
+        cfg, nb = sys.argv[2], int(sys.argv[3])
+        b = problems.chain_mass(nb, N=40, seed=1234) if cfg == "c2" else problems.named_config(cfg, nb)
+        o = default_opts()
+        s = CuipmSolver(b.shape, nb)
+        d_qp = torch.from_numpy(b.qp).cuda()
+        d_sol = torch.zeros((nb, b.layout.sol_stride), dtype=torch.float64, device="cuda")
+        d_info = torch.zeros(nb * INFO_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+        s.solve_device(nb, d_qp.data_ptr(), d_sol.data_ptr(), d_info.data_ptr(), o, sync=True)
+        print("kernel ms", s.last_kernel_ms)
+        s.close()
+    if what == "time2":
+        timing(problems.chain_mass(4096, N=40, seed=1234), "c2")
     if what in ("all", "time"):
         timing(problems.chain_mass(4096, N=40, seed=1234), "c2")
         timing(problems.chain_mass(8192, N=40, seed=1234), "c2")
