@@ -73,12 +73,12 @@ static int build_desc(cuipm_solver *s, const cuipm_shape *sh)
     CK(cudaMalloc(&s->d_ipool, sizeof(int) * (ipool.size() + 1)));
     if (!ipool.empty()) CK(cudaMemcpy(s->d_ipool, ipool.data(), sizeof(int) * ipool.size(), cudaMemcpyHostToDevice));
     // throughput kernel: eligible shape with a compiled instance
-    s->fast_ok = fast_plan(s->sd_host, s->P, s->F) && fast_available(s->F.s1.nx, s->F.s1.nu, s->F, &s->fast_qpw);
+    s->fast_ok = fast_plan(s->sd_host, ipool, s->P, s->F) && fast_available(s->F.s1.nx, s->F.s1.nu, s->F, &s->fast_qpw);
     if (s->fast_ok)
     {
         CK(cudaMalloc(&s->d_redo_list, sizeof(int) * (size_t) s->max_batch));
-        CK(cudaMalloc(&s->d_redo_count, sizeof(int) * cuipm_solver::kPipe));
-        CK(cudaMemset(s->d_redo_count, 0, sizeof(int) * cuipm_solver::kPipe));
+        CK(cudaMalloc(&s->d_redo_count, sizeof(int) * 2 * cuipm_solver::kPipe));      // hand-back counter + work counter per chunk
+        CK(cudaMemset(s->d_redo_count, 0, sizeof(int) * 2 * cuipm_solver::kPipe));
         CK(cudaMalloc(&s->d_qpk, sizeof(double) * s->F.qpk_stride * (size_t) s->max_batch));
         CK(cudaMemset(s->d_qpk, 0, sizeof(double) * s->F.qpk_stride * (size_t) s->max_batch));
     }
@@ -99,8 +99,8 @@ static int launch_batch(cuipm_solver *s, const LaunchArgs &a0, int slot, size_t 
         FastArgs F = s->F;
         F.nbatch = a.nbatch; F.ipool = a.ipool; F.qp = a.qp; F.sol = a.sol; F.work = a.work; F.info = a.info; F.stat = a.stat;
         F.qpk = s->d_qpk + s->F.qpk_stride * lo;
-        F.redo_list = s->d_redo_list + lo; F.redo_count = s->d_redo_count + slot; F.o = o;
-        cudaError_t e = cudaMemsetAsync(F.redo_count, 0, sizeof(int), stream);
+        F.redo_list = s->d_redo_list + lo; F.redo_count = s->d_redo_count + 2 * slot; F.next_qp = F.redo_count + 1; F.o = o;
+        cudaError_t e = cudaMemsetAsync(F.redo_count, 0, 2 * sizeof(int), stream);
         if (e != cudaSuccess) { set_error(std::string("cudaMemsetAsync: ") + cudaGetErrorString(e)); return CUIPM_ERR_CUDA; }
         int rc = launch_repack(F, s->d_sd, (void *) stream);
         if (rc != 0) { set_error(std::string("kernel launch (repack): ") + cudaGetErrorString((cudaError_t) rc)); return CUIPM_ERR_CUDA; }

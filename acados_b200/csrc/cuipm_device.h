@@ -76,6 +76,7 @@ struct FastArgs
     int N, nbatch, nct;
     int nce, nbe, ns2e, nve;       // even-rounded maxima over the stages: constraints, bounds, 2*slacks, nu+nx+2*ns
     int is;                        // index-pool stride of the interior stages
+    int nmaps;                     // index maps kept in shared memory: 3 (stages 0, 1, N: interior stages share theirs) or N+1
     unsigned qs, ss, ws;           // strides (doubles) of an interior stage in the QP / solution / work record
     unsigned w_bkp;                // work record: lam, t of the iterate of the last factorisation (solution layout)
     int vsize;                     // doubles of the per-QP vector pool in shared memory
@@ -98,6 +99,7 @@ struct FastArgs
     double *stat;                  // may be null
     int *redo_list;                // QPs that need a cold path (LQ refactorisation, iterative refinement, no active constraint):
     int *redo_count;               //   handed to the generic kernel, which solves them from scratch
+    int *next_qp;                  // work counter of the persistent warps (zero at launch)
     cuipm_opts o;
 };
 

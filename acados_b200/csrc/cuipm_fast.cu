@@ -45,15 +45,25 @@ static __device__ __forceinline__ void fk_mbar_wait(fk_mbar_t *b, unsigned parit
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(ba), "r"(parity)
         : "memory");
 }
-// orders this thread's earlier generic-proxy accesses to shared memory before later asynchronous-proxy (bulk copy) writes
+// L2 prefetch of a contiguous range (TMA bulk prefetch): no destination, no completion
+static __device__ __forceinline__ void fk_prefetch_l2(const double *gsrc, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+// orders this thread's earlier generic-proxy accesses to shared memory before later asynchronous-proxy (bulk copy) writes to it
 static __device__ __forceinline__ void fk_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// the same for all state spaces: once per sweep, before bulk copies read what earlier sweeps stored into the records
+static __device__ __forceinline__ void fk_fence_async_global() { asm volatile("fence.proxy.async;" ::: "memory"); }
 static __device__ __forceinline__ double fk_ldg(const double *p) { return __ldg(p); }
+typedef double2 fk_double2;
+// two consecutive doubles of shared memory, 16-byte aligned (LDS.128)
+static __device__ __forceinline__ fk_double2 fk_ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 static __device__ __forceinline__ double fk_rsqrt(double x) { return rsqrt(x); }
 static __device__ __forceinline__ int fk_atomic_inc(int *p) { return atomicAdd(p, 1); }
 
@@ -69,12 +79,18 @@ template <int NX, int NU, int G, int MINB>
 __global__ void __launch_bounds__(32, MINB) cuipm_fast_kernel(const __grid_constant__ FastArgs A)
 {
     using K = fastk::Ker<NX, NU, G>;
-    __shared__ __align__(8) fk_mbar_t bars[2];
-    K k(A, g_fsmem, bars, (int) blockIdx.x * K::QPW);
-    int q = (int) blockIdx.x * K::QPW + k.gq;
-    const bool valid = q < A.nbatch;
-    if (!valid) q = A.nbatch - 1;
-    k.solve(q, valid);
+    __shared__ __align__(8) fk_mbar_t bars[6];
+    K k(A, g_fsmem, bars);
+    // persistent warps: each one fetches the next 32/G QPs of the batch until none is left (QPs need 6..18 iterations, and
+    // a launch is a few waves of resident warps: a fixed assignment leaves SMs idle at the end of every wave)
+    for (;;)
+    {
+        int first = 0;
+        if (fk_lane() == 0) first = atomicAdd(A.next_qp, K::QPW);
+        first = __shfl_sync(0xffffffffu, first, 0);
+        if (first >= A.nbatch) break;
+        k.run(first);
+    }
 }
 
 // caller's QP records -> kernel-side records: dynamics block with leading dimension ld, Hessian as a full symmetric matrix
@@ -115,8 +131,9 @@ void sizes(FastArgs &F, int *qpw)
     using K = fastk::Ker<NX, NU, G>;
     F.vsize = fastk::vector_pool_doubles(NX, NX + NU, F.nce, F.nbe, F.ns2e, F.nve);
     int gs = K::MATS + F.vsize;
-    // 32 / G groups share a warp: a group stride of 4 (mod 16) doubles spreads their broadcast loads over the banks
-    while (gs % 16 != 4) gs++;
+    // 32 / G groups share a warp; 64-bit shared loads are served per half-warp: a group stride of 8 (mod 16) doubles puts the
+    // consecutive-row accesses of the two groups of a half-warp on disjoint banks
+    while (gs % 16 != 8) gs++;
     F.gstride = gs;
     *qpw = K::QPW;
 }
@@ -125,7 +142,7 @@ template <int NX, int NU, int G, int MINB>
 cudaError_t launch_one(const FastArgs &F, cudaStream_t stream)
 {
     using K = fastk::Ker<NX, NU, G>;
-    const size_t smem = sizeof(double) * (size_t) F.gstride * K::QPW;
+    const size_t smem = sizeof(double) * ((size_t) F.gstride * K::QPW + (size_t) F.nmaps * F.nbe);
     if (((size_t) F.qpk | (size_t) F.sol | (size_t) F.work) & 15) return cudaErrorMisalignedAddress;      // bulk copies need 16-byte aligned records
     cudaError_t err = cudaFuncSetAttribute(cuipm_fast_kernel<NX, NU, G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (err != cudaSuccess) return err;
@@ -139,7 +156,17 @@ cudaError_t launch_one(const FastArgs &F, cudaStream_t stream)
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, cuipm_fast_kernel<NX, NU, G, MINB>, 32, smem);
         fprintf(stderr, "cuipm_fast_kernel<%d,%d,%d>: %zu bytes of shared memory per CTA, %d CTAs (%d QPs) per SM\n", NX, NU, G, smem, nblk, nblk * K::QPW);
     }
-    const int grid = (F.nbatch + K::QPW - 1) / K::QPW;
+    static int resident = 0;        // CTAs per SM x SMs of this instance
+    if (!resident)
+    {
+        int nblk = 0, dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, cuipm_fast_kernel<NX, NU, G, MINB>, 32, smem);
+        resident = (nblk > 0 ? nblk : 1) * (sms > 0 ? sms : 1);
+    }
+    const int want = (F.nbatch + K::QPW - 1) / K::QPW;
+    const int grid = want < resident ? want : resident;
     cuipm_fast_kernel<NX, NU, G, MINB><<<grid, 32, smem, stream>>>(F);
     return cudaGetLastError();
 }
@@ -166,11 +193,11 @@ static int dev_g() { const char *e = getenv("CUIPM_FAST_G"); return e ? atoi(e) 
 bool fast_available(int nx, int nu, FastArgs &F, int *qp_per_warp)
 {
 #define X(NX_, NU_, G_, MB_) \
-    if (nx == NX_ && nu == NU_ && dev_g() == G_) { sizes<NX_, NU_, G_>(F, qp_per_warp); return sizeof(double) * (size_t) F.gstride * (32 / G_) <= 226 * 1024; }
+    if (nx == NX_ && nu == NU_ && dev_g() == G_) { sizes<NX_, NU_, G_>(F, qp_per_warp); return sizeof(double) * ((size_t) F.gstride * (32 / G_) + (size_t) F.nmaps * F.nbe) <= 226 * 1024; }
     CUIPM_FAST_DEV_INSTANCES(X)
 #undef X
 #define X(NX_, NU_, G_, MB_) \
-    if (nx == NX_ && nu == NU_) { sizes<NX_, NU_, G_>(F, qp_per_warp); return sizeof(double) * (size_t) F.gstride * (32 / G_) <= 226 * 1024; }
+    if (nx == NX_ && nu == NU_) { sizes<NX_, NU_, G_>(F, qp_per_warp); return sizeof(double) * ((size_t) F.gstride * (32 / G_) + (size_t) F.nmaps * F.nbe) <= 226 * 1024; }
     CUIPM_FAST_INSTANCES(X)
 #undef X
     return false;

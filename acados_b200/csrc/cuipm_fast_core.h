@@ -63,34 +63,67 @@ struct Ker
     };
 
     const FastArgs &A;
-    double *smem0;             // shared memory of the warp (after the two transaction barriers)
-    fk_mbar_t *bars;           // [0]: vector images, [1]: matrices
+    double *smem0;             // shared memory of the groups of the warp (after the index maps)
+    const int *IDX;            // index maps (idxb, idxs_rev), shared by the groups: entry e at IDX + 2*e*nbe (FastArgs::nmaps entries)
+    fk_mbar_t *bars;           // [0]: vector images, [1]: matrices, [2..5]: ring of the mu_aff reduction
     int li, gq, q0;            // lane within the group, group within the warp, first QP of the warp
     double *MA, *ML, *LU, *DD, *V;
     const double *qp, *qk;     // this group's QP record: the caller's, the kernel-side one
     double *sol, *wk;
     bool act;                  // this group's QP is being solved: global stores enabled
-    unsigned ph0, ph1;         // phase parities of the two barriers
+    const double *rbase[3];    // records of the warp's first QP: kernel-side QP record, solution, work (warp-uniform)
+    size_t rstep[3];           // record strides
+    int nvalid;                // QPs of this warp that exist (the others re-read the last one)
+    unsigned ph0, ph1, phm;    // phase parities of the barriers (phm: one bit per slot of the mu_aff ring); they live as long as the barriers
     unsigned tx0, tx1;         // bytes announced to them in the phase being filled
     double nc_mask_inv;
 
     struct View { const double *q; const double *k; double *s; double *w; const int *ip; unsigned kk; };
 
-    FK_DEV Ker(const FastArgs &a, double *smem, fk_mbar_t *b, int first_qp) : A(a)
+    FK_DEV Ker(const FastArgs &a, double *smem, fk_mbar_t *b) : A(a)
     {
         const int lane = fk_lane();
         li = lane % G;
         gq = lane / G;
-        q0 = first_qp;
+        q0 = 0;
+        // the index maps are the same for every QP (and, checked on the host, for every interior stage): one copy per warp
+        int *idx = reinterpret_cast<int *>(smem);
+        for (int e = 0; e < a.nmaps; e++)
+        {
+            // maps of entry e: stage 0 / 1 / N when the interior stages share their maps (nmaps = 3), else of stage e
+            const int k = a.nmaps == 3 ? (e == 0 ? 0 : (e == 1 ? 1 : a.N)) : e;
+            const StageDesc &sdk_ = k == 0 ? a.s0 : (k == a.N ? a.sN : a.s1);
+            const int off = sdk_.idx_off + ((k >= 1 && k < a.N) ? (k - 1) * a.is : 0);
+            for (int i = lane; i < 2 * sdk_.nb; i += 32) idx[2 * e * a.nbe + i] = a.ipool[off + i];
+        }
+        IDX = idx;
+        smem += a.nmaps * a.nbe;
         smem0 = smem;
         bars = b;
         double *S = smem + (size_t) gq * a.gstride;
         MA = S; ML = MA + SZA; LU = ML + SZL; DD = LU + SZU; V = DD + SZD;
         qp = nullptr; qk = nullptr; sol = nullptr; wk = nullptr; act = false;
-        ph0 = ph1 = 0; tx0 = tx1 = 0;
+        ph0 = ph1 = phm = 0; tx0 = tx1 = 0;
         nc_mask_inv = 0.0;
-        if (lane == 0) { fk_mbar_init(bars, 1); fk_mbar_init(bars + 1, 1); }
+        rbase[0] = rbase[1] = rbase[2] = nullptr;
+        rstep[0] = a.qpk_stride; rstep[1] = a.sol_stride; rstep[2] = a.work_stride;
+        nvalid = 0;
+        if (lane == 0)
+            for (int i = 0; i < 6; i++) fk_mbar_init(bars + i, 1);
         fk_fence_async();
+        fk_sync();
+    }
+
+    // solves QPs first_qp .. first_qp + QPW - 1 (those that exist), one per group
+    FK_DEV void run(int first_qp)
+    {
+        q0 = first_qp;
+        rbase[0] = A.qpk + (size_t) first_qp * A.qpk_stride; rbase[1] = A.sol + (size_t) first_qp * A.sol_stride; rbase[2] = A.work + (size_t) first_qp * A.work_stride;
+        nvalid = A.nbatch - first_qp < QPW ? A.nbatch - first_qp : QPW;
+        int q = first_qp + gq;
+        const bool valid = q < A.nbatch;
+        if (!valid) q = A.nbatch - 1;
+        solve(q, valid);
         fk_sync();
     }
 
@@ -140,18 +173,24 @@ struct Ker
     // One contiguous range of `nd` doubles (even) per QP of the warp, from record REC (0 kernel-side QP record, 1 solution,
     // 2 work) at record offset `off`, to offset `soff` of each group's shared memory; BAR: 0 vector images, 1 matrices.
     // Lane 0 issues the copies (operands depend on the warp only); every lane keeps the byte count.
+    // pf = +1 / -1: the same range of the next / previous interior stage is prefetched into L2 (the sweep gets there next)
     template <int REC, int BAR>
-    FK_DEV void bulk(int soff, size_t off, int nd)
+    FK_DEV void bulk(int soff, size_t off, int nd, int pf = 0)
     {
         if (fk_lane() == 0)
         {
+            const double *src = rbase[REC] + off;
+            double *dst = smem0 + soff;
+            const long pfo = (long) pf * (long) (REC == 0 ? A.kqs : (REC == 1 ? A.ss : A.ws));
 #pragma unroll
             for (int g = 0; g < QPW; g++)
             {
-                int q = q0 + g;
-                q = q < A.nbatch ? q : A.nbatch - 1;
-                const double *src = (REC == 0 ? A.qpk + (size_t) q * A.qpk_stride : (REC == 1 ? A.sol + (size_t) q * A.sol_stride : A.work + (size_t) q * A.work_stride)) + off;
-                fk_bulk(smem0 + (size_t) g * A.gstride + soff, src, (unsigned) nd * 8u, bars + BAR);
+                fk_bulk(dst, src, (unsigned) nd * 8u, bars + BAR);
+#ifdef FK_L2_PREFETCH
+                if (pf != 0) fk_prefetch_l2(src + pfo, (unsigned) nd * 8u);   // measured: -5 % on the headline shape, -38 % on small stages
+#endif
+                dst += A.gstride;
+                if (g + 1 < nvalid) src += rstep[REC];
             }
         }
         if (BAR == 0) tx0 += (unsigned) (QPW * nd) * 8u;
@@ -190,7 +229,8 @@ struct Ker
 #pragma unroll 4
         for (; j + 1 < nc; j += 2)
         {
-            const double x0 = x[j], x1 = x[j + 1];
+            const fk_double2 xx = fk_ld2(x + j);
+            const double x0 = xx.x, x1 = xx.y;
 #pragma unroll
             for (int m = 0; m < RP; m++)
             {
@@ -226,7 +266,8 @@ struct Ker
 #pragma unroll 4
         for (; i + 1 < nr; i += 2)
         {
-            const double w0 = w[i], w1 = w[i + 1];
+            const fk_double2 ww = fk_ld2(w + i);
+            const double w0 = ww.x, w1 = ww.y;
 #pragma unroll
             for (int m = 0; m < CP; m++)
             {
@@ -273,7 +314,7 @@ struct Ker
         const StageDesc &sd = sdk<KIND>();
         const View v = view<KIND>(k);
         const int nb = sd.nb, ns = sd.ns, nc = sd.nc;
-        const int *idxb = v.ip + sd.idx_off, *rev = idxb + nb;
+        const int *idxb = IDX + 2 * (A.nmaps == 3 ? KIND : k) * A.nbe, *rev = idxb + nb;
         const int nu1 = (nx1 > 0 && k + 1 < A.N) ? NU : 0, n1e = (nx1 + nu1 + 1) & ~1;
         // images
         const int solN = (int) (sd.sol.t - sd.sol.ux) + evn(nc), stpN = (int) (sd.step.t - sd.step.ux) + evn(nc);
@@ -281,19 +322,20 @@ struct Ker
         double *SOL = V, *STP = SOL + (A.nve + NXe + 2 * A.nce), *SOLN = STP + (A.nve + NXe + 2 * A.nce), *STPN = SOLN + NMe;
         double *QV = STPN + NMe, *tmp0 = QV + (NXe + NMe + 2 * A.nce + 2 * A.ns2e), *tmp1 = tmp0 + A.nbe, *g_ = tmp1 + A.nbe, *pim = g_ + A.nve;
         double *x1 = pim + NXe;
+        const int pf = (KIND == 1 && k + 1 < A.N) ? 1 : 0;
         stage_begin();
-        bulk<1, 0>(voff(SOL), (size_t) v.kk * A.ss + sd.sol.ux, solN);
-        if (update) bulk<2, 0>(voff(STP), (size_t) v.kk * A.ws + sd.step.ux, stpN);
-        bulk<0, 0>(voff(QV), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kV[KIND], evn(qvN));
+        bulk<1, 0>(voff(SOL), (size_t) v.kk * A.ss + sd.sol.ux, solN, pf);
+        if (update) bulk<2, 0>(voff(STP), (size_t) v.kk * A.ws + sd.step.ux, stpN, pf);
+        bulk<0, 0>(voff(QV), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kV[KIND], evn(qvN), pf);
         if (nx1 > 0)
         {
             const StageDesc &s1 = sdr(k + 1);
             const View v1 = viewr(k + 1);
             bulk<1, 0>(voff(SOLN), (size_t) v1.kk * A.ss + s1.sol.ux, n1e);
             if (update) bulk<2, 0>(voff(STPN), (size_t) v1.kk * A.ws + s1.step.ux, n1e);
-            bulk<0, 1>(voff(MA), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs, evn(LD * nx1));
+            bulk<0, 1>(voff(MA), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs, evn(LD * nx1), pf);
         }
-        bulk<0, 1>(voff(ML), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kH[KIND], LD * n);
+        bulk<0, 1>(voff(ML), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kH[KIND], LD * n, pf);
         stage_arm();
         wait_vec();
         double *ux = SOL, *pi = SOL + (sd.sol.pi - sd.sol.ux), *lam = SOL + (sd.sol.lam - sd.sol.ux), *t = SOL + (sd.sol.t - sd.sol.ux);
@@ -469,6 +511,8 @@ struct Ker
 
     FK_DEV void res_pass(int update, double alpha_u, QpState &Q)
     {
+        fk_fence_async_global();        // the records this sweep reads with bulk copies were written with plain stores by the sweeps before
+
         ResAcc R;
         R.a_mu = R.a_obj = R.a_gap = R.m0 = R.m1 = R.m2 = R.m3 = R.m4 = 0.0;
         R.f0 = R.f1 = R.f2 = R.f3 = R.f4 = 0;
@@ -639,17 +683,25 @@ struct Ker
         const StageDesc &sd = sdk<KIND>();
         const View v = view<KIND>(k);
         const int nb = sd.nb, ns = sd.ns, nc = sd.nc;
-        const int *idxb = v.ip + sd.idx_off, *rev = idxb + nb;
+        const int *idxb = IDX + 2 * (A.nmaps == 3 ? KIND : k) * A.nbe, *rev = idxb + nb;
         const int nu1 = (nx1 > 0 && k + 1 < A.N) ? NU : 0;
         const int resN = (int) (sd.res.m - sd.res.g) + evn(nc), ltN = (int) (sd.sol.t - sd.sol.lam) + evn(nc);
         double *RES = V, *LT = RES + (A.nve + NXe + 2 * A.nce), *ZQ = LT + 2 * A.nce, *Gam = ZQ + A.ns2e, *gam = Gam + A.nce;
         double *tmp0 = gam + A.nce, *tmp1 = tmp0 + A.nbe, *dadd = tmp1 + A.nbe, *Linv = dadd + NMe, *Zi = Linv + NMe, *ds = Zi + A.ns2e;
         double *alb = ds + A.ns2e, *lvec = alb + NXe, *lprev = lvec + NMe;
+        const int pf = (KIND == 1 && k > 1) ? -1 : 0;
         stage_begin();
-        bulk<2, 0>(voff(RES), (size_t) v.kk * A.ws + sd.res.g, resN);
-        bulk<1, 0>(voff(LT), (size_t) v.kk * A.ss + sd.sol.lam, ltN);
+        bulk<2, 0>(voff(RES), (size_t) v.kk * A.ws + sd.res.g, resN, pf);
+        bulk<1, 0>(voff(LT), (size_t) v.kk * A.ss + sd.sol.lam, ltN, pf);
         if (ns > 0) bulk<0, 0>(voff(ZQ), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kV[KIND] + (sd.q_Z - sd.q_b), evn(2 * ns));
-        if (nx1 > 0) bulk<0, 1>(voff(MA), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs, evn(LD * nx1));
+        if (nx1 > 0) bulk<0, 1>(voff(MA), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs, evn(LD * nx1), pf);
+#ifdef FK_L2_PREFETCH
+        if (pf != 0 && fk_lane() == 0)
+        {   // the Hessian rows are read with plain loads: bring the block of the next stage of the sweep into L2 as well
+            const double *hp = rbase[0] + ((size_t) A.kq[KIND] + (size_t) (v.kk - 1) * A.kqs + A.kH[KIND]);
+            for (int g = 0; g < nvalid; g++) fk_prefetch_l2(hp + (size_t) g * rstep[0], (unsigned) (LD * n) * 8u);
+        }
+#endif
         stage_arm();
         wait_vec();
         double *rowv = RES;
@@ -823,7 +875,11 @@ struct Ker
 #pragma unroll
                     for (int m = 0; m < RP; m++) a[m] = m >= m0 ? MA[(li + G * m < n ? li + G * m : 0) + LD * c] : 0.0;
 #pragma unroll
-                    for (int q = 0; q < 8; q++) b[q] = q < w ? MA[jt + q + LD * c] : 0.0;
+                    for (int q = 0; q < 8; q += 2)
+                    {
+                        const fk_double2 t2 = fk_ld2(MA + jt + q + LD * c);       // rows jt+q, jt+q+1 of column c: 16-byte aligned
+                        b[q] = t2.x; b[q + 1] = t2.y;
+                    }
 #pragma unroll
                     for (int m = 0; m < RP; m++)
                         if (m >= m0)
@@ -844,7 +900,11 @@ struct Ker
 #pragma unroll
                 for (int m = 0; m < RP; m++) a[m] = m >= m0 ? ML[(li + G * m < n ? li + G * m : 0) + LD * c] : 0.0;
 #pragma unroll
-                for (int q = 0; q < 8; q++) b[q] = q < w ? ML[jt + q + LD * c] : 0.0;
+                for (int q = 0; q < 8; q += 2)
+                {
+                    const fk_double2 t2 = fk_ld2(ML + jt + q + LD * c);
+                    b[q] = t2.x; b[q + 1] = t2.y;
+                }
 #pragma unroll
                 for (int m = 0; m < RP; m++)
                     if (m >= m0)
@@ -877,7 +937,11 @@ struct Ker
                 {
                     double b[4];
 #pragma unroll
-                    for (int q = 0; q < 4; q++) b[q] = 4 + q < w ? ML[jt + 4 + q + LD * (jt + c)] : 0.0;
+                    for (int q = 0; q < 4; q += 2)
+                    {
+                        const fk_double2 t2 = fk_ld2(ML + jt + 4 + q + LD * (jt + c));
+                        b[q] = t2.x; b[q + 1] = t2.y;
+                    }
 #pragma unroll
                     for (int m = 0; m < RP; m++)
                         if (m >= m1)
@@ -899,6 +963,8 @@ struct Ker
 
     FK_DEV void fact_backward()
     {
+        fk_fence_async_global();        // the records this sweep reads with bulk copies were written with plain stores by the sweeps before
+
         fact_stage<2>(A.N);
         for (int k = A.N - 1; k >= 1; k--) fact_stage<1>(k);
         fact_stage<0>(0);
@@ -919,7 +985,7 @@ struct Ker
         const StageDesc &sd = sdk<KIND>();
         const View v = view<KIND>(k);
         const int nb = sd.nb, ns = sd.ns, nc = sd.nc;
-        const int *idxb = v.ip + sd.idx_off, *rev = idxb + nb;
+        const int *idxb = IDX + 2 * (A.nmaps == 3 ? KIND : k) * A.nbe, *rev = idxb + nb;
         const int resN = (int) (sd.res.m - sd.res.g) + evn(nc), ltN = (int) (sd.sol.t - sd.sol.lam) + evn(nc);
         const int fvN = (int) (sd.w_Zsi - sd.w_Linv) + evn(2 * ns), stN = (int) (sd.step.t - sd.step.lam) + evn(nc);
         const int qmN = (int) (sd.q_Z - sd.q_dmask) + evn(2 * ns);
@@ -927,15 +993,16 @@ struct Ker
         double *QM = STL + 2 * A.nce, *Gam = QM + (A.nce + A.ns2e), *gam = Gam + A.nce, *tmp0 = gam + A.nce, *tmp1 = tmp0 + A.nbe;
         double *ds = tmp1 + A.nbe, *xprev = ds + A.ns2e, *tmpx = xprev + NXe;
         const bool so = act && stw;
+        const int pf = (KIND == 1 && k > 1) ? -1 : 0;
         stage_begin();
-        bulk<2, 0>(voff(RES), (size_t) v.kk * A.ws + sd.res.g, resN);
-        bulk<1, 0>(voff(LT), (size_t) v.kk * A.ss + sd.sol.lam, ltN);
-        bulk<2, 0>(voff(FV), (size_t) v.kk * A.ws + sd.w_Linv, fvN);
-        bulk<2, 0>(voff(RMB), (size_t) v.kk * A.ws + sd.w_rmb, evn(nc));
-        bulk<2, 0>(voff(STL), (size_t) v.kk * A.ws + sd.step.lam, stN);
-        bulk<0, 0>(voff(QM), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kV[KIND] + (sd.q_dmask - sd.q_b), qmN);
-        if (nx1 > 0) bulk<0, 1>(voff(MA), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs, evn(LD * nx1));
-        if (nsolve > 0) bulk<2, 1>(voff(LU), (size_t) v.kk * A.ws + sd.w_L, evn(n * nsolve));
+        bulk<2, 0>(voff(RES), (size_t) v.kk * A.ws + sd.res.g, resN, pf);
+        bulk<1, 0>(voff(LT), (size_t) v.kk * A.ss + sd.sol.lam, ltN, pf);
+        bulk<2, 0>(voff(FV), (size_t) v.kk * A.ws + sd.w_Linv, fvN, pf);
+        bulk<2, 0>(voff(RMB), (size_t) v.kk * A.ws + sd.w_rmb, evn(nc), pf);
+        bulk<2, 0>(voff(STL), (size_t) v.kk * A.ws + sd.step.lam, stN, pf);
+        bulk<0, 0>(voff(QM), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kV[KIND] + (sd.q_dmask - sd.q_b), qmN, pf);
+        if (nx1 > 0) bulk<0, 1>(voff(MA), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs, evn(LD * nx1), pf);
+        if (nsolve > 0) bulk<2, 1>(voff(LU), (size_t) v.kk * A.ws + sd.w_L, evn(n * nsolve), pf);
         stage_arm();
         wait_vec();
         double *vv = RES;
@@ -1030,6 +1097,8 @@ struct Ker
 
     FK_DEV void solve_backward(int rm_mode, double sigma_mu, bool stw)
     {
+        fk_fence_async_global();        // the records this sweep reads with bulk copies were written with plain stores by the sweeps before
+
         solve_stage<2>(A.N, rm_mode, sigma_mu, stw);
         for (int k = A.N - 1; k >= 1; k--) solve_stage<1>(k, rm_mode, sigma_mu, stw);
         solve_stage<0>(0, rm_mode, sigma_mu, stw);
@@ -1058,7 +1127,7 @@ struct Ker
         const StageDesc &sd = sdk<KIND>();
         const View v = view<KIND>(k);
         const int nb = sd.nb, ns = sd.ns, nc = sd.nc;
-        const int *idxb = v.ip + sd.idx_off, *rev = idxb + nb;
+        const int *idxb = IDX + 2 * (A.nmaps == 3 ? KIND : k) * A.nbe, *rev = idxb + nb;
         const int nu1 = (nx1 > 0 && k + 1 < A.N) ? NU : 0, n1 = nx1 + nu1, n1e = (n1 + 1) & ~1;
         const int resN = (int) (sd.res.m - sd.res.g) + evn(nc), ltN = (int) (sd.sol.t - sd.sol.lam) + evn(nc);
         const int fvN = (int) (sd.w_Zsi - sd.w_Linv) + evn(2 * ns), qmN = (int) (sd.q_Z - sd.q_dmask) + evn(2 * ns);
@@ -1070,21 +1139,22 @@ struct Ker
         View v1 = v;
         const StageDesc *s1p = &sd;
         if (nx1 > 0) { s1p = &sdr(k + 1); v1 = viewr(k + 1); }
+        const int pf = (KIND == 1 && k + 2 < A.N) ? 1 : 0;
         stage_begin();
-        bulk<2, 0>(voff(RES), (size_t) v.kk * A.ws + sd.res.g, resN);
-        bulk<1, 0>(voff(LT), (size_t) v.kk * A.ss + sd.sol.lam, ltN);
-        bulk<2, 0>(voff(FV), (size_t) v.kk * A.ws + sd.w_Linv, fvN);
-        bulk<2, 0>(voff(SUX), (size_t) v.kk * A.ws + sd.step.ux, evn(n + 2 * ns));
-        bulk<0, 0>(voff(QM), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kV[KIND] + (sd.q_dmask - sd.q_b), qmN);
+        bulk<2, 0>(voff(RES), (size_t) v.kk * A.ws + sd.res.g, resN, pf);
+        bulk<1, 0>(voff(LT), (size_t) v.kk * A.ss + sd.sol.lam, ltN, pf);
+        bulk<2, 0>(voff(FV), (size_t) v.kk * A.ws + sd.w_Linv, fvN, pf);
+        bulk<2, 0>(voff(SUX), (size_t) v.kk * A.ws + sd.step.ux, evn(n + 2 * ns), pf);
+        bulk<0, 0>(voff(QM), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kV[KIND] + (sd.q_dmask - sd.q_b), qmN, pf);
         if (nx1 > 0)
         {
             // p part (gradient vector of stage k+1) / backward value of x_{k+1}
-            bulk<2, 0>(voff(P1), (size_t) v1.kk * A.ws + (after_fact ? s1p->w_lrow : s1p->step.ux), n1e);
-            bulk<0, 1>(voff(MA), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs, evn(LD * nx1));
+            bulk<2, 0>(voff(P1), (size_t) v1.kk * A.ws + (after_fact ? s1p->w_lrow : s1p->step.ux), n1e, pf);
+            bulk<0, 1>(voff(MA), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs, evn(LD * nx1), pf);
         }
-        if (nsolve > 0) bulk<2, 1>(voff(LU), (size_t) v.kk * A.ws + sd.w_L, evn(n * nsolve));
-        if (do_lin) bulk<0, 1>(voff(ML), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kH[KIND], LD * n);
-        else if (nx1 > 0) bulk<2, 1>(voff(ML), (size_t) v1.kk * A.ws + s1p->w_L, evn(n1 * n1));
+        if (nsolve > 0) bulk<2, 1>(voff(LU), (size_t) v.kk * A.ws + sd.w_L, evn(n * nsolve), pf);
+        if (do_lin) bulk<0, 1>(voff(ML), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kH[KIND], LD * n, pf);
+        else if (nx1 > 0) bulk<2, 1>(voff(ML), (size_t) v1.kk * A.ws + s1p->w_L, evn(n1 * n1), pf);
         stage_arm();
         wait_vec();
         const double *gv = RES, *bs = RES + (sd.res.b - sd.res.g), *rds = RES + (sd.res.d - sd.res.g), *rms = RES + (sd.res.m - sd.res.g);
@@ -1139,7 +1209,7 @@ struct Ker
             if (nx1 > 0)
             {
                 stage_begin();
-                bulk<2, 1>(voff(ML), (size_t) v1.kk * A.ws + s1p->w_L, evn(n1 * n1));
+                bulk<2, 1>(voff(ML), (size_t) v1.kk * A.ws + s1p->w_L, evn(n1 * n1), pf);
                 stage_arm_mat();
             }
         }
@@ -1245,37 +1315,25 @@ struct Ker
         {
             if (do_lin) wait_mat();
             fk_sync();
-            const double *Lx = ML + nu1 + n1 * nu1;                          // Lxx of stage k+1, leading dimension n1
+            const double *Lx = ML + nu1 + n1 * nu1;                          // Lxx of stage k+1, leading dimension n1, zero above the diagonal
+            double tt_[RPM > 0 ? RPM : 1];
+            cols_dot<nx1, nx1>(Lx, n1, x1, tt_);
 #pragma unroll
             for (int m = 0; m < CP; m++)
             {
                 const int j = li + G * m;
-                if (j < nx1)
-                {
-                    double s0 = 0.0, s1 = 0.0;
-                    const double *lcol = Lx + n1 * j;
-                    int i = j;
-                    for (; i + 1 < nx1; i += 2) { s0 += lcol[i] * x1[i]; s1 += lcol[i + 1] * x1[i + 1]; }
-                    if (i < nx1) s0 += lcol[i] * x1[i];
-                    const double acc = s0 + s1;
-                    tmp[j] = after_fact ? acc + P1[nu1 + j] : acc;
-                }
+                if (j < nx1) tmp[j] = after_fact ? tt_[m] + P1[nu1 + j] : tt_[m];
             }
             fk_sync();
             double *pi = v.w + sd.step.pi;
+            rows_dot<nx1, nx1>(Lx, n1, tmp, tt_);
 #pragma unroll
             for (int m = 0; m < CP; m++)
             {
                 const int i = li + G * m;
                 if (i < nx1)
                 {
-                    double s0 = 0.0, s1 = 0.0;
-                    const double *lr = Lx + i;
-                    int c = 0;
-                    for (; c + 1 <= i; c += 2) { s0 += lr[n1 * c] * tmp[c]; s1 += lr[n1 * (c + 1)] * tmp[c + 1]; }
-                    if (c <= i) s0 += lr[n1 * c] * tmp[c];
-                    const double acc = s0 + s1;
-                    const double pv = after_fact ? acc : acc + P1[nu1 + i];
+                    const double pv = after_fact ? tt_[m] : tt_[m] + P1[nu1 + i];
                     if (so) pi[i] = pv;
                     pik[i] = pv;
                 }
@@ -1338,6 +1396,8 @@ struct Ker
     // returns the step length; lin_nrm = inf-norms of the residual of the linear system (do_lin)
     FK_DEV double forward_pass(int after_fact, int do_lin, bool stw, double lin_nrm[4])
     {
+        fk_fence_async_global();        // the records this sweep reads with bulk copies were written with plain stores by the sweeps before
+
         FwdAcc F;
         F.alpha = 1.0;
         F.m0 = F.m1 = F.m2 = F.m3 = 0.0;
@@ -1355,16 +1415,53 @@ struct Ker
         return gmin(F.alpha);
     }
 
-    // COMPUTE_MU_AFF_QP (x_core_qp_ipm_aux.c:636-668)
+    // COMPUTE_MU_AFF_QP (x_core_qp_ipm_aux.c:636-668): a streaming reduction over (lam, t) of the solution record and
+    // (dlam, dt) of the step, four stages in flight (one transaction barrier per slot of the ring)
     FK_DEV double mu_aff_pass(double alpha)
     {
+        constexpr int D = 4;
+        const int N = A.N, slot_sz = 4 * A.nce;
         double acc = 0.0;
+        auto issue = [&](int k, int slot) {
+            const StageDesc &s = sdr(k);
+            const unsigned kk = (k >= 1 && k < N) ? (unsigned) (k - 1) : 0u;
+            const int ltN = (int) (s.sol.t - s.sol.lam) + evn(s.nc), stN = (int) (s.step.t - s.step.lam) + evn(s.nc);
+            if (fk_lane() == 0)
+            {
+                const double *s1 = rbase[1] + ((size_t) kk * A.ss + s.sol.lam), *s2 = rbase[2] + ((size_t) kk * A.ws + s.step.lam);
+                double *dst = smem0 + voff(V) + slot * slot_sz;
+                for (int g = 0; g < QPW; g++)
+                {
+                    fk_bulk(dst, s1, (unsigned) ltN * 8u, bars + 2 + slot);
+                    fk_bulk(dst + 2 * A.nce, s2, (unsigned) stN * 8u, bars + 2 + slot);
+                    dst += A.gstride;
+                    if (g + 1 < nvalid) { s1 += rstep[1]; s2 += rstep[2]; }
+                }
+                fk_mbar_arrive_tx(bars + 2 + slot, (unsigned) (QPW * (ltN + stN)) * 8u);
+            }
+        };
+#ifndef FK_MU_RING        // the ring of bulk copies below was measured neutral on the headline shape, slower on small stages
         for (int k = 0; k <= A.N; k++)
         {
             const StageDesc &s = sdr(k);
             const View v = viewr(k);
             const double *l = v.s + s.sol.lam, *t = v.s + s.sol.t, *dl = v.w + s.step.lam, *dt = v.w + s.step.t;
             for (int i = li; i < s.nc; i += G) acc += fabs((l[i] + alpha * dl[i]) * (t[i] + alpha * dt[i]));
+        }
+        return gsum(acc) * nc_mask_inv;
+#endif
+        stage_begin();
+        for (int d = 0; d < D && d <= N; d++) issue(d, d);
+        for (int k = 0; k <= N; k++)
+        {
+            const int slot = k % D;
+            fk_mbar_wait(bars + 2 + slot, (phm >> slot) & 1u);
+            phm ^= 1u << slot;
+            const StageDesc &s = sdr(k);
+            const double *l = V + slot * slot_sz, *t = l + (s.sol.t - s.sol.lam), *dl = l + 2 * A.nce, *dt = dl + (s.step.t - s.step.lam);
+            for (int i = li; i < s.nc; i += G) acc += fabs((l[i] + alpha * dl[i]) * (t[i] + alpha * dt[i]));
+            fk_sync();
+            if (k + D <= N) issue(k + D, slot);
         }
         return gsum(acc) * nc_mask_inv;
     }
@@ -1405,7 +1502,7 @@ struct Ker
             const StageDesc &s = sdr(k);
             const View v = viewr(k);
             const int n = s.n, nb = s.nb, ns = s.ns, nc = s.nc;
-            const int *idxb = v.ip + s.idx_off, *rev = idxb + nb;
+            const int *idxb = IDX + 2 * (A.nmaps == 3 ? (k == 0 ? 0 : (k == A.N ? 2 : 1)) : k) * A.nbe, *rev = idxb + nb;
             const double *d = v.q + s.q_d;
             double *gux = v.s + s.sol.ux, *gpi = v.s + s.sol.pi, *gl = v.s + s.sol.lam, *gt = v.s + s.sol.t;
             for (int i = li; i < s.nx1; i += G) st(gpi + i, 0.0);
@@ -1638,8 +1735,9 @@ inline int vector_pool_doubles(int NX, int NM, int nce, int nbe, int ns2e, int n
     const int v_fact = img + 2 * nce + ns2e + 2 * nce + 2 * nbe + 2 * nme + 2 * ns2e + nxe + nme + nxe;
     const int v_slv = img + 2 * nce + (2 * nme + nxe + ns2e) + nce + 2 * nce + (nce + ns2e) + 2 * nce + 2 * nbe + ns2e + 2 * nxe;
     const int v_fwd = img + 2 * nce + (2 * nme + nxe + ns2e) + nve + nme + (nce + ns2e) + nve + nxe + nve + 2 * nxe + 2 * nce + ns2e + nbe;
-    const int v_init = nve + nce;
+    const int v_init = nve + nce, v_mu = 16 * nce;
     int m = v_res;
+    if (v_mu > m) m = v_mu;
     if (v_fact > m) m = v_fact;
     if (v_slv > m) m = v_slv;
     if (v_fwd > m) m = v_fwd;

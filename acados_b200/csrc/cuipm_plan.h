@@ -114,7 +114,7 @@ inline int build_plan(const cuipm_shape *sh, const cuipm_layout *l, std::vector<
 // no general constraints, no repeated bound index, N >= 3; then every array offset of an interior stage is the offset of
 // stage 1 plus (k-1) times a constant stride, and the kernel needs three descriptors only (first, interior, last).
 // Fills F (records / pointers are set by the caller); returns false if the shape is not eligible.
-inline bool fast_plan(const std::vector<StageDesc> &sd, const ProbDesc &P, FastArgs &F)
+inline bool fast_plan(const std::vector<StageDesc> &sd, const std::vector<int> &ipool, const ProbDesc &P, FastArgs &F)
 {
     const int N = P.N;
     if (N < 3) return false;
@@ -126,10 +126,13 @@ inline bool fast_plan(const std::vector<StageDesc> &sd, const ProbDesc &P, FastA
     // affine offsets over the interior stages: compare every unsigned offset field
     const unsigned qs = N >= 3 ? sd[2].q_stage - a.q_stage : 0, ss = N >= 3 ? sd[2].sol.ux - a.sol.ux : 0, ws = N >= 3 ? sd[2].w_fac - a.w_fac : 0;
     const int is = N >= 3 ? sd[2].idx_off - a.idx_off : 0;
+    bool same_maps = true;
     for (int k = 1; k <= N - 1; k++)
     {
         const StageDesc &d = sd[k];
         if (d.nx != a.nx || d.nu != a.nu || d.nb != a.nb || d.ns != a.ns) return false;
+        for (int i = 0; i < 2 * a.nb; i++)       // one copy of the index maps on chip if the interior stages share them, else one per stage
+            if (ipool[d.idx_off + i] != ipool[a.idx_off + i]) same_maps = false;
         const unsigned dq = qs * (unsigned) (k - 1), dsol = ss * (unsigned) (k - 1), dw = ws * (unsigned) (k - 1);
         bool ok = d.idx_off == a.idx_off + is * (k - 1);
         ok = ok && d.q_BAt == a.q_BAt + dq && d.q_RSQ == a.q_RSQ + dq && d.q_b == a.q_b + dq && d.q_rq == a.q_rq + dq && d.q_d == a.q_d + dq
@@ -143,6 +146,7 @@ inline bool fast_plan(const std::vector<StageDesc> &sd, const ProbDesc &P, FastA
     }
     F.N = N;
     F.nct = P.nct;
+    F.nmaps = same_maps ? 3 : N + 1;
     F.s0 = sd[0]; F.s1 = sd[1]; F.sN = sd[N];
     F.qs = qs; F.ss = ss; F.ws = ws; F.is = is;
     F.qp_stride = P.qp_stride; F.sol_stride = P.sol_stride; F.work_stride = P.work_stride; F.w_bkp = P.w_bkp;

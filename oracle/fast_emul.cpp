@@ -23,7 +23,15 @@ static inline void fk_bulk(double *dst, const double *src, unsigned bytes, fk_mb
 static inline void fk_mbar_arrive_tx(fk_mbar_t *b, unsigned bytes) { simt::mbar_arrive_tx(b, (int) bytes); }
 static inline void fk_mbar_wait(fk_mbar_t *b, unsigned parity) { simt::mbar_wait(b, (int) parity); }
 static inline void fk_fence_async() {}
+static inline void fk_fence_async_global() {}
+static inline void fk_prefetch_l2(const double *, unsigned) {}
 static inline double fk_ldg(const double *p) { return *p; }
+struct fk_double2 { double x, y; };
+static inline fk_double2 fk_ld2(const double *p)
+{
+    if ((size_t) p & 15) { std::fprintf(stderr, "fast_emul: misaligned 16-byte load\n"); std::abort(); }
+    return fk_double2{p[0], p[1]};
+}
 static inline double fk_rsqrt(double x) { return 1.0 / std::sqrt(x); }
 static inline int fk_atomic_inc(int *p) { return (*p)++; }
 using std::fabs;
@@ -42,9 +50,9 @@ int run(cuipm::FastArgs F, int order)
     using K = cuipm::fastk::Ker<NX, NU, G>;
     F.vsize = cuipm::fastk::vector_pool_doubles(NX, NX + NU, F.nce, F.nbe, F.ns2e, F.nve);
     int gs = K::MATS + F.vsize;
-    while (gs % 16 != 4) gs++;
+    while (gs % 16 != 8) gs++;
     F.gstride = gs;
-    std::vector<double> smem((size_t) gs * K::QPW + 64);
+    std::vector<double> smem((size_t) gs * K::QPW + (size_t) F.nmaps * F.nbe + 64);
     // 16-byte aligned base
     double *base = smem.data();
     while ((size_t) base & 15) base++;
@@ -52,13 +60,10 @@ int run(cuipm::FastArgs F, int order)
     for (int w = 0; w < nwarp; w++)
     {
         for (double &x : smem) x = std::nan("");      // uninitialised shared memory
-        simt::MBar bars[2];
+        simt::MBar bars[6];
         simt::run_warp([&]() {
-            K k(F, base, bars, w * K::QPW);
-            int q = w * K::QPW + k.gq;
-            const bool valid = q < F.nbatch;
-            if (!valid) q = F.nbatch - 1;
-            k.solve(q, valid);
+            K k(F, base, bars);
+            k.run(w * K::QPW);
         }, order);
     }
     return 0;
@@ -79,7 +84,7 @@ extern "C" int fast_emul_solve(const cuipm_shape *sh, int nbatch, const double *
     std::string err;
     if (cuipm::build_plan(sh, l, sd, ipool, P, err) != CUIPM_OK) { cuipm_layout_destroy(l); return -3; }
     cuipm::FastArgs F{};
-    if (!cuipm::fast_plan(sd, P, F)) { cuipm_layout_destroy(l); return -1; }
+    if (!cuipm::fast_plan(sd, ipool, P, F)) { cuipm_layout_destroy(l); return -1; }
     std::vector<double> work((size_t) P.work_stride * nbatch, 0.0);
     ipool.push_back(0);
     F.nbatch = nbatch;

@@ -62,6 +62,9 @@ if __name__ == "__main__":
         s.solve_device(nb, d_qp.data_ptr(), d_sol.data_ptr(), d_info.data_ptr(), o, sync=True)
         print("kernel ms", s.last_kernel_ms)
         s.close()
+    if what == "time3":
+        timing(problems.chain_mass(4096, N=40, seed=1234), "c2")
+        timing(problems.named_config("c3", 16384), "c3")
     if what == "time2":
         timing(problems.chain_mass(4096, N=40, seed=1234), "c2")
     if what in ("all", "time"):
