@@ -38,7 +38,7 @@ struct Plan
     const int *st_offu, *st_offs;             // per original stage: offset of its inputs / slacks inside its block's stage
     const int *box_ptr, *box_stage, *box_i;   // condensed box p of block b (p in box_ptr[b]..box_ptr[b+1]): original (stage, bound index)
     const int *gen_ptr, *gen_stage, *gen_kind, *gen_i;   // condensed general constraint: kind 0 = state bound i of an inner stage, 1 = general constraint i
-    int nxmax, n2max;                         // scratch sizing: max nx over stages, max (nu2 + nx) over blocks
+    int nxmax, n2max;                         // scratch sizing: max of nx and nu over stages, max (nu2 + nx) over blocks
 };
 
 CC_HD inline int scratch_doubles(const Plan &P) { return 2 * P.nxmax * P.n2max + 4 * P.nxmax + 2 * P.n2max + 16; }

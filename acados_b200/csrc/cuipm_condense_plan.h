@@ -96,7 +96,8 @@ inline bool build_plan(const cuipm_shape *sh, int cond_N, HostPlan &hp)
     hp.nx2.push_back(sh->nx[N]); hp.nu2.push_back(sh->nu[N]); hp.nb2.push_back(sh->nb[N]); hp.ng2.push_back(sh->ng[N]); hp.ns2.push_back(sh->ns[N]);
     hp.idxb2[cond_N].assign(sh->idxb[N], sh->idxb[N] + sh->nb[N]);
     for (int i = 0; i < sh->nb[N] + sh->ng[N]; i++) hp.rev2[cond_N].push_back(rev_of(N, i));
-    for (int kk = 0; kk <= N; kk++) hp.nxmax = std::max(hp.nxmax, sh->nx[kk]);
+    // the scratch blocks T, T2 (nxmax x n2max) also hold S_j T (nu_j x n2): size them by the larger of nx and nu
+    for (int kk = 0; kk <= N; kk++) hp.nxmax = std::max(hp.nxmax, std::max(sh->nx[kk], sh->nu[kk]));
     for (int b = 0; b <= cond_N; b++)
     {
         if (hp.idxb2[b].empty()) hp.idxb2[b].push_back(0);

@@ -34,6 +34,17 @@ static __device__ __forceinline__ void fk_bulk(double *sdst, const double *gsrc,
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sa), "l"(gsrc), "r"(bytes), "r"(ba)
                  : "memory");
 }
+// the same range of the records of the n QPs of a warp (record stride rstep; the groups beyond nvalid re-read the last one) into
+// the n groups' shared memory (group stride gstride doubles); kept out of line
+static __device__ __noinline__ void fk_bulk_groups(double *sdst, const double *gsrc, unsigned bytes, fk_mbar_t *b, int n, int gstride, size_t rstep, int nvalid)
+{
+    for (int g = 0; g < n; g++)
+    {
+        fk_bulk(sdst, gsrc, bytes, b);
+        sdst += gstride;
+        if (g + 1 < nvalid) gsrc += rstep;
+    }
+}
 static __device__ __forceinline__ void fk_mbar_arrive_tx(fk_mbar_t *b, unsigned bytes)
 {
     const unsigned ba = (unsigned) __cvta_generic_to_shared(b);

@@ -10,8 +10,9 @@
 // "images" of the contiguous vector ranges of the three records -- is brought into shared memory by bulk asynchronous
 // copies (TMA, cp.async.bulk) issued by one lane with warp-uniform operands and completed on an mbarrier; the arithmetic
 // then runs on shared memory and registers only, results leave through plain stores.  The matrices come from the
-// kernel-side QP record (FastArgs::qpk, written by the repack pass): leading dimension LD = 2 (mod 4) (row and column
-// accesses both bank-conflict free, 16-byte aligned columns), Hessian stored as a full symmetric matrix.
+// kernel-side QP record (FastArgs::qpk, written by the repack pass): odd leading dimension (row and column accesses of a
+// group both bank-conflict free), Hessian stored as a full symmetric matrix; the factorisation takes the dynamics block
+// from the caller's record (even leading dimension n: its broadcast operand is read with 128-bit loads).
 //
 // Algorithm and work-record layout are those of the generic kernel (cuipm_kernel.cu), which restates HPIPM's
 // d_ocp_qp_ipm_solve (external/hpipm/ocp_qp/x_ocp_qp_ipm.c:2684-3120): the sensitivity kernel and the Riccati getters
@@ -46,11 +47,13 @@ struct Ker
 {
     static constexpr int NM = NX + NU;                    // rows of an interior stage block
     static constexpr int QPW = 32 / G;                    // QPs per warp
-    static constexpr int LD = ((NM + 2) / 4) * 4 + 2;     // >= NM+1, = 2 mod 4 (the leading dimension of the kernel-side record)
+    static constexpr int LDK = NM | 1;                     // leading dimension of the kernel-side record (odd: row and column accesses
+                                                          // of a group in shared memory are both bank-conflict free)
+    static constexpr int LDW = ((NM + 1) / 4) * 4 + 2;    // leading dimension of the factor being built (>= NM, = 2 mod 4: 16-byte aligned columns)
     static constexpr int RPM = (NM + G - 1) / G;          // row slots per lane
     static constexpr int NXe = (NX + 1) & ~1, NMe = (NM + 2) & ~1;
-    static constexpr int SZA = LD * NX;                   // dynamics block [B'; A'] -> A Lxx in place
-    static constexpr int SZL = LD * NM;                   // L_{k+1} -> L_k (factorisation); Hessian / L_{k+1} (other sweeps)
+    static constexpr int SZA = (LDK * NX + 1) & ~1;       // dynamics block [B'; A'] (-> A Lxx in place in the factorisation, leading dimension n there)
+    static constexpr int SZL = LDW * NM;                  // L_{k+1} -> L_k (factorisation); Hessian / L_{k+1} (other sweeps)
     static constexpr int SZU = (NM * NU + 1) & ~1;        // first nu columns of L_k (substitutions), leading dimension n
     static constexpr int SZD = 20;                        // 4 x 4 diagonal block + 4 gradient entries
     static constexpr int MATS = SZA + SZL + SZU + SZD;
@@ -71,8 +74,8 @@ struct Ker
     const double *qp, *qk;     // this group's QP record: the caller's, the kernel-side one
     double *sol, *wk;
     bool act;                  // this group's QP is being solved: global stores enabled
-    const double *rbase[3];    // records of the warp's first QP: kernel-side QP record, solution, work (warp-uniform)
-    size_t rstep[3];           // record strides
+    const double *rbase[4];    // records of the warp's first QP: kernel-side QP record, solution, work, caller's QP record (warp-uniform)
+    size_t rstep[4];           // record strides
     int nvalid;                // QPs of this warp that exist (the others re-read the last one)
     unsigned ph0, ph1, phm;    // phase parities of the barriers (phm: one bit per slot of the mu_aff ring); they live as long as the barriers
     unsigned tx0, tx1;         // bytes announced to them in the phase being filled
@@ -105,8 +108,8 @@ struct Ker
         qp = nullptr; qk = nullptr; sol = nullptr; wk = nullptr; act = false;
         ph0 = ph1 = phm = 0; tx0 = tx1 = 0;
         nc_mask_inv = 0.0;
-        rbase[0] = rbase[1] = rbase[2] = nullptr;
-        rstep[0] = a.qpk_stride; rstep[1] = a.sol_stride; rstep[2] = a.work_stride;
+        rbase[0] = rbase[1] = rbase[2] = rbase[3] = nullptr;
+        rstep[0] = a.qpk_stride; rstep[1] = a.sol_stride; rstep[2] = a.work_stride; rstep[3] = a.qp_stride;
         nvalid = 0;
         if (lane == 0)
             for (int i = 0; i < 6; i++) fk_mbar_init(bars + i, 1);
@@ -119,6 +122,7 @@ struct Ker
     {
         q0 = first_qp;
         rbase[0] = A.qpk + (size_t) first_qp * A.qpk_stride; rbase[1] = A.sol + (size_t) first_qp * A.sol_stride; rbase[2] = A.work + (size_t) first_qp * A.work_stride;
+        rbase[3] = A.qp + (size_t) first_qp * A.qp_stride;
         nvalid = A.nbatch - first_qp < QPW ? A.nbatch - first_qp : QPW;
         int q = first_qp + gq;
         const bool valid = q < A.nbatch;
@@ -168,31 +172,28 @@ struct Ker
         return isnan_ ? NAN : v;
     }
     FK_DEV void st(double *p, double v) const { if (act) *p = v; }
+    // two consecutive doubles of shared memory: one 128-bit load where the address is known to be 16-byte aligned
+    template <bool ALIGNED>
+    FK_DEV fk_double2 ld_pair(const double *p) const
+    {
+        if (ALIGNED) return fk_ld2(p);
+        fk_double2 r;
+        r.x = p[0]; r.y = p[1];
+        return r;
+    }
 
     // ---- staging: bulk asynchronous copies with warp-uniform operands ---------------------------------------------------
     // One contiguous range of `nd` doubles (even) per QP of the warp, from record REC (0 kernel-side QP record, 1 solution,
-    // 2 work) at record offset `off`, to offset `soff` of each group's shared memory; BAR: 0 vector images, 1 matrices.
+    // 2 work, 3 the caller's QP record) at record offset `off`, to offset `soff` of each group's shared memory; BAR: 0 vector
+    // images, 1 matrices.
     // Lane 0 issues the copies (operands depend on the warp only); every lane keeps the byte count.
     // pf = +1 / -1: the same range of the next / previous interior stage is prefetched into L2 (the sweep gets there next)
     template <int REC, int BAR>
     FK_DEV void bulk(int soff, size_t off, int nd, int pf = 0)
     {
-        if (fk_lane() == 0)
-        {
-            const double *src = rbase[REC] + off;
-            double *dst = smem0 + soff;
-            const long pfo = (long) pf * (long) (REC == 0 ? A.kqs : (REC == 1 ? A.ss : A.ws));
-#pragma unroll
-            for (int g = 0; g < QPW; g++)
-            {
-                fk_bulk(dst, src, (unsigned) nd * 8u, bars + BAR);
-#ifdef FK_L2_PREFETCH
-                if (pf != 0) fk_prefetch_l2(src + pfo, (unsigned) nd * 8u);   // measured: -5 % on the headline shape, -38 % on small stages
-#endif
-                dst += A.gstride;
-                if (g + 1 < nvalid) src += rstep[REC];
-            }
-        }
+        // (one out-of-line copy of the issue loop: the ~35 call sites of a kernel instance were a quarter of its code)
+        if (fk_lane() == 0) fk_bulk_groups(smem0 + soff, rbase[REC] + off, (unsigned) nd * 8u, bars + BAR, QPW, A.gstride, rstep[REC], nvalid);
+        (void) pf;
         if (BAR == 0) tx0 += (unsigned) (QPW * nd) * 8u;
         else tx1 += (unsigned) (QPW * nd) * 8u;
     }
@@ -204,7 +205,12 @@ struct Ker
         if (fk_lane() == 0) { fk_mbar_arrive_tx(bars, tx0); fk_mbar_arrive_tx(bars + 1, tx1); }
         tx0 = tx1 = 0;
     }
-    // a second batch of matrix copies inside a stage
+    FK_DEV void stage_arm_vec()
+    {
+        if (fk_lane() == 0) fk_mbar_arrive_tx(bars, tx0);
+        tx0 = 0;
+    }
+    // matrix copies announced separately (a second batch inside a stage, requests for the next stage)
     FK_DEV void stage_arm_mat()
     {
         if (fk_lane() == 0) fk_mbar_arrive_tx(bars + 1, tx1);
@@ -292,6 +298,17 @@ struct Ker
         for (int m = 0; m < CP; m++) out[m] += o2[m];
     }
 
+    // matrices of stage k of the residual sweep: dynamics block and symmetric Hessian of the kernel-side record
+    FK_DEV void res_issue_mat(int k)
+    {
+        const StageDesc &s = sdr(k);
+        const unsigned kk = (k >= 1 && k < A.N) ? (unsigned) (k - 1) : 0u;
+        const int kind = k == 0 ? 0 : (k == A.N ? 2 : 1);
+        if (s.nx1 > 0) bulk<0, 1>(voff(MA), (size_t) A.kq[kind] + (size_t) kk * A.kqs, evn(LDK * s.nx1));
+        bulk<0, 1>(voff(ML), (size_t) A.kq[kind] + (size_t) kk * A.kqs + A.kH[kind], evn(LDK * s.n));
+        stage_arm_mat();
+    }
+
     // ---------------------------------------------------------------------------------------------
     // residuals of the QP at the iterate (OCP_QP_RES_COMPUTE, x_ocp_qp_res.c:345-531) -> residual set 0, with
     // UPDATE_VAR_QP fused (x_core_qp_ipm_aux.c:472-582: the iterate first moves by alpha_u along the step, with the
@@ -333,10 +350,9 @@ struct Ker
             const View v1 = viewr(k + 1);
             bulk<1, 0>(voff(SOLN), (size_t) v1.kk * A.ss + s1.sol.ux, n1e);
             if (update) bulk<2, 0>(voff(STPN), (size_t) v1.kk * A.ws + s1.step.ux, n1e);
-            bulk<0, 1>(voff(MA), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs, evn(LD * nx1), pf);
         }
-        bulk<0, 1>(voff(ML), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kH[KIND], LD * n, pf);
-        stage_arm();
+        stage_arm_vec();
+        if (KIND == 0) res_issue_mat(k);        // the matrices of every later stage were requested by the stage before it
         wait_vec();
         double *ux = SOL, *pi = SOL + (sd.sol.pi - sd.sol.ux), *lam = SOL + (sd.sol.lam - sd.sol.ux), *t = SOL + (sd.sol.t - sd.sol.ux);
         const double *du = STP, *dp = STP + (sd.step.pi - sd.step.ux), *dl = STP + (sd.step.lam - sd.step.ux), *dtt = STP + (sd.step.t - sd.step.ux);
@@ -395,8 +411,8 @@ struct Ker
         // ---- rows of res_g (lane = row), res_b (lane = column)
         {
             double hx[RPM > 0 ? RPM : 1], ap[RPM > 0 ? RPM : 1];
-            rows_dot<n, n>(ML, LD, ux, hx);
-            if (nx1 > 0) rows_dot<n, nx1>(MA, LD, pi, ap);
+            rows_dot<n, n>(ML, LDK, ux, hx);
+            if (nx1 > 0) rows_dot<n, nx1>(MA, LDK, pi, ap);
 #pragma unroll
             for (int m = 0; m < RP; m++)
             {
@@ -416,7 +432,7 @@ struct Ker
             if (nx1 > 0)
             {
                 double au[RPM > 0 ? RPM : 1];
-                cols_dot<n, nx1>(MA, LD, ux, au);
+                cols_dot<n, nx1>(MA, LDK, ux, au);
                 double *ob = v.w + sd.res.b;
 #pragma unroll
                 for (int m = 0; m < CP; m++)
@@ -435,7 +451,14 @@ struct Ker
                 }
             }
         }
-        fk_sync();
+        // last use of the two matrices: request those of the next stage, they arrive during the vector work below
+        if (KIND != 2)
+        {
+            stage_begin();
+            res_issue_mat(k + 1);
+        }
+        else
+            fk_sync();
         // ---- box scatter, slack rows
         for (int i = li; i < nb; i += G)
         {
@@ -635,11 +658,11 @@ struct Ker
             if (rr >= W4) hh[m] -= x0 * g0 + x1 * g1 + x2 * g2 + x3 * g3;
             if (rr >= 0 && r < n)
             {
-                double *mr = ML + r + LD * j0;
+                double *mr = ML + r + LDW * j0;
                 mr[0] = x0;
-                if (W4 > 1) mr[LD] = x1;
-                if (W4 > 2) mr[2 * LD] = x2;
-                if (W4 > 3) mr[3 * LD] = x3;
+                if (W4 > 1) mr[LDW] = x1;
+                if (W4 > 2) mr[2 * LDW] = x2;
+                if (W4 > 3) mr[3 * LDW] = x3;
                 if (act)
                 {
                     double *gr = Lg + r + n * j0;
@@ -667,6 +690,26 @@ struct Ker
         fk_sync();
     }
 
+    // inputs of stage k of the factorisation sweep (any stage: the offsets come from its descriptor at run time)
+    FK_DEV void fact_issue_vec(int k)
+    {
+        const StageDesc &s = sdr(k);
+        const unsigned kk = (k >= 1 && k < A.N) ? (unsigned) (k - 1) : 0u;
+        const int kind = k == 0 ? 0 : (k == A.N ? 2 : 1);
+        const int oRES = voff(V), oLT = oRES + (A.nve + NXe + 2 * A.nce), oZQ = oLT + 2 * A.nce;
+        bulk<2, 0>(oRES, (size_t) kk * A.ws + s.res.g, (int) (s.res.m - s.res.g) + evn(s.nc));
+        bulk<1, 0>(oLT, (size_t) kk * A.ss + s.sol.lam, (int) (s.sol.t - s.sol.lam) + evn(s.nc));
+        if (s.ns > 0) bulk<0, 0>(oZQ, (size_t) A.kq[kind] + (size_t) kk * A.kqs + A.kV[kind] + (s.q_Z - s.q_b), evn(2 * s.ns));
+        stage_arm_vec();
+    }
+    FK_DEV void fact_issue_mat(int k)
+    {
+        const StageDesc &s = sdr(k);
+        const unsigned kk = (k >= 1 && k < A.N) ? (unsigned) (k - 1) : 0u;
+        if (s.nx1 > 0) bulk<3, 1>(voff(MA), (size_t) kk * A.qs + s.q_BAt, evn(s.n * s.nx1));      // the caller's block: leading dimension n
+        stage_arm_mat();
+    }
+
     // ---------------------------------------------------------------------------------------------
     // one stage of the backward Riccati sweep with factorisation (OCP_QP_FACT_SOLVE_KKT_STEP, x_ocp_qp_kkt.c:880-966),
     // right-hand side = residual set 0.  ML holds L_{k+1} on entry and L_k on exit, lprev the x part of the gradient
@@ -685,24 +728,17 @@ struct Ker
         const int nb = sd.nb, ns = sd.ns, nc = sd.nc;
         const int *idxb = IDX + 2 * (A.nmaps == 3 ? KIND : k) * A.nbe, *rev = idxb + nb;
         const int nu1 = (nx1 > 0 && k + 1 < A.N) ? NU : 0;
-        const int resN = (int) (sd.res.m - sd.res.g) + evn(nc), ltN = (int) (sd.sol.t - sd.sol.lam) + evn(nc);
         double *RES = V, *LT = RES + (A.nve + NXe + 2 * A.nce), *ZQ = LT + 2 * A.nce, *Gam = ZQ + A.ns2e, *gam = Gam + A.nce;
         double *tmp0 = gam + A.nce, *tmp1 = tmp0 + A.nbe, *dadd = tmp1 + A.nbe, *Linv = dadd + NMe, *Zi = Linv + NMe, *ds = Zi + A.ns2e;
         double *alb = ds + A.ns2e, *lvec = alb + NXe, *lprev = lvec + NMe;
-        const int pf = (KIND == 1 && k > 1) ? -1 : 0;
-        stage_begin();
-        bulk<2, 0>(voff(RES), (size_t) v.kk * A.ws + sd.res.g, resN, pf);
-        bulk<1, 0>(voff(LT), (size_t) v.kk * A.ss + sd.sol.lam, ltN, pf);
-        if (ns > 0) bulk<0, 0>(voff(ZQ), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kV[KIND] + (sd.q_Z - sd.q_b), evn(2 * ns));
-        if (nx1 > 0) bulk<0, 1>(voff(MA), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs, evn(LD * nx1), pf);
-#ifdef FK_L2_PREFETCH
-        if (pf != 0 && fk_lane() == 0)
-        {   // the Hessian rows are read with plain loads: bring the block of the next stage of the sweep into L2 as well
-            const double *hp = rbase[0] + ((size_t) A.kq[KIND] + (size_t) (v.kk - 1) * A.kqs + A.kH[KIND]);
-            for (int g = 0; g < nvalid; g++) fk_prefetch_l2(hp + (size_t) g * rstep[0], (unsigned) (LD * n) * 8u);
+        // the inputs of stage N are fetched here; those of every other stage were requested by the stage before it in the sweep
+        // (vector images after its prologue, dynamics block after its last use of MA)
+        if (KIND == 2)
+        {
+            stage_begin();
+            fact_issue_vec(k);
+            fact_issue_mat(k);
         }
-#endif
-        stage_arm();
         wait_vec();
         double *rowv = RES;
         const double *rb = RES + (sd.res.b - sd.res.g), *rd = RES + (sd.res.d - sd.res.g), *rm = RES + (sd.res.m - sd.res.g);
@@ -754,7 +790,7 @@ struct Ker
         for (int m = 0; m < RP; m++) hh[m] = rowv[(li + G * m) < n ? li + G * m : 0];
         if (nx1 > 0)
         {
-            const double *Lx = ML + nu1 + LD * nu1;                 // Lxx(c, j) = Lx[c + LD*j], lower triangular
+            const double *Lx = ML + nu1 + LDW * nu1;                 // Lxx(c, j) = Lx[c + LDW*j], lower triangular
             // ---- gradient: alb = Lxx' b (lane = column), Pb = Lxx alb (lane = row), then alb += l_{k+1,x}
 #pragma unroll
             for (int m = 0; m < CP; m++)
@@ -763,7 +799,7 @@ struct Ker
                 if (j < nx1)
                 {
                     double s0 = 0.0, s1 = 0.0;
-                    const double *lcol = Lx + LD * j;
+                    const double *lcol = Lx + LDW * j;
                     int c = j;
                     for (; c + 1 < nx1; c += 2) { s0 += lcol[c] * rb[c]; s1 += lcol[c + 1] * rb[c + 1]; }
                     if (c < nx1) s0 += lcol[c] * rb[c];
@@ -781,14 +817,25 @@ struct Ker
                     {
                         double s0 = 0.0, s1 = 0.0;
                         int c = 0;
-                        for (; c + 1 <= i; c += 2) { s0 += Lx[i + LD * c] * alb[c]; s1 += Lx[i + LD * (c + 1)] * alb[c + 1]; }
-                        if (c <= i) s0 += Lx[i + LD * c] * alb[c];
+                        for (; c + 1 <= i; c += 2) { s0 += Lx[i + LDW * c] * alb[c]; s1 += Lx[i + LDW * (c + 1)] * alb[c + 1]; }
+                        if (c <= i) s0 += Lx[i + LDW * c] * alb[c];
                         st(Pb + i, s0 + s1);
                     }
                 }
             }
             fk_sync();
             for (int j = li; j < nx1; j += G) alb[j] += lprev[j];
+        }
+        // the vector images are dead from here on (gradient and diagonal additions are in registers / in their own arrays):
+        // request those of the next stage of the sweep, they arrive during the matrix work below
+        if (k > 0)
+        {
+            stage_begin();
+            fact_issue_vec(k - 1);
+        }
+        if (nx1 > 0)
+        {
+            const double *Lx = ML + nu1 + LDW * nu1;
             // ---- in place: AL = A * Lxx   (row slots x 8-column tiles)
 #pragma unroll
             for (int jt = 0; jt < nx1; jt += 8)
@@ -807,11 +854,11 @@ struct Ker
                     const int c = jt + h;
                     double a[RPM > 0 ? RPM : 1];
 #pragma unroll
-                    for (int m = 0; m < RP; m++) a[m] = MA[(li + G * m < n ? li + G * m : 0) + LD * c];
+                    for (int m = 0; m < RP; m++) a[m] = MA[(li + G * m < n ? li + G * m : 0) + n * c];
 #pragma unroll
                     for (int q = 0; q <= h; q++)
                     {
-                        const double l = Lx[c + LD * (jt + q)];
+                        const double l = Lx[c + LDW * (jt + q)];
 #pragma unroll
                         for (int m = 0; m < RP; m++) acc[m][q] += a[m] * l;
                     }
@@ -821,11 +868,11 @@ struct Ker
                 {
                     double a[RPM > 0 ? RPM : 1];
 #pragma unroll
-                    for (int m = 0; m < RP; m++) a[m] = MA[(li + G * m < n ? li + G * m : 0) + LD * c];
+                    for (int m = 0; m < RP; m++) a[m] = MA[(li + G * m < n ? li + G * m : 0) + n * c];
 #pragma unroll
                     for (int q = 0; q < 8; q++)
                     {
-                        const double l = Lx[c + LD * (jt + q)];
+                        const double l = Lx[c + LDW * (jt + q)];
 #pragma unroll
                         for (int m = 0; m < RP; m++) acc[m][q] += a[m] * l;
                     }
@@ -838,7 +885,7 @@ struct Ker
                     {
 #pragma unroll
                         for (int q = 0; q < 8; q++)
-                            if (q < w) MA[r + LD * (jt + q)] = acc[m][q];
+                            if (q < w) MA[r + n * (jt + q)] = acc[m][q];
                     }
                 }
             }
@@ -863,7 +910,7 @@ struct Ker
                 for (int q = 0; q < 8; q++)
                 {
                     acc[m][q] = 0.0;
-                    h[m][q] = (q < w && r < n && r >= jt + q) ? fk_ldg(Hk + r + LD * (jt + q)) : 0.0;
+                    h[m][q] = (q < w && r < n && r >= jt + q) ? fk_ldg(Hk + r + LDK * (jt + q)) : 0.0;
                 }
             }
             if (nx1 > 0)
@@ -873,11 +920,11 @@ struct Ker
                 {
                     double a[RPM > 0 ? RPM : 1], b[8];
 #pragma unroll
-                    for (int m = 0; m < RP; m++) a[m] = m >= m0 ? MA[(li + G * m < n ? li + G * m : 0) + LD * c] : 0.0;
+                    for (int m = 0; m < RP; m++) a[m] = m >= m0 ? MA[(li + G * m < n ? li + G * m : 0) + n * c] : 0.0;
 #pragma unroll
                     for (int q = 0; q < 8; q += 2)
                     {
-                        const fk_double2 t2 = fk_ld2(MA + jt + q + LD * c);       // rows jt+q, jt+q+1 of column c: 16-byte aligned
+                        const fk_double2 t2 = ld_pair<n % 2 == 0>(MA + jt + q + n * c);       // rows jt+q, jt+q+1 of column c
                         b[q] = t2.x; b[q + 1] = t2.y;
                     }
 #pragma unroll
@@ -893,16 +940,21 @@ struct Ker
                     }
                 }
             }
+            if (jt + 8 >= n && k > 0)
+            {   // last use of the dynamics block: request the one of the next stage of the sweep
+                stage_begin();
+                fact_issue_mat(k - 1);
+            }
 #pragma unroll 2
             for (int c = 0; c < jt; c++)
             {
                 double a[RPM > 0 ? RPM : 1], b[8];
 #pragma unroll
-                for (int m = 0; m < RP; m++) a[m] = m >= m0 ? ML[(li + G * m < n ? li + G * m : 0) + LD * c] : 0.0;
+                for (int m = 0; m < RP; m++) a[m] = m >= m0 ? ML[(li + G * m < n ? li + G * m : 0) + LDW * c] : 0.0;
 #pragma unroll
                 for (int q = 0; q < 8; q += 2)
                 {
-                    const fk_double2 t2 = fk_ld2(ML + jt + q + LD * c);
+                    const fk_double2 t2 = fk_ld2(ML + jt + q + LDW * c);
                     b[q] = t2.x; b[q + 1] = t2.y;
                 }
 #pragma unroll
@@ -939,7 +991,7 @@ struct Ker
 #pragma unroll
                     for (int q = 0; q < 4; q += 2)
                     {
-                        const fk_double2 t2 = fk_ld2(ML + jt + 4 + q + LD * (jt + c));
+                        const fk_double2 t2 = fk_ld2(ML + jt + 4 + q + LDW * (jt + c));
                         b[q] = t2.x; b[q + 1] = t2.y;
                     }
 #pragma unroll
@@ -1001,7 +1053,7 @@ struct Ker
         bulk<2, 0>(voff(RMB), (size_t) v.kk * A.ws + sd.w_rmb, evn(nc), pf);
         bulk<2, 0>(voff(STL), (size_t) v.kk * A.ws + sd.step.lam, stN, pf);
         bulk<0, 0>(voff(QM), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kV[KIND] + (sd.q_dmask - sd.q_b), qmN, pf);
-        if (nx1 > 0) bulk<0, 1>(voff(MA), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs, evn(LD * nx1), pf);
+        if (nx1 > 0) bulk<0, 1>(voff(MA), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs, evn(LDK * nx1), pf);
         if (nsolve > 0) bulk<2, 1>(voff(LU), (size_t) v.kk * A.ws + sd.w_L, evn(n * nsolve), pf);
         stage_arm();
         wait_vec();
@@ -1047,7 +1099,7 @@ struct Ker
         if (nx1 > 0)
         {
             double ap[RPM > 0 ? RPM : 1];
-            rows_dot<n, nx1>(MA, LD, tmpx, ap);
+            rows_dot<n, nx1>(MA, LDK, tmpx, ap);
 #pragma unroll
             for (int m = 0; m < RP; m++) x[m] += ap[m];
             fk_sync();
@@ -1150,10 +1202,10 @@ struct Ker
         {
             // p part (gradient vector of stage k+1) / backward value of x_{k+1}
             bulk<2, 0>(voff(P1), (size_t) v1.kk * A.ws + (after_fact ? s1p->w_lrow : s1p->step.ux), n1e, pf);
-            bulk<0, 1>(voff(MA), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs, evn(LD * nx1), pf);
+            bulk<0, 1>(voff(MA), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs, evn(LDK * nx1), pf);
         }
         if (nsolve > 0) bulk<2, 1>(voff(LU), (size_t) v.kk * A.ws + sd.w_L, evn(n * nsolve), pf);
-        if (do_lin) bulk<0, 1>(voff(ML), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kH[KIND], LD * n, pf);
+        if (do_lin) bulk<0, 1>(voff(ML), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kH[KIND], evn(LDK * n), pf);
         else if (nx1 > 0) bulk<2, 1>(voff(ML), (size_t) v1.kk * A.ws + s1p->w_L, evn(n1 * n1), pf);
         stage_arm();
         wait_vec();
@@ -1205,7 +1257,7 @@ struct Ker
         double hx[RPM > 0 ? RPM : 1];
         if (do_lin)
         {
-            rows_dot<n, n>(ML, LD, vv, hx);
+            rows_dot<n, n>(ML, LDK, vv, hx);
             if (nx1 > 0)
             {
                 stage_begin();
@@ -1217,7 +1269,7 @@ struct Ker
         if (nx1 > 0)
         {
             double av[RPM > 0 ? RPM : 1];
-            cols_dot<n, nx1>(MA, LD, vv, av);
+            cols_dot<n, nx1>(MA, LDK, vv, av);
             double *ob = v.w + sd.ires.b;
 #pragma unroll
             for (int m = 0; m < CP; m++)
@@ -1345,7 +1397,7 @@ struct Ker
             // ---- res_g of the linear system (lane = row): H dux + rhs_g - dpi_{k-1} + A dpi_k + constraint multipliers
             for (int i = li; i < nb; i += G) tmp0[i] = dlm[nb + i] - dlm[i];
             double ap[RPM > 0 ? RPM : 1];
-            if (nx1 > 0) rows_dot<n, nx1>(MA, LD, pik, ap);
+            if (nx1 > 0) rows_dot<n, nx1>(MA, LDK, pik, ap);
 #pragma unroll
             for (int m = 0; m < RP; m++)
             {

@@ -150,7 +150,8 @@ int cuipm::opts_check(const cuipm_opts *o)
     if (o->var_init_scheme != 1) { set_error("only var_init_scheme=1 (the acados default) is supported"); return CUIPM_ERR_INVALID; }
     if (o->m_relax != 0.0) { set_error("tau_min/m relaxation (m != 0) is not supported"); return CUIPM_ERR_INVALID; }
     if (o->itref_pred_max != 0) { set_error("itref_pred_max must be 0"); return CUIPM_ERR_INVALID; }
-    if (o->iter_max < 0 || o->stat_max < o->iter_max) { set_error("need 0 <= iter_max <= stat_max"); return CUIPM_ERR_INVALID; }
+    // stat_max may be smaller than iter_max: the kernels write row kk+1 of the statistics table only while kk+1 < stat_max
+    if (o->iter_max < 0 || o->stat_max < 0) { set_error("need iter_max >= 0 and stat_max >= 0"); return CUIPM_ERR_INVALID; }
     if (o->itref_corr_max < 0 || o->itref_corr_max > 8) { set_error("itref_corr_max out of range"); return CUIPM_ERR_INVALID; }
     return CUIPM_OK;
 }

@@ -152,17 +152,16 @@ inline bool fast_plan(const std::vector<StageDesc> &sd, const std::vector<int> &
     F.qp_stride = P.qp_stride; F.sol_stride = P.sol_stride; F.work_stride = P.work_stride; F.w_bkp = P.w_bkp;
     auto e = [](int n) { return (n + 1) & ~1; };
     F.nce = e(P.ncmax); F.nbe = e(P.nbgmax); F.ns2e = e(2 * P.nsmax); F.nve = e(P.nvsmax);
-    // kernel-side record: leading dimension >= nu+nx+1, = 2 (mod 4): row and column accesses in shared memory are both
-    // bank-conflict free and every column starts on a 16-byte boundary
+    // kernel-side record: odd leading dimension >= nu+nx: row and column accesses in shared memory are both bank-conflict free
     const int NM = a.nx + a.nu;
-    F.ld = ((NM + 2) / 4) * 4 + 2;
+    F.ld = NM | 1;
     unsigned o = 0;
     const StageDesc *three[3] = {&sd[0], &sd[1], &sd[N]};
     unsigned size[3];
     for (int t = 0; t < 3; t++)
     {
         const StageDesc &d = *three[t];
-        const unsigned szA = (unsigned) e(F.ld * d.nx1), szH = (unsigned) (F.ld * d.n);
+        const unsigned szA = (unsigned) e(F.ld * d.nx1), szH = (unsigned) e(F.ld * d.n);
         const unsigned szV = (d.q_stage + (unsigned) (d.q_stage_bytes / sizeof(double))) - d.q_b;
         F.kH[t] = szA; F.kV[t] = szA + szH;
         size[t] = szA + szH + (unsigned) e((int) szV);

@@ -137,6 +137,7 @@ void *ocp_qp_cuipm_memory_assign(void *config_, void *dims_, void *opts_, void *
     mem->seed_rec = (double *) c_ptr; c_ptr += l->sol_stride * sizeof(double);
     mem->sens_rec = (double *) c_ptr; c_ptr += l->sol_stride * sizeof(double);
     mem->stat = (double *) c_ptr; c_ptr += (acados_size_t) (opts->c.stat_max + 1) * CUIPM_STAT_M * sizeof(double);
+    mem->stat_max_alloc = opts->c.stat_max;
     cuipm_layout_destroy(l);
     mem->solver = NULL;
     mem->status = 0;
@@ -154,7 +155,7 @@ void ocp_qp_cuipm_memory_get(void *config_, void *mem_, const char *field, void 
     else if (!strcmp(field, "tau_iter"))
     {   /* barrier parameter of the last corrector step = sigma * mu of the last iteration (stat columns 3 and 6) */
         double tau = 0.0;
-        if (mem->iter > 0) tau = mem->stat[CUIPM_STAT_M * mem->iter + 3] * mem->stat[CUIPM_STAT_M * (mem->iter - 1) + 6];
+        if (mem->iter > 0 && mem->iter < mem->stat_max_alloc) tau = mem->stat[CUIPM_STAT_M * mem->iter + 3] * mem->stat[CUIPM_STAT_M * (mem->iter - 1) + 6];
         *(double *) value = tau;
     }
     else
@@ -295,7 +296,11 @@ int ocp_qp_cuipm(void *config_, void *qp_in_, void *qp_out_, void *opts_, void *
     double interface_time = acados_toc(&tot_timer);
 
     acados_tic(&qp_timer);
-    int rc = cuipm_solve_host(mem->solver, 1, mem->qp_rec, mem->sol_rec, &mem->info, mem->stat, &opts->c);
+    /* the statistics table was sized when the memory was created: iter_max may have been raised since (the reference
+     * keeps ws->stat_max of the workspace creation and guards every write with it, x_ocp_qp_ipm.c:2227) */
+    cuipm_opts o = opts->c;
+    if (o.stat_max > mem->stat_max_alloc) o.stat_max = mem->stat_max_alloc;
+    int rc = cuipm_solve_host(mem->solver, 1, mem->qp_rec, mem->sol_rec, &mem->info, mem->stat, &o);
     if (rc != CUIPM_OK)
     {
         printf("\nerror: ocp_qp_cuipm: %s\n", cuipm_last_error());
@@ -318,7 +323,7 @@ int ocp_qp_cuipm(void *config_, void *qp_in_, void *qp_out_, void *opts_, void *
     if (opts->print_level > 0)
     {
         printf("\nalpha_prim_aff\talpha_dual_aff\tmu_aff\t\tsigma\t\talpha_prim\talpha_dual\tmu\t\tres_stat\tres_eq\t\tres_ineq\tres_comp\tdual gap\tobj\n");
-        for (int i = 0; i <= mem->iter && i <= opts->c.stat_max; i++)
+        for (int i = 0; i <= mem->iter && i < mem->stat_max_alloc; i++)
         {
             for (int j = 0; j < 13; j++) printf("%e\t", mem->stat[CUIPM_STAT_M * i + j]);
             printf("\n");

@@ -36,6 +36,7 @@ typedef struct ocp_qp_cuipm_memory_
     double *qp_rec, *sol_rec;   /* host staging records for the single-QP path (pinned lazily is not possible in raw memory) */
     double *seed_rec, *sens_rec; /* staging records of eval_forw_sens / eval_adj_sens (solution layout) */
     double *stat;               /* (stat_max+1) x CUIPM_STAT_M table of the last solve (HPIPM's layout: row per iteration) */
+    int stat_max_alloc;         /* stat_max the table was sized with at memory creation (the reference freezes ws->stat_max there too) */
     cuipm_info info;
     double time_qp_solver_call;
     int iter;

@@ -20,6 +20,15 @@ static inline bool fk_any(bool p) { return simt::ballot(p) != 0u; }
 typedef simt::MBar fk_mbar_t;
 static inline void fk_mbar_init(fk_mbar_t *b, int count) { simt::mbar_init(b, count); }
 static inline void fk_bulk(double *dst, const double *src, unsigned bytes, fk_mbar_t *b) { simt::bulk_copy(b, dst, src, (int) bytes); }
+static inline void fk_bulk_groups(double *sdst, const double *gsrc, unsigned bytes, fk_mbar_t *b, int n, int gstride, size_t rstep, int nvalid)
+{
+    for (int g = 0; g < n; g++)
+    {
+        fk_bulk(sdst, gsrc, bytes, b);
+        sdst += gstride;
+        if (g + 1 < nvalid) gsrc += rstep;
+    }
+}
 static inline void fk_mbar_arrive_tx(fk_mbar_t *b, unsigned bytes) { simt::mbar_arrive_tx(b, (int) bytes); }
 static inline void fk_mbar_wait(fk_mbar_t *b, unsigned parity) { simt::mbar_wait(b, (int) parity); }
 static inline void fk_fence_async() {}

@@ -124,7 +124,11 @@ inline void mbar_init(MBar *b, int count) { *b = MBar(); b->pending_arrivals = c
 inline void bulk_copy(MBar *b, void *dst, const void *src, int bytes)
 {
     if (((size_t) dst & 15) || ((size_t) src & 15) || (bytes & 15)) { std::fprintf(stderr, "simt_emul: misaligned bulk copy\n"); std::abort(); }
-    b->copies.push_back({dst, src, bytes});
+    // a bulk copy may land at any time between its issue and the wait: SIMT_EMUL_EAGER=1 delivers it at once (a buffer that is
+    // overwritten while still in use shows up), the default delivers it at the wait (a buffer that is read too early shows up)
+    static const bool eager = std::getenv("SIMT_EMUL_EAGER") != nullptr;
+    if (eager) std::memcpy(dst, src, (size_t) bytes);
+    else b->copies.push_back({dst, src, bytes});
     b->tx -= bytes;
 }
 // arrive (one of `count` arrivals) and expect `bytes` more bytes of copies
