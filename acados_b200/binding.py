@@ -115,6 +115,10 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.cuipm_expand_device.restype = ip
     lib.cuipm_set_tuning.argtypes = [vp, C.c_char_p, ip]
     lib.cuipm_set_tuning.restype = ip
+    lib.cuipm_last_handed_back.argtypes = [vp]
+    lib.cuipm_last_handed_back.restype = ip
+    lib.cuipm_last_main_kernel_ms.argtypes = [vp]
+    lib.cuipm_last_main_kernel_ms.restype = C.c_float
     _lib = lib
     return lib
 
@@ -230,6 +234,14 @@ class CuipmSolver:
     @property
     def last_kernel_ms(self) -> float:
         return float(self.lib.cuipm_last_kernel_ms(self.handle))
+
+    @property
+    def last_main_kernel_ms(self) -> float:
+        return float(self.lib.cuipm_last_main_kernel_ms(self.handle))
+
+    @property
+    def last_handed_back(self) -> int:
+        return int(self.lib.cuipm_last_handed_back(self.handle))
 
     @property
     def last_launch_count(self) -> int:

@@ -49,6 +49,8 @@ struct cuipm_solver
     FastArgs F{};
     int *d_redo_list = nullptr, *d_redo_count = nullptr;
     double *d_qpk = nullptr;                 // kernel-side QP records (repack pass)
+    cudaEvent_t evk0 = nullptr, evk1 = nullptr;   // around the throughput kernel of the last cuipm_solve_device call
+    bool timed_fast = false;
 };
 
 #define CK(call)                                                                                        \
@@ -105,7 +107,9 @@ static int launch_batch(cuipm_solver *s, const LaunchArgs &a0, int slot, size_t 
         int rc = launch_repack(F, s->d_sd, (void *) stream);
         if (rc != 0) { set_error(std::string("kernel launch (repack): ") + cudaGetErrorString((cudaError_t) rc)); return CUIPM_ERR_CUDA; }
         (*launches)++;
+        if (slot == 0 && s->evk0) cudaEventRecord(s->evk0, stream);
         rc = launch_fast(F, (void *) stream);
+        if (slot == 0 && s->evk1) { cudaEventRecord(s->evk1, stream); s->timed_fast = true; }
         if (rc != 0) { set_error(std::string("kernel launch (throughput kernel): ") + cudaGetErrorString((cudaError_t) rc)); return CUIPM_ERR_CUDA; }
         (*launches)++;
         a.redo_list = F.redo_list;
@@ -146,6 +150,8 @@ extern "C" cuipm_solver *cuipm_create(const cuipm_shape *shape, int max_batch, i
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(); }
     cudaEventCreate(&s->ev0);
     cudaEventCreate(&s->ev1);
+    cudaEventCreate(&s->evk0);
+    cudaEventCreate(&s->evk1);
     for (int i = 0; i < cuipm_solver::kPipe; i++)
     {
         cudaStreamCreateWithFlags(&s->pipe[i], cudaStreamNonBlocking);
@@ -169,6 +175,8 @@ extern "C" void cuipm_destroy(cuipm_solver *s)
     cudaFree(s->d_redo_list); cudaFree(s->d_redo_count); cudaFree(s->d_qpk);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->evk0) cudaEventDestroy(s->evk0);
+    if (s->evk1) cudaEventDestroy(s->evk1);
     for (int i = 0; i < cuipm_solver::kPipe; i++)
     {
         if (s->pipe[i]) { cudaStreamSynchronize(s->pipe[i]); cudaStreamDestroy(s->pipe[i]); }
@@ -179,12 +187,36 @@ extern "C" void cuipm_destroy(cuipm_solver *s)
     delete s;
 }
 
+extern "C" void *cuipm_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { set_error("cudaHostAlloc failed"); return nullptr; }
+    return p;
+}
+extern "C" void cuipm_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 extern "C" const cuipm_layout *cuipm_get_layout(const cuipm_solver *s) { return s->layout; }
 extern "C" double *cuipm_device_qp_buffer(cuipm_solver *s) { return s->d_qp; }
 extern "C" double *cuipm_device_sol_buffer(cuipm_solver *s) { return s->d_sol; }
 extern "C" cuipm_info *cuipm_device_info_buffer(cuipm_solver *s) { return s->d_info; }
 extern "C" void *cuipm_stream(cuipm_solver *s) { return (void *) s->stream; }
 extern "C" int cuipm_last_launch_count(const cuipm_solver *s) { return s->last_launches; }
+extern "C" int cuipm_last_handed_back(cuipm_solver *s)
+{
+    if (!s || !s->fast_ok || !s->d_redo_count) return 0;
+    int total = 0, h[2 * cuipm_solver::kPipe];
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    if (cudaMemcpy(h, s->d_redo_count, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    for (int c = 0; c < cuipm_solver::kPipe; c++) total += h[2 * c];
+    return total;
+}
+extern "C" float cuipm_last_main_kernel_ms(cuipm_solver *s)
+{
+    float ms = 0.f;
+    if (s && s->timed_fast && cudaEventElapsedTime(&ms, s->evk0, s->evk1) == cudaSuccess) return ms;
+    return s ? s->last_ms : 0.f;
+}
 extern "C" float cuipm_last_kernel_ms(const cuipm_solver *s) { return s->last_ms; }
 
 extern "C" int cuipm_set_tuning(cuipm_solver *s, const char *key, int value)

@@ -27,7 +27,9 @@ struct StageDesc
     unsigned q_stage, q_stage_bytes;      // this stage's sub-record inside the QP record (16-byte multiple)
     unsigned w_fac, w_fac_bytes;          // factor part of the work record (L, Linv, lrow, Pb, Zs_inv)
     unsigned w_vec, w_vec_bytes;          // vector part of the work record
-    unsigned pad2_;                       // sizeof(StageDesc) is a multiple of 8: the kernel copies descriptors with 8-byte cp.async
+    unsigned w_Lxx;                       // work record: copy of the state block Lxx of L (nx x nx, leading dimension nx|1, zero above the
+                                          // diagonal) kept by the throughput kernel for its forward sweeps (odd leading dimension: row and
+                                          // column accesses both bank-conflict free); sizeof(StageDesc) stays a multiple of 8
 };
 static_assert(sizeof(StageDesc) % 8 == 0, "StageDesc must be a multiple of 8 bytes");
 

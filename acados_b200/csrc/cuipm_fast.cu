@@ -20,6 +20,14 @@ static __device__ __forceinline__ void fk_sync() { __syncwarp(); }
 static __device__ __forceinline__ double fk_shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 static __device__ __forceinline__ int fk_shfl_xor_i(int v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 static __device__ __forceinline__ bool fk_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+// 16-byte asynchronous global -> shared copies by single lanes (LDGSTS, no register staging; L1 bypassed: each range is read once
+// per sweep), completed by the per-thread group wait + a warp barrier
+static __device__ __forceinline__ void fk_cp16(double *sdst, const double *gsrc)
+{
+    const unsigned sa = (unsigned) __cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+static __device__ __forceinline__ void fk_cp_wait() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 // bulk asynchronous copies (TMA, cp.async.bulk): global -> shared, 16-byte aligned, multiple of 16 bytes, completion
 // counted in bytes on an mbarrier in shared memory (no register staging, one instruction per contiguous range)
 typedef unsigned long long fk_mbar_t;
@@ -78,6 +86,18 @@ static __device__ __forceinline__ fk_double2 fk_ld2(const double *p) { return *r
 static __device__ __forceinline__ double fk_rsqrt(double x) { return rsqrt(x); }
 static __device__ __forceinline__ int fk_atomic_inc(int *p) { return atomicAdd(p, 1); }
 
+#ifdef FK_PROFILE
+// development: cycles per sweep and per kind of wait, accumulated by lane 0 of every warp into cuipm_fast_prof[16]
+// (0 residual sweep, 1 factorisation, 2 forward sweeps, 3 backward substitutions, 4 mu_aff, 5 waits for vector images,
+// 6 waits for matrices, 7 whole solve, 8 warps)
+__device__ unsigned long long cuipm_fast_prof[32];
+__shared__ long long g_prof[32];
+#define FK_PROF_T0() long long t0_ = clock64()
+#define FK_PROF_ADD(slot) do { if (fk_lane() == 0) g_prof[slot] += clock64() - t0_; } while (0)
+// consecutive phases inside a stage: each ADD2 charges the time since the previous one
+#define FK_PROF_T2() long long t2_ = clock64()
+#define FK_PROF_ADD2(slot) do { const long long tn_ = clock64(); if (fk_lane() == 0) g_prof[slot] += tn_ - t2_; t2_ = tn_; } while (0)
+#endif
 #include "cuipm_fast_core.h"
 
 namespace cuipm {
@@ -91,6 +111,10 @@ __global__ void __launch_bounds__(32, MINB) cuipm_fast_kernel(const __grid_const
 {
     using K = fastk::Ker<NX, NU, G>;
     __shared__ __align__(8) fk_mbar_t bars[6];
+#ifdef FK_PROFILE
+    if (fk_lane() == 0) for (int i = 0; i < 32; i++) g_prof[i] = 0;
+    const long long tk0 = clock64();
+#endif
     K k(A, g_fsmem, bars);
     // persistent warps: each one fetches the next 32/G QPs of the batch until none is left (QPs need 6..18 iterations, and
     // a launch is a few waves of resident warps: a fixed assignment leaves SMs idle at the end of every wave)
@@ -102,6 +126,13 @@ __global__ void __launch_bounds__(32, MINB) cuipm_fast_kernel(const __grid_const
         if (first >= A.nbatch) break;
         k.run(first);
     }
+#ifdef FK_PROFILE
+    if (fk_lane() == 0)
+    {
+        g_prof[7] = clock64() - tk0; g_prof[8] = 1;
+        for (int i = 0; i < 32; i++) atomicAdd(&cuipm_fast_prof[i], (unsigned long long) g_prof[i]);
+    }
+#endif
 }
 
 // caller's QP records -> kernel-side records: dynamics block with leading dimension ld, Hessian as a full symmetric matrix
@@ -221,6 +252,15 @@ int launch_repack(const FastArgs &F, const StageDesc *sd, void *stream_)
     cuipm_repack_kernel<<<grid, 256, 0, stream>>>(F, sd);
     return (int) cudaGetLastError();
 }
+
+#ifdef FK_PROFILE
+extern "C" void cuipm_fast_prof_read(unsigned long long *out, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, cuipm_fast_prof, sizeof(unsigned long long) * 32);
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(cuipm_fast_prof, z, sizeof(z)); }
+}
+#endif
 
 int launch_fast(const FastArgs &F, void *stream_)
 {

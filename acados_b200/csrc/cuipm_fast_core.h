@@ -30,6 +30,13 @@
 
 #include "cuipm_device.h"
 
+#ifndef FK_PROF_T0
+#define FK_PROF_T0() do {} while (0)
+#define FK_PROF_ADD(slot) do {} while (0)
+#define FK_PROF_T2() do {} while (0)
+#define FK_PROF_ADD2(slot) do {} while (0)
+#endif
+
 namespace cuipm {
 namespace fastk {
 
@@ -55,7 +62,7 @@ struct Ker
     static constexpr int SZA = (LDK * NX + 1) & ~1;       // dynamics block [B'; A'] (-> A Lxx in place in the factorisation, leading dimension n there)
     static constexpr int SZL = LDW * NM;                  // L_{k+1} -> L_k (factorisation); Hessian / L_{k+1} (other sweeps)
     static constexpr int SZU = (NM * NU + 1) & ~1;        // first nu columns of L_k (substitutions), leading dimension n
-    static constexpr int SZD = 20;                        // 4 x 4 diagonal block + 4 gradient entries
+    static constexpr int SZD = 0;                         // (the diagonal blocks of the factorisation are published in the vector pool)
     static constexpr int MATS = SZA + SZL + SZU + SZD;
 
     // stage kinds: 0 = first (nx = 0), 1 = interior, 2 = last (nu = 0)
@@ -191,34 +198,58 @@ struct Ker
     template <int REC, int BAR>
     FK_DEV void bulk(int soff, size_t off, int nd, int pf = 0)
     {
-        // (one out-of-line copy of the issue loop: the ~35 call sites of a kernel instance were a quarter of its code)
-        if (fk_lane() == 0) fk_bulk_groups(smem0 + soff, rbase[REC] + off, (unsigned) nd * 8u, bars + BAR, QPW, A.gstride, rstep[REC], nvalid);
+        // lane 0 of every group issues the copy of its QP (the compiler serialises the 32/G different operand sets)
+        if (li == 0)
+            fk_bulk(smem0 + (size_t) gq * A.gstride + soff, (REC == 0 ? qk : (REC == 1 ? sol : (REC == 2 ? wk : qp))) + off, (unsigned) nd * 8u, bars + BAR);
         (void) pf;
         if (BAR == 0) tx0 += (unsigned) (QPW * nd) * 8u;
         else tx1 += (unsigned) (QPW * nd) * 8u;
+    }
+    // Vector images: contiguous range of `nd` doubles (even) of this group's record REC at record offset `off` -> dst (shared
+    // memory of the group), as 16-byte asynchronous copies by the lanes of the group (LDGSTS: all groups of the warp copy at
+    // once, a handful of instructions per range; a bulk copy per group costs ~25 issue slots of operand marshalling each).
+    // Completed by wait_vec().
+    template <int REC>
+    FK_DEV void vcopy(double *dst, size_t off, int nd)
+    {
+        const double *src = (REC == 0 ? qk : (REC == 1 ? sol : (REC == 2 ? wk : qp))) + off;
+        for (int e = 2 * li; e < nd; e += 2 * G) fk_cp16(dst + e, src + e);
     }
     // all lanes are done with the buffers the next copies overwrite
     FK_DEV void stage_begin() { fk_fence_async(); fk_sync(); }
     // the copies of this stage have been issued: announce their bytes
     FK_DEV void stage_arm()
     {
-        if (fk_lane() == 0) { fk_mbar_arrive_tx(bars, tx0); fk_mbar_arrive_tx(bars + 1, tx1); }
-        tx0 = tx1 = 0;
+        if (fk_lane() == 0) fk_mbar_arrive_tx(bars + 1, tx1);
+        tx1 = 0;
     }
-    FK_DEV void stage_arm_vec()
-    {
-        if (fk_lane() == 0) fk_mbar_arrive_tx(bars, tx0);
-        tx0 = 0;
-    }
+    FK_DEV void stage_arm_vec() {}
     // matrix copies announced separately (a second batch inside a stage, requests for the next stage)
     FK_DEV void stage_arm_mat()
     {
         if (fk_lane() == 0) fk_mbar_arrive_tx(bars + 1, tx1);
         tx1 = 0;
     }
-    FK_DEV void wait_vec() { fk_mbar_wait(bars, ph0); ph0 ^= 1u; }
-    FK_DEV void wait_mat() { fk_mbar_wait(bars + 1, ph1); ph1 ^= 1u; }
+    FK_DEV void wait_vec() { FK_PROF_T0(); fk_cp_wait(); fk_sync(); FK_PROF_ADD(5); }      // own copies landed, then everybody's
+    FK_DEV void wait_mat() { FK_PROF_T0(); fk_mbar_wait(bars + 1, ph1); ph1 ^= 1u; FK_PROF_ADD(6); }
     FK_DEV int voff(const double *p) const { return (int) (p - (smem0 + (size_t) gq * A.gstride)); }
+
+    // out[i] = 1 / t[i], i < nc, over the lanes of the group; four reciprocals per lane are in flight at once (a double
+    // precision division is a dependent chain of ~10 instructions: one after the other they dominated the vector phases)
+    FK_DEV void recip_vec(const double *t, double *out, int nc) const
+    {
+        for (int i0 = li; i0 < nc; i0 += 4 * G)
+        {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = t[i0 + G * u < nc ? i0 + G * u : i0];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = 1.0 / v[u];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (i0 + G * u < nc) out[i0 + G * u] = v[u];
+        }
+    }
 
     // ---- small dense helpers on shared memory -----------------------------------------------------------------------
     // y[i] (+)= sum_j M[i + ld*j] * x[j], j < nc, for the rows i = li, li+G, ... < nr of this lane (row access), x broadcast
@@ -341,15 +372,15 @@ struct Ker
         double *x1 = pim + NXe;
         const int pf = (KIND == 1 && k + 1 < A.N) ? 1 : 0;
         stage_begin();
-        bulk<1, 0>(voff(SOL), (size_t) v.kk * A.ss + sd.sol.ux, solN, pf);
-        if (update) bulk<2, 0>(voff(STP), (size_t) v.kk * A.ws + sd.step.ux, stpN, pf);
-        bulk<0, 0>(voff(QV), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kV[KIND], evn(qvN), pf);
+        vcopy<1>(SOL, (size_t) v.kk * A.ss + sd.sol.ux, solN);
+        if (update) vcopy<2>(STP, (size_t) v.kk * A.ws + sd.step.ux, stpN);
+        vcopy<0>(QV, (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kV[KIND], evn(qvN));
         if (nx1 > 0)
         {
             const StageDesc &s1 = sdr(k + 1);
             const View v1 = viewr(k + 1);
-            bulk<1, 0>(voff(SOLN), (size_t) v1.kk * A.ss + s1.sol.ux, n1e);
-            if (update) bulk<2, 0>(voff(STPN), (size_t) v1.kk * A.ws + s1.step.ux, n1e);
+            vcopy<1>(SOLN, (size_t) v1.kk * A.ss + s1.sol.ux, n1e);
+            if (update) vcopy<2>(STPN, (size_t) v1.kk * A.ws + s1.step.ux, n1e);
         }
         stage_arm_vec();
         if (KIND == 0) res_issue_mat(k);        // the matrices of every later stage were requested by the stage before it
@@ -505,7 +536,7 @@ struct Ker
                 R.m2 = fmax(R.m2, a);
                 R.f2 |= (a != a);
                 R.a_gap -= dv * lam[i];
-                double mm = lam[i] * t[i];
+                double mm = lam[i] * t[i] - A.o.m_relax;        // qp->m = m_relax everywhere (ocp_qp_hpipm.c:338-342)
                 mm *= msk[i];
                 R.a_mu += fabs(mm);
                 st(obk + i, mm);
@@ -596,96 +627,112 @@ struct Ker
     }
 
     // ---------------------------------------------------------------------------------------------
-    // 4-column panel of the left-looking Cholesky: x[m][xo..xo+3] hold the raw (updated) entries of columns j0..j0+3 of
-    // this lane's rows, hh[m] the gradient entries of those rows.  The 4 x 4 diagonal block and the 4 gradient entries are
-    // published through DD, the block is factorised redundantly by every lane (pivot rule blasfeo_ref/x_lapack_ref.c:84-91:
-    // a non-positive pivot gives a zero column), the rows below are scaled; the gradient takes one step of the forward
-    // substitution l = L^{-1} h (its entries j0..j0+3 become final, the entries of the rows below are updated).
-    // Results: x (kept for the update of the second half of the tile), ML (final columns of L), the work record (lower
-    // part), lvec / lrow (gradient), Linv.
+    // W-column panel (W <= 8: one tile) of the left-looking Cholesky: x[m][0..W-1] hold the raw (updated) entries of columns
+    // j0..j0+W-1 of this lane's rows, hh[m] the gradient entries of those rows.  The W x W diagonal block and its W
+    // gradient entries are published through DD8 (8 x 8 column-major + 8), the block is factorised redundantly by every
+    // lane (pivot rule blasfeo_ref/x_lapack_ref.c:84-91: a non-positive pivot gives a zero column) -- one chain of W
+    // reciprocal square roots per tile for all QPs of the warp --, every row then runs the same substitution against it (for
+    // a row of the block itself that reproduces the factor's row, the entries right of the diagonal are zero); the gradient
+    // takes W steps of the forward substitution l = L^{-1} h.
+    // Results: ML (final columns of L), the work record (lower part), lvec / lrow (gradient), Linv.
     // ---------------------------------------------------------------------------------------------
-    template <int n, int RP, int W4>
-    FK_DEV void panel4(int j0, int m0, double (&x)[RPM > 0 ? RPM : 1][8], int xo, double (&hh)[RPM > 0 ? RPM : 1], double *Lg, double *lrow,
-                       double *lvec, double *Linv)
+    template <int n, int nu, int RP, int W>
+    FK_DEV void panel8(int j0, int m0, double (&x)[RPM > 0 ? RPM : 1][8], double (&hh)[RPM > 0 ? RPM : 1], double *DD8, double *Lg, double *Lxg,
+                       double *lrow, double *lvec, double *Linv)
     {
 #pragma unroll
         for (int m = 0; m < RP; m++)
         {
             if (m < m0) continue;
             const int rr = li + G * m - j0;
-            if (rr >= 0 && rr < W4)
+            if (rr >= 0 && rr < W)
             {
 #pragma unroll
-                for (int q = 0; q < W4; q++) DD[rr + 4 * q] = x[m][xo + q];
-                DD[16 + rr] = hh[m];
+                for (int q = 0; q < W; q++) DD8[rr + 8 * q] = x[m][q];
+                DD8[64 + rr] = hh[m];
             }
         }
         fk_sync();
-        double d00 = DD[0], d10 = 0, d20 = 0, d30 = 0, d11 = 0, d21 = 0, d31 = 0, d22 = 0, d32 = 0, d33 = 0;
-        double h0 = DD[16], h1 = 0, h2 = 0, h3 = 0;
-        if (W4 > 1) { d10 = DD[1]; d11 = DD[5]; h1 = DD[17]; }
-        if (W4 > 2) { d20 = DD[2]; d21 = DD[6]; d22 = DD[10]; h2 = DD[18]; }
-        if (W4 > 3) { d30 = DD[3]; d31 = DD[7]; d32 = DD[11]; d33 = DD[15]; h3 = DD[19]; }
-        const double i0 = d00 > 0.0 ? fk_rsqrt(d00) : 0.0;
-        const double l10 = d10 * i0, l20 = d20 * i0, l30 = d30 * i0;
-        d11 -= l10 * l10;
-        const double i1 = d11 > 0.0 ? fk_rsqrt(d11) : 0.0;
-        const double l21 = (d21 - l20 * l10) * i1, l31 = (d31 - l30 * l10) * i1;
-        d22 -= l20 * l20 + l21 * l21;
-        const double i2 = d22 > 0.0 ? fk_rsqrt(d22) : 0.0;
-        const double l32 = (d32 - l30 * l20 - l31 * l21) * i2;
-        d33 -= l30 * l30 + l31 * l31 + l32 * l32;
-        const double i3 = d33 > 0.0 ? fk_rsqrt(d33) : 0.0;
-        // gradient entries of the block
-        const double g0 = h0 * i0;
-        const double g1 = W4 > 1 ? (h1 - l10 * g0) * i1 : 0.0;
-        const double g2 = W4 > 2 ? (h2 - l20 * g0 - l21 * g1) * i2 : 0.0;
-        const double g3 = W4 > 3 ? (h3 - l30 * g0 - l31 * g1 - l32 * g2) * i3 : 0.0;
+        double d[8][8], iv[8], g[8];       // d[i][j], i >= j: block entries, overwritten by the factor
+#pragma unroll
+        for (int j = 0; j < W; j++)
+        {
+#pragma unroll
+            for (int i = j; i < W; i++) d[i][j] = DD8[i + 8 * j];
+            g[j] = DD8[64 + j];
+        }
+#pragma unroll
+        for (int j = 0; j < W; j++)
+        {
+            double dj = d[j][j];
+#pragma unroll
+            for (int c = 0; c < j; c++) dj -= d[j][c] * d[j][c];
+            iv[j] = dj > 0.0 ? fk_rsqrt(dj) : 0.0;
+            double gj = g[j];
+#pragma unroll
+            for (int c = 0; c < j; c++) gj -= d[j][c] * g[c];
+            g[j] = gj * iv[j];
+#pragma unroll
+            for (int i = j + 1; i < W; i++)
+            {
+                double v = d[i][j];
+#pragma unroll
+                for (int c = 0; c < j; c++) v -= d[i][c] * d[j][c];
+                d[i][j] = v * iv[j];
+            }
+        }
 #pragma unroll
         for (int m = 0; m < RP; m++)
         {
             if (m < m0) continue;
-            const int r = li + G * m, rr = r - j0;     // position inside the panel: rows 0..3 form the diagonal block
-            double x0 = x[m][xo] * i0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
-            if (rr == 0) x0 = d00 * i0;
-            if (W4 > 1) x1 = rr == 0 ? 0.0 : (rr == 1 ? d11 * i1 : (x[m][xo + 1] - x0 * l10) * i1);
-            if (W4 > 2) x2 = rr <= 1 ? 0.0 : (rr == 2 ? d22 * i2 : (x[m][xo + 2] - x0 * l20 - x1 * l21) * i2);
-            if (W4 > 3) x3 = rr <= 2 ? 0.0 : (rr == 3 ? d33 * i3 : (x[m][xo + 3] - x0 * l30 - x1 * l31 - x2 * l32) * i3);
-            x[m][xo] = x0;
-            if (W4 > 1) x[m][xo + 1] = x1;
-            if (W4 > 2) x[m][xo + 2] = x2;
-            if (W4 > 3) x[m][xo + 3] = x3;
-            if (rr >= W4) hh[m] -= x0 * g0 + x1 * g1 + x2 * g2 + x3 * g3;
+            const int r = li + G * m, rr = r - j0;     // position relative to the panel: rows 0..W-1 form the diagonal block
+            double xs[8];
+#pragma unroll
+            for (int q = 0; q < W; q++)
+            {
+                double v = x[m][q];
+#pragma unroll
+                for (int c = 0; c < q; c++) v -= xs[c] * d[q][c];
+                v *= iv[q];
+                xs[q] = rr >= q ? v : 0.0;              // a row of the block ends at its diagonal entry
+            }
+            if (rr >= W)
+            {
+                double hv = hh[m];
+#pragma unroll
+                for (int q = 0; q < W; q++) hv -= xs[q] * g[q];
+                hh[m] = hv;
+            }
             if (rr >= 0 && r < n)
             {
                 double *mr = ML + r + LDW * j0;
-                mr[0] = x0;
-                if (W4 > 1) mr[LDW] = x1;
-                if (W4 > 2) mr[2 * LDW] = x2;
-                if (W4 > 3) mr[3 * LDW] = x3;
+#pragma unroll
+                for (int q = 0; q < W; q++) mr[q * LDW] = xs[q];
                 if (act)
                 {
                     double *gr = Lg + r + n * j0;
-                    gr[0] = x0;
-                    if (W4 > 1 && rr >= 1) gr[n] = x1;
-                    if (W4 > 2 && rr >= 2) gr[2 * n] = x2;
-                    if (W4 > 3 && rr >= 3) gr[3 * n] = x3;
+#pragma unroll
+                    for (int q = 0; q < W; q++)
+                        if (rr >= q) gr[q * n] = xs[q];
+                    // state block once more with an odd leading dimension, for the forward sweeps (zeros right of the diagonal
+                    // inside the block; what lies above the block is never written and stays zero)
+                    constexpr int nxk = n - nu, ldx = nxk | 1;
+                    if (nxk > 0 && r >= nu)
+                    {
+#pragma unroll
+                        for (int q = 0; q < W; q++)
+                            if (j0 + q >= nu) Lxg[(r - nu) + ldx * (j0 + q - nu)] = xs[q];
+                    }
                 }
             }
         }
         if (li == 0)
         {
-            Linv[j0] = i0; lvec[j0] = g0;
-            if (W4 > 1) { Linv[j0 + 1] = i1; lvec[j0 + 1] = g1; }
-            if (W4 > 2) { Linv[j0 + 2] = i2; lvec[j0 + 2] = g2; }
-            if (W4 > 3) { Linv[j0 + 3] = i3; lvec[j0 + 3] = g3; }
+#pragma unroll
+            for (int q = 0; q < W; q++) { Linv[j0 + q] = iv[q]; lvec[j0 + q] = g[q]; }
             if (act)
-            {
-                lrow[j0] = g0;
-                if (W4 > 1) lrow[j0 + 1] = g1;
-                if (W4 > 2) lrow[j0 + 2] = g2;
-                if (W4 > 3) lrow[j0 + 3] = g3;
-            }
+#pragma unroll
+                for (int q = 0; q < W; q++) lrow[j0 + q] = g[q];
         }
         fk_sync();
     }
@@ -697,9 +744,9 @@ struct Ker
         const unsigned kk = (k >= 1 && k < A.N) ? (unsigned) (k - 1) : 0u;
         const int kind = k == 0 ? 0 : (k == A.N ? 2 : 1);
         const int oRES = voff(V), oLT = oRES + (A.nve + NXe + 2 * A.nce), oZQ = oLT + 2 * A.nce;
-        bulk<2, 0>(oRES, (size_t) kk * A.ws + s.res.g, (int) (s.res.m - s.res.g) + evn(s.nc));
-        bulk<1, 0>(oLT, (size_t) kk * A.ss + s.sol.lam, (int) (s.sol.t - s.sol.lam) + evn(s.nc));
-        if (s.ns > 0) bulk<0, 0>(oZQ, (size_t) A.kq[kind] + (size_t) kk * A.kqs + A.kV[kind] + (s.q_Z - s.q_b), evn(2 * s.ns));
+        vcopy<2>((smem0 + (size_t) gq * A.gstride + oRES), (size_t) kk * A.ws + s.res.g, (int) (s.res.m - s.res.g) + evn(s.nc));
+        vcopy<1>((smem0 + (size_t) gq * A.gstride + oLT), (size_t) kk * A.ss + s.sol.lam, (int) (s.sol.t - s.sol.lam) + evn(s.nc));
+        if (s.ns > 0) vcopy<0>((smem0 + (size_t) gq * A.gstride + oZQ), (size_t) A.kq[kind] + (size_t) kk * A.kqs + A.kV[kind] + (s.q_Z - s.q_b), evn(2 * s.ns));
         stage_arm_vec();
     }
     FK_DEV void fact_issue_mat(int k)
@@ -723,14 +770,18 @@ struct Ker
     {
         constexpr int nx = KD<KIND>::nx, nu = KD<KIND>::nu, n = nx + nu, nx1 = KD<KIND>::nx1;
         constexpr int RP = (n + G - 1) / G, CP = (nx1 + G - 1) / G;
+        FK_PROF_T2();
         const StageDesc &sd = sdk<KIND>();
         const View v = view<KIND>(k);
         const int nb = sd.nb, ns = sd.ns, nc = sd.nc;
         const int *idxb = IDX + 2 * (A.nmaps == 3 ? KIND : k) * A.nbe, *rev = idxb + nb;
         const int nu1 = (nx1 > 0 && k + 1 < A.N) ? NU : 0;
         double *RES = V, *LT = RES + (A.nve + NXe + 2 * A.nce), *ZQ = LT + 2 * A.nce, *Gam = ZQ + A.ns2e, *gam = Gam + A.nce;
-        double *tmp0 = gam + A.nce, *tmp1 = tmp0 + A.nbe, *dadd = tmp1 + A.nbe, *Linv = dadd + NMe, *Zi = Linv + NMe, *ds = Zi + A.ns2e;
-        double *alb = ds + A.ns2e, *lvec = alb + NXe, *lprev = lvec + NMe;
+        double *tmp0 = gam + A.nce, *tmp1 = tmp0 + A.nbe, *Zi = tmp1 + A.nbe, *ds = Zi + A.ns2e, *ddx = ds + A.ns2e;
+        // Gam .. ds are dead once the gradient and the diagonal additions are formed: the diagonal blocks of the tiles are
+        // published there (72 doubles; ddx pads the block where the constraint arrays are shorter)
+        const int ddpad = 72 - (2 * A.nce + 2 * A.nbe + 2 * A.ns2e) > 0 ? 72 - (2 * A.nce + 2 * A.nbe + 2 * A.ns2e) : 0;
+        double *DD8 = Gam, *dadd = ddx + ddpad, *Linv = dadd + NMe, *alb = Linv + NMe, *lvec = alb + NXe, *lprev = lvec + NMe;
         // the inputs of stage N are fetched here; those of every other stage were requested by the stage before it in the sweep
         // (vector images after its prologue, dynamics block after its last use of MA)
         if (KIND == 2)
@@ -746,9 +797,10 @@ struct Ker
         {
             // Gamma, gamma (COMPUTE_GAMMA_GAMMA_QP, x_core_qp_ipm_aux.c:38-86)
             const double t_min_inv = A.o.t_min > 0 ? 1.0 / A.o.t_min : 1e30;
+            recip_vec(gt, Gam, nc);                  // same lane, same index below: no barrier needed
             for (int i = li; i < nc; i += G)
             {
-                const double l = gl[i], tt = gt[i], ti = 1.0 / tt;
+                const double l = gl[i], tt = gt[i], ti = Gam[i];
                 if (A.o.t_lam_min == 1)
                     Gam[i] = (tt < A.o.t_min ? t_min_inv : ti) * (l < A.o.lam_min ? A.o.lam_min : l);
                 else
@@ -785,6 +837,7 @@ struct Ker
         }
         wait_mat();
         fk_sync();
+        FK_PROF_ADD2(10);      /* prologue + waits */
         double hh[RPM > 0 ? RPM : 1];
 #pragma unroll
         for (int m = 0; m < RP; m++) hh[m] = rowv[(li + G * m) < n ? li + G * m : 0];
@@ -792,36 +845,19 @@ struct Ker
         {
             const double *Lx = ML + nu1 + LDW * nu1;                 // Lxx(c, j) = Lx[c + LDW*j], lower triangular
             // ---- gradient: alb = Lxx' b (lane = column), Pb = Lxx alb (lane = row), then alb += l_{k+1,x}
+            // (ML is zero above the diagonal for the whole sweep: fact_backward clears it, the panels write zeros there)
+            {
+                double tt_[RPM > 0 ? RPM : 1];
+                cols_dot<nx1, nx1>(Lx, LDW, rb, tt_);
 #pragma unroll
-            for (int m = 0; m < CP; m++)
-            {
-                const int j = li + G * m;
-                if (j < nx1)
-                {
-                    double s0 = 0.0, s1 = 0.0;
-                    const double *lcol = Lx + LDW * j;
-                    int c = j;
-                    for (; c + 1 < nx1; c += 2) { s0 += lcol[c] * rb[c]; s1 += lcol[c + 1] * rb[c + 1]; }
-                    if (c < nx1) s0 += lcol[c] * rb[c];
-                    alb[j] = s0 + s1;
-                }
-            }
-            fk_sync();
-            {
+                for (int m = 0; m < CP; m++)
+                    if (li + G * m < nx1) alb[li + G * m] = tt_[m];
+                fk_sync();
+                rows_dot<nx1, nx1>(Lx, LDW, alb, tt_);
                 double *Pb = v.w + sd.w_Pb;
 #pragma unroll
                 for (int m = 0; m < CP; m++)
-                {
-                    const int i = li + G * m;
-                    if (i < nx1)
-                    {
-                        double s0 = 0.0, s1 = 0.0;
-                        int c = 0;
-                        for (; c + 1 <= i; c += 2) { s0 += Lx[i + LDW * c] * alb[c]; s1 += Lx[i + LDW * (c + 1)] * alb[c + 1]; }
-                        if (c <= i) s0 += Lx[i + LDW * c] * alb[c];
-                        st(Pb + i, s0 + s1);
-                    }
-                }
+                    if (li + G * m < nx1) st(Pb + li + G * m, tt_[m]);
             }
             fk_sync();
             for (int j = li; j < nx1; j += G) alb[j] += lprev[j];
@@ -836,6 +872,7 @@ struct Ker
         if (nx1 > 0)
         {
             const double *Lx = ML + nu1 + LDW * nu1;
+            FK_PROF_ADD2(11);      /* gradient */
             // ---- in place: AL = A * Lxx   (row slots x 8-column tiles)
 #pragma unroll
             for (int jt = 0; jt < nx1; jt += 8)
@@ -863,7 +900,7 @@ struct Ker
                         for (int m = 0; m < RP; m++) acc[m][q] += a[m] * l;
                     }
                 }
-#pragma unroll 2
+#pragma unroll 4
                 for (int c = jt + 8; c < nx1; c++)
                 {
                     double a[RPM > 0 ? RPM : 1];
@@ -891,6 +928,7 @@ struct Ker
             }
             fk_sync();
         }
+        FK_PROF_ADD2(12);      /* TRMM */
         // ---- column tiles: SYRK + left-looking Cholesky, rows r >= jt; gradient h = g + AL alb in the first tile
         const double *Hk = v.k + A.kH[KIND];
         double *Lg = v.w + sd.w_L, *lrow = v.w + sd.w_lrow;
@@ -975,36 +1013,17 @@ struct Ker
                         if (q < w && r == jt + q) acc[m][q] += dadd[r < n ? r : 0];
                     }
                 }
-            // ---- first half of the tile
-            if (w >= 4) panel4<n, RP, 4>(jt, m0, acc, 0, hh, Lg, lrow, lvec, Linv);
-            else if (w == 3) panel4<n, RP, 3>(jt, m0, acc, 0, hh, Lg, lrow, lvec, Linv);
-            else if (w == 2) panel4<n, RP, 2>(jt, m0, acc, 0, hh, Lg, lrow, lvec, Linv);
-            else panel4<n, RP, 1>(jt, m0, acc, 0, hh, Lg, lrow, lvec, Linv);
-            if (w > 4)
-            {
-                // ---- second half: update with the four columns just finished, then its own panel
-                const int m1 = (jt + 4) / G;
-#pragma unroll
-                for (int c = 0; c < 4; c++)
-                {
-                    double b[4];
-#pragma unroll
-                    for (int q = 0; q < 4; q += 2)
-                    {
-                        const fk_double2 t2 = fk_ld2(ML + jt + 4 + q + LDW * (jt + c));
-                        b[q] = t2.x; b[q + 1] = t2.y;
-                    }
-#pragma unroll
-                    for (int m = 0; m < RP; m++)
-                        if (m >= m1)
-#pragma unroll
-                            for (int q = 0; q < 4; q++) acc[m][4 + q] -= acc[m][c] * b[q];
-                }
-                if (w >= 8) panel4<n, RP, 4>(jt + 4, m1, acc, 4, hh, Lg, lrow, lvec, Linv);
-                else if (w == 7) panel4<n, RP, 3>(jt + 4, m1, acc, 4, hh, Lg, lrow, lvec, Linv);
-                else if (w == 6) panel4<n, RP, 2>(jt + 4, m1, acc, 4, hh, Lg, lrow, lvec, Linv);
-                else panel4<n, RP, 1>(jt + 4, m1, acc, 4, hh, Lg, lrow, lvec, Linv);
-            }
+            FK_PROF_ADD2(13);      /* SYRK + update + H */
+            // ---- the tile's columns: diagonal block, rows below, gradient
+            if (w >= 8) panel8<n, nu, RP, 8>(jt, m0, acc, hh, DD8, Lg, v.w + sd.w_Lxx, lrow, lvec, Linv);
+            else if (w == 7) panel8<n, nu, RP, 7>(jt, m0, acc, hh, DD8, Lg, v.w + sd.w_Lxx, lrow, lvec, Linv);
+            else if (w == 6) panel8<n, nu, RP, 6>(jt, m0, acc, hh, DD8, Lg, v.w + sd.w_Lxx, lrow, lvec, Linv);
+            else if (w == 5) panel8<n, nu, RP, 5>(jt, m0, acc, hh, DD8, Lg, v.w + sd.w_Lxx, lrow, lvec, Linv);
+            else if (w == 4) panel8<n, nu, RP, 4>(jt, m0, acc, hh, DD8, Lg, v.w + sd.w_Lxx, lrow, lvec, Linv);
+            else if (w == 3) panel8<n, nu, RP, 3>(jt, m0, acc, hh, DD8, Lg, v.w + sd.w_Lxx, lrow, lvec, Linv);
+            else if (w == 2) panel8<n, nu, RP, 2>(jt, m0, acc, hh, DD8, Lg, v.w + sd.w_Lxx, lrow, lvec, Linv);
+            else panel8<n, nu, RP, 1>(jt, m0, acc, hh, DD8, Lg, v.w + sd.w_Lxx, lrow, lvec, Linv);
+            FK_PROF_ADD2(14);      /* panels */
         }
         {
             double *li_ = v.w + sd.w_Linv;
@@ -1015,6 +1034,10 @@ struct Ker
 
     FK_DEV void fact_backward()
     {
+        // the factor is built in ML; its strict upper triangle must read as zero (the triangular products of the sweep run
+        // over full rows / columns), and the other sweeps leave the Hessian there
+        fk_sync();
+        for (int e = li; e < SZL; e += G) ML[e] = 0.0;
         fk_fence_async_global();        // the records this sweep reads with bulk copies were written with plain stores by the sweeps before
 
         fact_stage<2>(A.N);
@@ -1047,12 +1070,12 @@ struct Ker
         const bool so = act && stw;
         const int pf = (KIND == 1 && k > 1) ? -1 : 0;
         stage_begin();
-        bulk<2, 0>(voff(RES), (size_t) v.kk * A.ws + sd.res.g, resN, pf);
-        bulk<1, 0>(voff(LT), (size_t) v.kk * A.ss + sd.sol.lam, ltN, pf);
-        bulk<2, 0>(voff(FV), (size_t) v.kk * A.ws + sd.w_Linv, fvN, pf);
-        bulk<2, 0>(voff(RMB), (size_t) v.kk * A.ws + sd.w_rmb, evn(nc), pf);
-        bulk<2, 0>(voff(STL), (size_t) v.kk * A.ws + sd.step.lam, stN, pf);
-        bulk<0, 0>(voff(QM), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kV[KIND] + (sd.q_dmask - sd.q_b), qmN, pf);
+        vcopy<2>(RES, (size_t) v.kk * A.ws + sd.res.g, resN);
+        vcopy<1>(LT, (size_t) v.kk * A.ss + sd.sol.lam, ltN);
+        vcopy<2>(FV, (size_t) v.kk * A.ws + sd.w_Linv, fvN);
+        vcopy<2>(RMB, (size_t) v.kk * A.ws + sd.w_rmb, evn(nc));
+        vcopy<2>(STL, (size_t) v.kk * A.ws + sd.step.lam, stN);
+        vcopy<0>(QM, (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kV[KIND] + (sd.q_dmask - sd.q_b), qmN);
         if (nx1 > 0) bulk<0, 1>(voff(MA), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs, evn(LDK * nx1), pf);
         if (nsolve > 0) bulk<2, 1>(voff(LU), (size_t) v.kk * A.ws + sd.w_L, evn(n * nsolve), pf);
         stage_arm();
@@ -1064,9 +1087,10 @@ struct Ker
         {
             double *grm = v.w + sd.res.m;
             const double t_min_inv = A.o.t_min > 0 ? 1.0 / A.o.t_min : 1e30;
+            recip_vec(gt, Gam, nc);
             for (int i = li; i < nc; i += G)
             {
-                const double l = gl[i], tt = gt[i], ti = 1.0 / tt;
+                const double l = gl[i], tt = gt[i], ti = Gam[i];
                 double m = rm_mode == 1 ? RMB[i] + dtt[i] * dl[i] - sigma_mu : RMB[i] - sigma_mu;
                 m *= gm[i];
                 if (so) grm[i] = m;
@@ -1176,6 +1200,7 @@ struct Ker
         constexpr int nx = KD<KIND>::nx, nu = KD<KIND>::nu, n = nx + nu, nx1 = KD<KIND>::nx1;
         constexpr int nsolve = nu;
         constexpr int RP = (n + G - 1) / G, CP = (nx1 + G - 1) / G;
+        FK_PROF_T2();
         const StageDesc &sd = sdk<KIND>();
         const View v = view<KIND>(k);
         const int nb = sd.nb, ns = sd.ns, nc = sd.nc;
@@ -1193,20 +1218,20 @@ struct Ker
         if (nx1 > 0) { s1p = &sdr(k + 1); v1 = viewr(k + 1); }
         const int pf = (KIND == 1 && k + 2 < A.N) ? 1 : 0;
         stage_begin();
-        bulk<2, 0>(voff(RES), (size_t) v.kk * A.ws + sd.res.g, resN, pf);
-        bulk<1, 0>(voff(LT), (size_t) v.kk * A.ss + sd.sol.lam, ltN, pf);
-        bulk<2, 0>(voff(FV), (size_t) v.kk * A.ws + sd.w_Linv, fvN, pf);
-        bulk<2, 0>(voff(SUX), (size_t) v.kk * A.ws + sd.step.ux, evn(n + 2 * ns), pf);
-        bulk<0, 0>(voff(QM), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kV[KIND] + (sd.q_dmask - sd.q_b), qmN, pf);
+        vcopy<2>(RES, (size_t) v.kk * A.ws + sd.res.g, resN);
+        vcopy<1>(LT, (size_t) v.kk * A.ss + sd.sol.lam, ltN);
+        vcopy<2>(FV, (size_t) v.kk * A.ws + sd.w_Linv, fvN);
+        vcopy<2>(SUX, (size_t) v.kk * A.ws + sd.step.ux, evn(n + 2 * ns));
+        vcopy<0>(QM, (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kV[KIND] + (sd.q_dmask - sd.q_b), qmN);
         if (nx1 > 0)
         {
             // p part (gradient vector of stage k+1) / backward value of x_{k+1}
-            bulk<2, 0>(voff(P1), (size_t) v1.kk * A.ws + (after_fact ? s1p->w_lrow : s1p->step.ux), n1e, pf);
+            vcopy<2>(P1, (size_t) v1.kk * A.ws + (after_fact ? s1p->w_lrow : s1p->step.ux), n1e);
             bulk<0, 1>(voff(MA), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs, evn(LDK * nx1), pf);
         }
         if (nsolve > 0) bulk<2, 1>(voff(LU), (size_t) v.kk * A.ws + sd.w_L, evn(n * nsolve), pf);
         if (do_lin) bulk<0, 1>(voff(ML), (size_t) A.kq[KIND] + (size_t) v.kk * A.kqs + A.kH[KIND], evn(LDK * n), pf);
-        else if (nx1 > 0) bulk<2, 1>(voff(ML), (size_t) v1.kk * A.ws + s1p->w_L, evn(n1 * n1), pf);
+        else if (nx1 > 0) bulk<2, 1>(voff(ML), (size_t) v1.kk * A.ws + s1p->w_Lxx, evn((nx1 | 1) * nx1), pf);
         stage_arm();
         wait_vec();
         const double *gv = RES, *bs = RES + (sd.res.b - sd.res.g), *rds = RES + (sd.res.d - sd.res.g), *rms = RES + (sd.res.m - sd.res.g);
@@ -1221,6 +1246,7 @@ struct Ker
         }
         wait_mat();
         fk_sync();
+        FK_PROF_ADD2(16);      /* issue + waits */
         // ---- TRSV_LTN(_MN): u = -Luu^{-T} (l_u + Lxu' x): the dot products over the x rows by the group, the small triangle
         // redundantly by every lane
         if (nsolve > 0)
@@ -1253,6 +1279,7 @@ struct Ker
             for (int i = li; i < n; i += G)
                 if (so) o_[i] = vv[i];
         }
+        FK_PROF_ADD2(17);      /* u */
         // ---- H v (for the residual of the linear system) while ML holds the Hessian, then ML <- L_{k+1}
         double hx[RPM > 0 ? RPM : 1];
         if (do_lin)
@@ -1261,10 +1288,11 @@ struct Ker
             if (nx1 > 0)
             {
                 stage_begin();
-                bulk<2, 1>(voff(ML), (size_t) v1.kk * A.ws + s1p->w_L, evn(n1 * n1), pf);
+                bulk<2, 1>(voff(ML), (size_t) v1.kk * A.ws + s1p->w_Lxx, evn((nx1 | 1) * nx1), pf);
                 stage_arm_mat();
             }
         }
+        FK_PROF_ADD2(18);      /* H v */
         // ---- x+ = A' v + b
         if (nx1 > 0)
         {
@@ -1291,8 +1319,12 @@ struct Ker
                 }
             }
         }
+        FK_PROF_ADD2(19);      /* x+ */
         // ---- constraint part of the step at this stage
         {
+            double *tis = dlm;                   // 1 / t; shares the array of the masked multiplier steps: entry i is read, then
+                                                 // overwritten, by the same lane in the loop over the constraints below
+            recip_vec(ts, tis, nc);
             for (int i = li; i < nb; i += G)
             {
                 const double a = vv[idxb[i]];
@@ -1311,7 +1343,7 @@ struct Ker
                         if (rev[i] == jj)
                         {
                             const double l = lam[offc + i], tt = ts[offc + i];
-                            const double Gm = A.o.t_lam_min == 1 ? (tt < A.o.t_min ? t_min_inv : 1.0 / tt) * (l < A.o.lam_min ? A.o.lam_min : l) : (1.0 / tt) * l;
+                            const double Gm = A.o.t_lam_min == 1 ? (tt < A.o.t_min ? t_min_inv : tis[offc + i]) * (l < A.o.lam_min ? A.o.lam_min : l) : tis[offc + i] * l;
                             d += Gm * dt[offc + i];
                         }
                     d = -Zi[j] * d;
@@ -1332,7 +1364,7 @@ struct Ker
             double *odl = v.w + sd.step.lam, *odt = v.w + sd.step.t, *ld_ = v.w + sd.ires.d, *lm_ = v.w + sd.ires.m;
             for (int i = li; i < nc; i += G)
             {
-                const double l = lam[i], tt = ts[i], ti = 1.0 / tt, rdi = rds[i], rmi = rms[i];
+                const double l = lam[i], tt = ts[i], ti = tis[i], rdi = rds[i], rmi = rms[i];
                 const double dtr = dt[i];
                 double dl = -ti * (rmi + (l * dtr) - (l * rdi));
                 double dti = dtr - rdi;
@@ -1362,14 +1394,16 @@ struct Ker
                 }
             }
         }
+        FK_PROF_ADD2(20);      /* constraint step */
         // ---- pi = P x+ + p with the factor of the next stage
         if (nx1 > 0)
         {
             if (do_lin) wait_mat();
             fk_sync();
-            const double *Lx = ML + nu1 + n1 * nu1;                          // Lxx of stage k+1, leading dimension n1, zero above the diagonal
+            const double *Lx = ML;                                           // Lxx of stage k+1, odd leading dimension, zero above the diagonal
+            constexpr int ldx = nx1 | 1;
             double tt_[RPM > 0 ? RPM : 1];
-            cols_dot<nx1, nx1>(Lx, n1, x1, tt_);
+            cols_dot<nx1, nx1>(Lx, ldx, x1, tt_);
 #pragma unroll
             for (int m = 0; m < CP; m++)
             {
@@ -1378,7 +1412,7 @@ struct Ker
             }
             fk_sync();
             double *pi = v.w + sd.step.pi;
-            rows_dot<nx1, nx1>(Lx, n1, tmp, tt_);
+            rows_dot<nx1, nx1>(Lx, ldx, tmp, tt_);
 #pragma unroll
             for (int m = 0; m < CP; m++)
             {
@@ -1392,6 +1426,7 @@ struct Ker
             }
         }
         fk_sync();
+        FK_PROF_ADD2(21);      /* pi */
         if (do_lin)
         {
             // ---- res_g of the linear system (lane = row): H dux + rhs_g - dpi_{k-1} + A dpi_k + constraint multipliers
@@ -1435,6 +1470,7 @@ struct Ker
                 F.f0 |= (a != a);
             }
         }
+        FK_PROF_ADD2(22);      /* residual rows */
         if (nx1 > 0)
         {
             for (int j = li; j < nx1; j += G)
@@ -1670,7 +1706,7 @@ struct Ker
         // one inner loop.
         for (int kk = 0;; kk++)
         {
-            res_pass(kk > 0, Q.alpha, Q);
+            { FK_PROF_T0(); res_pass(kk > 0, Q.alpha, Q); FK_PROF_ADD(0); }
             if (stat && act && kk < A.o.stat_max && li == 0)
             {
                 double *sr = stat + SM * (size_t) kk;
@@ -1711,11 +1747,10 @@ struct Ker
             for (int ph = 0; ph < 3; ph++)
             {
                 const bool stw = ph < 2 ? true : need;
-                if (ph == 0) fact_backward();
-                else solve_backward(ph, sigma_mu, stw);
+                { FK_PROF_T0(); if (ph == 0) fact_backward(); else solve_backward(ph, sigma_mu, stw); FK_PROF_ADD(ph == 0 ? 1 : 3); }
                 const int do_lin = ph == 0 ? A.o.lq_fact == 1 : A.o.itref_corr_max > 0;
                 double nr[4] = {0, 0, 0, 0};
-                const double al = forward_pass(ph == 0, do_lin, stw, nr);
+                double al; { FK_PROF_T0(); al = forward_pass(ph == 0, do_lin, stw, nr); FK_PROF_ADD(2); }
                 if (stw) { alpha = al; nrm[0] = nr[0]; nrm[1] = nr[1]; nrm[2] = nr[2]; nrm[3] = nr[3]; }
                 if (ph == 0)
                 {
@@ -1733,7 +1768,7 @@ struct Ker
                 else if (ph == 2 || A.o.cond_pred_corr != 1)
                     break;
                 const double mu_aff0 = mu_aff;
-                mu_aff = mu_aff_pass(alpha);
+                { FK_PROF_T0(); mu_aff = mu_aff_pass(alpha); FK_PROF_ADD(4); }
                 if (ph == 0)
                 {
                     const double tmp = mu_aff / Q.mu;
@@ -1784,7 +1819,8 @@ inline int vector_pool_doubles(int NX, int NM, int nce, int nbe, int ns2e, int n
     const int nxe = (NX + 1) & ~1, nme = (NM + 2) & ~1;
     const int img = nve + nxe + 2 * nce;                                  // image of a (ux|g, pi|b, lam|d, t|m) record range
     const int v_res = 2 * img + 2 * nme + (nxe + nme + 2 * nce + 2 * ns2e) + 2 * nbe + nve + 2 * nxe;
-    const int v_fact = img + 2 * nce + ns2e + 2 * nce + 2 * nbe + 2 * nme + 2 * ns2e + nxe + nme + nxe;
+    const int dd8 = 72 - (2 * nce + 2 * nbe + 2 * ns2e) > 0 ? 72 - (2 * nce + 2 * nbe + 2 * ns2e) : 0;
+    const int v_fact = img + 2 * nce + ns2e + 2 * nce + 2 * nbe + 2 * ns2e + dd8 + 2 * nme + nxe + nme + nxe;
     const int v_slv = img + 2 * nce + (2 * nme + nxe + ns2e) + nce + 2 * nce + (nce + ns2e) + 2 * nce + 2 * nbe + ns2e + 2 * nxe;
     const int v_fwd = img + 2 * nce + (2 * nme + nxe + ns2e) + nve + nme + (nce + ns2e) + nve + nxe + nve + 2 * nxe + 2 * nce + ns2e + nbe;
     const int v_init = nve + nce, v_mu = 16 * nce;

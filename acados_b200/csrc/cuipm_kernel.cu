@@ -490,7 +490,7 @@ struct Ker
                     if (!lin)
                     {
                         a_gap -= dv * lam[i];
-                        mm = lam[i] * t[i];
+                        mm = lam[i] * t[i] - CX.o.m_relax;        // qp->m = m_relax everywhere (ocp_qp_hpipm.c:338-342, x_ocp_qp_res.c:513-514)
                         if (CX.mask_constr) mm *= msk[i];
                         a_mu += fabs(mm);
                         obk[i] = mm;

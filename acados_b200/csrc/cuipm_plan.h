@@ -60,6 +60,7 @@ inline int build_plan(const cuipm_shape *sh, const cuipm_layout *l, std::vector<
         d.q_stage_bytes = (unsigned) ((l->qp_stage[k + 1] - l->qp_stage[k]) * sizeof(double));
         d.w_fac = (unsigned) w;
         d.w_L = take((size_t) d.n * d.n); d.w_Linv = take(d.n); d.w_lrow = take(d.n); d.w_Pb = take(d.nx1); d.w_Zsi = take(2 * d.ns);
+        d.w_Lxx = take((size_t) (d.nx | 1) * d.nx);
         d.w_fac_bytes = (unsigned) ((w - d.w_fac) * sizeof(double));
         d.w_vec = (unsigned) w;
         d.step = VOff{take(nvs), take(d.nx1), take(d.nc), take(d.nc)};
@@ -138,7 +139,7 @@ inline bool fast_plan(const std::vector<StageDesc> &sd, const std::vector<int> &
         ok = ok && d.q_BAt == a.q_BAt + dq && d.q_RSQ == a.q_RSQ + dq && d.q_b == a.q_b + dq && d.q_rq == a.q_rq + dq && d.q_d == a.q_d + dq
              && d.q_dmask == a.q_dmask + dq && d.q_Z == a.q_Z + dq && d.q_z == a.q_z + dq && d.q_stage == a.q_stage + dq;
         ok = ok && d.sol.ux == a.sol.ux + dsol && d.sol.pi == a.sol.pi + dsol && d.sol.lam == a.sol.lam + dsol && d.sol.t == a.sol.t + dsol;
-        ok = ok && d.w_L == a.w_L + dw && d.w_Linv == a.w_Linv + dw && d.w_lrow == a.w_lrow + dw && d.w_Pb == a.w_Pb + dw && d.w_Zsi == a.w_Zsi + dw
+        ok = ok && d.w_L == a.w_L + dw && d.w_Linv == a.w_Linv + dw && d.w_lrow == a.w_lrow + dw && d.w_Pb == a.w_Pb + dw && d.w_Zsi == a.w_Zsi + dw && d.w_Lxx == a.w_Lxx + dw
              && d.step.ux == a.step.ux + dw && d.step.pi == a.step.pi + dw && d.step.lam == a.step.lam + dw && d.step.t == a.step.t + dw
              && d.res.g == a.res.g + dw && d.res.b == a.res.b + dw && d.res.d == a.res.d + dw && d.res.m == a.res.m + dw && d.w_rmb == a.w_rmb + dw
              && d.itref.pi == a.itref.pi + dw && d.itref.lam == a.itref.lam + dw && d.itref.t == a.itref.t + dw;

@@ -341,11 +341,19 @@ int ocp_qp_cuipm_batch_solve(void *config_, int n, ocp_qp_in **qp_in, ocp_qp_out
     acados_tic(&timer);
     ensure_solver(mem, opts, qp_in[0], n);
     const cuipm_layout *l = cuipm_get_layout(mem->solver);
-    /* batch staging buffers: plain heap (the raw memory handed to the plugin is sized for one QP) */
-    double *qp = (double *) malloc(sizeof(double) * l->qp_stride * (size_t) n);
-    double *sol = (double *) calloc(l->sol_stride * (size_t) n, sizeof(double));
-    cuipm_info *infos = (cuipm_info *) malloc(sizeof(cuipm_info) * (size_t) n);
-    if (!qp || !sol || !infos) { printf("\nerror: ocp_qp_cuipm_batch_solve: out of memory\n"); exit(1); }
+    /* batch staging buffers: page-locked, owned by the memory object (the raw memory handed to the plugin is sized for one QP
+     * and pageable); grown when a larger batch arrives */
+    if (mem->b_cap < n)
+    {
+        cuipm_host_free(mem->b_qp); cuipm_host_free(mem->b_sol); cuipm_host_free(mem->b_info);
+        mem->b_qp = (double *) cuipm_host_alloc(sizeof(double) * l->qp_stride * (size_t) n);
+        mem->b_sol = (double *) cuipm_host_alloc(sizeof(double) * l->sol_stride * (size_t) n);
+        mem->b_info = (cuipm_info *) cuipm_host_alloc(sizeof(cuipm_info) * (size_t) n);
+        mem->b_cap = n;
+        if (!mem->b_qp || !mem->b_sol || !mem->b_info) { printf("\nerror: ocp_qp_cuipm_batch_solve: %s\n", cuipm_last_error()); exit(1); }
+    }
+    double *qp = mem->b_qp, *sol = mem->b_sol;
+    cuipm_info *infos = mem->b_info;
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < n; i++)
     {
@@ -371,7 +379,6 @@ int ocp_qp_cuipm_batch_solve(void *config_, int n, ocp_qp_in **qp_in, ocp_qp_out
         if (st != ACADOS_SUCCESS && worst == ACADOS_SUCCESS) worst = st;
     }
     mem->info = infos[n - 1]; mem->status = infos[n - 1].status; mem->iter = infos[n - 1].iter; mem->time_qp_solver_call = t_solve;
-    free(qp); free(sol); free(infos);
     return worst;
 }
 
@@ -382,6 +389,8 @@ void ocp_qp_cuipm_memory_reset(void *config_, void *qp_in_, void *qp_out_, void 
     if (mem->solver) cuipm_destroy(mem->solver);
     mem->solver = NULL;
     mem->max_batch = 0;
+    cuipm_host_free(mem->b_qp); cuipm_host_free(mem->b_sol); cuipm_host_free(mem->b_info);
+    mem->b_qp = mem->b_sol = NULL; mem->b_info = NULL; mem->b_cap = 0;
     mem->status = 0;
     mem->iter = 0;
 }
@@ -456,7 +465,12 @@ void ocp_qp_cuipm_terminate(void *config_, void *mem_, void *work_)
 {
     ocp_qp_cuipm_memory *mem = mem_;
     if (mem && mem->solver) cuipm_destroy(mem->solver);
-    if (mem) mem->solver = NULL;
+    if (mem)
+    {
+        mem->solver = NULL;
+        cuipm_host_free(mem->b_qp); cuipm_host_free(mem->b_sol); cuipm_host_free(mem->b_info);
+        mem->b_qp = mem->b_sol = NULL; mem->b_info = NULL; mem->b_cap = 0;
+    }
 }
 
 void ocp_qp_cuipm_config_initialize_default(void *config_)

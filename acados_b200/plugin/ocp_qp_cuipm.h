@@ -37,6 +37,11 @@ typedef struct ocp_qp_cuipm_memory_
     double *seed_rec, *sens_rec; /* staging records of eval_forw_sens / eval_adj_sens (solution layout) */
     double *stat;               /* (stat_max+1) x CUIPM_STAT_M table of the last solve (HPIPM's layout: row per iteration) */
     int stat_max_alloc;         /* stat_max the table was sized with at memory creation (the reference freezes ws->stat_max there too) */
+    /* batch entry: page-locked staging buffers owned by the memory object (cuipm_host_alloc), grown on demand, freed in
+     * terminate / memory_reset -- no allocation per call */
+    double *b_qp, *b_sol;
+    cuipm_info *b_info;
+    int b_cap;                  /* QPs the staging buffers hold */
     cuipm_info info;
     double time_qp_solver_call;
     int iter;

@@ -60,9 +60,15 @@ typedef struct { ocp_qp_xcond_solver_config *config; ocp_qp_xcond_solver_dims *d
 static chain make_chain(int use_cuipm, int N2)
 {
     chain c;
+#ifdef CUIPM_REGISTERED
+    /* a libacados built with ACADOS_WITH_CUIPM (integration/Makefile): the solver is selected by name, like any other */
+    c.config = ocp_qp_xcond_solver_config_create_from_name(use_cuipm ? "PARTIAL_CONDENSING_CUIPM" : "PARTIAL_CONDENSING_HPIPM");
+    if (!c.config || !c.config->qp_solver) { printf("create_from_name failed\n"); exit(2); }
+#else
     ocp_qp_solver_plan_t plan; plan.qp_solver = PARTIAL_CONDENSING_HPIPM;
     c.config = ocp_qp_xcond_solver_config_create(plan);
     if (use_cuipm) ocp_qp_cuipm_config_initialize_default(c.config->qp_solver);
+#endif
     c.dims = ocp_qp_xcond_solver_dims_create(c.config, NN);
     for (int k = 0; k <= NN; k++)
     {

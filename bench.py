@@ -138,6 +138,8 @@ def main():
     ap.add_argument("--warps", type=int, default=0, help="warps per QP (0 = solver default)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="QPs in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--fast", type=int, default=1, help="0: keep the throughput kernel off (generic one-warp-per-QP kernel only)")
+    ap.add_argument("--no-tight", action="store_true", help="skip the second parity pass (all tolerances 1e-12)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -192,6 +194,7 @@ def main():
     solver = CuipmSolver(b.shape, nb, device=local_rank)
     if args.warps:
         solver.set_tuning("warps", args.warps)
+    solver.set_tuning("fast", args.fast)
     stream = torch.cuda.ExternalStream(solver.lib.cuipm_stream(solver.handle), device=torch.device("cuda", local_rank))
 
     # pinned host buffers (the plugin's view) and device-resident copies (the kernel-only view)
@@ -230,7 +233,9 @@ def main():
     dev_ms = ev0.elapsed_time(ev1)
     # per-launch duration of the solve kernel (events recorded around each launch by the solver itself)
     solver.solve_device(nb, d_qp.data_ptr(), d_sol.data_ptr(), d_info.data_ptr(), opts, sync=True)
-    kernel_ms = solver.last_kernel_ms
+    solve_ms = solver.last_kernel_ms                 # all kernels of one solve (repack, throughput kernel, generic kernel over hand-backs)
+    kernel_ms = solver.last_main_kernel_ms           # the dominant kernel alone (CUDA events around its launch on the solver's stream)
+    handed_back = solver.last_handed_back
     info = np.frombuffer(d_info.cpu().numpy().tobytes(), dtype=INFO_DTYPE)
     iters_mean = float(info["iter"].mean())
 
@@ -241,6 +246,7 @@ def main():
     solver2 = CuipmSolver(b.shape, nb, device=local_rank)
     if args.warps:
         solver2.set_tuning("warps", args.warps)
+    solver2.set_tuning("fast", args.fast)
     h_sol2 = torch.zeros((nb, b.layout.sol_stride), dtype=torch.float64).pin_memory()
     h_info2 = torch.zeros(nb * INFO_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
     lanes = [(solver, h_sol, h_info), (solver2, h_sol2, h_info2)]
@@ -267,10 +273,10 @@ def main():
     assert np.array_equal(h_info.numpy(), h_info2.numpy()) or steps < 2, "the two lanes solved the same batch: results must agree"
     hinfo = np.frombuffer(h_info.numpy().tobytes(), dtype=INFO_DTYPE)
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s * 1e3, kernel_ms, solve_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, kernel_ms = (float(x) for x in t.cpu())
+    dev_ms, e2e_ms, kernel_ms, solve_ms = (float(x) for x in t.cpu())
     total_qps = nb * world * steps
     value = total_qps / (dev_ms * 1e-3)
     e2e_value = total_qps / (e2e_ms * 1e-3)
@@ -282,6 +288,12 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        fp64 = {}
+        try:
+            fp64 = json.load(open(os.path.join(ROOT, "profiles", "r02_fp64_peak.json")))
+        except Exception:
+            pass
+        fp64_peak = float(fp64.get("dfma_tflops", 33.9))
         ab = algorithmic_bytes_per_qp(b)
         achieved = ab["B_min"] * nb / (kernel_ms * 1e-3) / 1e9
         stream_gbs = ab["B_stream_iter"] * iters_mean * nb / (kernel_ms * 1e-3) / 1e9
@@ -293,12 +305,30 @@ def main():
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": traffic, "kernel": "cuipm_solve_kernel", "kernel_ms": kernel_ms,
+        ncu = {}
+        tp = os.path.join(ROOT, "profiles", "r02_ncu_headline.json")
+        if os.path.exists(tp):
+            try:
+                ncu = json.load(open(tp))
+            except Exception:
+                ncu = {}
+        if traffic is None:
+            traffic = ncu.get("dram_bytes_per_launch")
+        # the path is bounded by the FP64 pipe or by HBM; frac = the larger of the two fractions.  HBM term on
+        # ALGORITHMIC bytes (B_min: every record read once, the solution written once), FP64 term on algorithmic flops against
+        # the DFMA rate measured on this GPU type (scripts/ubench_fp64.cu -> profiles/r02_ubench_fp64.txt).
+        frac_hbm, frac_fp64 = achieved / hbm_peak, tflops / fp64_peak
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": max(frac_hbm, frac_fp64),
+                    "frac_hbm_algorithmic": frac_hbm, "frac_fp64_algorithmic": frac_fp64, "frac_is": "fp64" if frac_fp64 > frac_hbm else "hbm",
+                    "traffic": traffic, "kernel": "cuipm_fast_kernel" if args.fast and launches_per_step > 1 else "cuipm_solve_kernel",
+                    "kernel_ms": kernel_ms, "solve_ms_all_kernels": solve_ms,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
                     "algorithmic_bytes_per_qp": ab["B_min"], "mean_ipm_iterations": iters_mean,
                     "stream_model": {"bytes_per_qp": ab["B_stream_iter"] * iters_mean, "achieved_gbs": stream_gbs, "frac": stream_gbs / hbm_peak},
-                    "fp64": {"achieved_tflops": tflops, "nominal_peak_tflops": 40.0, "frac": tflops / 40.0}}
+                    "fp64": {"achieved_tflops": tflops, "peak_tflops": fp64_peak,
+                             "peak_source": "measured DFMA rate, profiles/r02_ubench_fp64.txt" if fp64 else "33.9 TFLOP/s (measured earlier on a B200 of this pool)",
+                             "frac": frac_fp64, "ncu_pipe_fp64_cycles_active_pct": ncu.get("sm__pipe_fp64_cycles_active_pct")},
+                    "ncu": ncu or None}
         cpu, parity = None, None
         if not args.no_cpu:
             try:
@@ -312,6 +342,28 @@ def main():
                           "iter_equal_frac": float((hinfo["iter"][:nsamp] == rinfo["iter"]).mean()),
                           "status_equal_frac": float((hinfo["status"][:nsamp] == rinfo["status"]).mean()),
                           "iter_mean_reference": float(rinfo["iter"].mean())}
+                parity["iter_hist_cuda"] = np.bincount(hinfo["iter"][:nsamp]).tolist()
+                parity["iter_hist_reference"] = np.bincount(rinfo["iter"]).tolist()
+                if not args.no_tight:
+                    # second pass with all tolerances 1e-12 on the same instances, for the 1e-10 comparison
+                    # (at the default tolerances both solvers stop ~1e-8 from the solution and round-off decides the last digits)
+                    from oracle import oracle_binding as ob
+                    from acados_b200.problems import Batch
+                    topts = default_opts(res_g_max=1e-12, res_b_max=1e-12, res_d_max=1e-12, res_m_max=1e-12)
+                    tsol, tinfo = solver.solve(b.qp[:nsamp], topts)
+                    sub = Batch(b.shape, b.layout, np.ascontiguousarray(b.qp[:nsamp]), b.name)
+                    if ob.have_ref():
+                        trsol, trinfo, _ = ob.ref_solve(sub, topts, nthreads=len(os.sched_getaffinity(0)))
+                    else:
+                        trsol, trinfo = ob.oracle_solve(sub, topts, nthreads=len(os.sched_getaffinity(0)))
+                    tdu = np.max(np.abs(b.layout.u_traj(tsol) - b.layout.u_traj(trsol)), axis=1)
+                    parity["tight_1e-12"] = {"instances": int(nsamp), "max_abs_du": float(tdu.max()), "frac_du_le_1e-10": float((tdu <= 1e-10).mean()),
+                                             "iter_equal_frac": float((tinfo["iter"] == trinfo["iter"]).mean()),
+                                             "iter_within_one_frac": float((np.abs(tinfo["iter"] - trinfo["iter"]) <= 1).mean()),
+                                             "status_hist_cuda": np.bincount(tinfo["status"], minlength=5).tolist(),
+                                             "status_hist_reference": np.bincount(trinfo["status"], minlength=5).tolist(),
+                                             "iter_hist_cuda": np.bincount(tinfo["iter"]).tolist(),
+                                             "iter_hist_reference": np.bincount(trinfo["iter"]).tolist()}
             except Exception as e:  # noqa: BLE001
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
@@ -326,7 +378,9 @@ def main():
                 "gpu_launches": steps * launches_per_step,
                 "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
                 "solver": {"status_hist": np.bincount(hinfo["status"], minlength=5).tolist(), "iter_mean": iters_mean,
-                           "iter_max": int(info["iter"].max()), "lq_count": int(info["lq_count"].sum())}}
+                           "iter_max": int(info["iter"].max()), "lq_count": int(info["lq_count"].sum()),
+                           "throughput_kernel": bool(args.fast and launches_per_step > 1), "launches_per_step": launches_per_step,
+                           "handed_back_to_generic_kernel": handed_back}}
         print(json.dumps(line))
     solver.close()
     solver2.close()

@@ -188,6 +188,12 @@ int cuipm_wait(cuipm_solver *s);
 int cuipm_solve_device(cuipm_solver *s, int nbatch, const double *d_qp, double *d_sol, cuipm_info *d_info,
                        double *d_stat, const cuipm_opts *opts, int sync);
 
+/* Page-locked host memory for the record buffers handed to cuipm_solve_host[_async]: with pageable memory the "asynchronous"
+ * copies are staged synchronously by the driver.  The acados plugin keeps its batch staging buffers here (no CUDA header
+ * in the plugin: it stays plain C).  cuipm_host_alloc returns NULL on failure. */
+void *cuipm_host_alloc(size_t bytes);
+void cuipm_host_free(void *p);
+
 /* Device memory owned by the solver, for callers that stage data themselves (bench, multi-GPU scatter). */
 double *cuipm_device_qp_buffer(cuipm_solver *s);       /* max_batch * qp_stride doubles  */
 double *cuipm_device_sol_buffer(cuipm_solver *s);      /* max_batch * sol_stride doubles */
@@ -244,12 +250,19 @@ int cuipm_get_ric(cuipm_solver *s, int iqp, const char *field, int stage, double
 
 /* number of kernels the last solve call launched (bench.py's gpu_launches claim) */
 int cuipm_last_launch_count(const cuipm_solver *s);
-/* device time in milliseconds of the main kernel of the last cuipm_solve_* call with sync (CUDA events) */
+/* device time in milliseconds of the last cuipm_solve_* call with sync, all its kernels (CUDA events on the solver's stream) */
 float cuipm_last_kernel_ms(const cuipm_solver *s);
-/* launch tuning without a reference counterpart: key "warps" = warps cooperating on one QP (1, 2 or 4; the default is
- * chosen from the stage dimensions); key "pipe" = chunks (1..8, default 8) the host entry splits a batch into so that
- * the copies of one chunk overlap the solve of the others.  Results do not depend on either beyond floating-point
- * summation order. */
+/* device time in milliseconds of the dominant kernel alone (the throughput kernel where the shape has one; CUDA events around
+ * that launch) of the last synchronous cuipm_solve_device call */
+float cuipm_last_main_kernel_ms(cuipm_solver *s);
+/* QPs of the last solve that the throughput kernel handed back to the generic kernel (cold paths: LQ refactorisation,
+ * iterative refinement, no active constraint); 0 where the generic kernel solved everything.  Synchronises. */
+int cuipm_last_handed_back(cuipm_solver *s);
+/* launch tuning without a reference counterpart: key "warps" = warps cooperating on one QP in the generic kernel (1, 2 or 4;
+ * the default is chosen from the stage dimensions); key "pipe" = chunks (1..8, default 8) the host entry splits a batch into
+ * so that the copies of one chunk overlap the solve of the others; key "fast" = 0 keeps eligible shapes off the throughput
+ * kernel (several QPs per warp, acados_b200/csrc/cuipm_fast.cu).  Results do not depend on any of them beyond
+ * floating-point summation order. */
 int cuipm_set_tuning(cuipm_solver *s, const char *key, int value);
 
 #ifdef __cplusplus

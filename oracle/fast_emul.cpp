@@ -17,6 +17,12 @@ static inline void fk_sync() { simt::sync(); }
 static inline double fk_shfl_xor(double v, int m) { return simt::shfl(v, simt::lane() ^ m); }
 static inline int fk_shfl_xor_i(int v, int m) { return simt::shfl_i(v, simt::lane() ^ m); }
 static inline bool fk_any(bool p) { return simt::ballot(p) != 0u; }
+static inline void fk_cp16(double *dst, const double *src)
+{
+    if (((size_t) dst & 15) || ((size_t) src & 15)) { std::fprintf(stderr, "fast_emul: misaligned 16-byte copy\n"); std::abort(); }
+    simt::cp_async(dst, src, 16);
+}
+static inline void fk_cp_wait() { simt::cp_wait(); }
 typedef simt::MBar fk_mbar_t;
 static inline void fk_mbar_init(fk_mbar_t *b, int count) { simt::mbar_init(b, count); }
 static inline void fk_bulk(double *dst, const double *src, unsigned bytes, fk_mbar_t *b) { simt::bulk_copy(b, dst, src, (int) bytes); }

@@ -18,7 +18,7 @@
  * golden fixtures in tests/golden/.
  *
  * Not restated (the product rejects these option values as well): abs_form=1, split_step=1,
- * var_init_scheme=0, non-zero m (acados "tau_min" relaxation).  info.lq_count counts the LQ refactorisations
+ * var_init_scheme=0.  info.lq_count counts the LQ refactorisations
  * (OCP_QP_FACT_LQ_SOLVE_KKT_STEP) of a solve; the Hessian factor the reference caches per solve (use_hess_fact) is
  * recomputed at each of them.
  */
@@ -112,6 +112,7 @@ typedef struct
     double *lq;                   /* nvmax x (2 nvmax + ngmax + nxmax) scratch of the LQ refactorisation */
     double *tmp0, *tmp1, *tmp2, *tmp3, *tmpx, *tmpl; /* nb+ng / nx scratch */
     int mask_constr;
+    double m_relax;     /* entries of qp->m (all equal) */
     double nc_mask_inv;
     char *arena;
 } work;
@@ -355,7 +356,7 @@ static void res_body(work *w, int lin, const vset *p, const rset *rhs, const vse
             double tmu = 0.0;
             for (int i = 0; i < nc; i++)
             {
-                rm[i] = LMASK(i) * t[i];       /* m == 0 */
+                rm[i] = LMASK(i) * t[i] - w->m_relax;       /* qp->m = m_relax everywhere (ocp_qp_hpipm.c:338-342, x_ocp_qp_res.c:513-514) */
                 if (w->mask_constr) rm[i] *= mask[i];
                 tmu += fabs(rm[i]);
             }
@@ -1098,6 +1099,7 @@ static int itref_ok(const double nrm[4], const double resmax[4], const cuipm_opt
 
 static void solve_one(work *w, const cuipm_opts *o, cuipm_info *info, double *stat)
 {
+    w->m_relax = o->m_relax;
     int N = w->N;
     const int SM = CUIPM_STAT_M;
     double res_max[4] = {0, 0, 0, 0}, mu = 0, obj = 0, gap = 0;

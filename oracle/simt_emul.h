@@ -111,6 +111,8 @@ inline unsigned ballot(bool p)
 inline void cp_async(void *dst, const void *src, int bytes)
 {
     Warp *w = cur_warp();
+    static const bool eager = std::getenv("SIMT_EMUL_EAGER") != nullptr;       // see bulk_copy
+    if (eager) { std::memcpy(dst, src, (size_t) bytes); return; }
     w->pend[w->cur].push_back({dst, src, bytes});
 }
 inline void cp_wait()

@@ -62,6 +62,30 @@ if __name__ == "__main__":
         s.solve_device(nb, d_qp.data_ptr(), d_sol.data_ptr(), d_info.data_ptr(), o, sync=True)
         print("kernel ms", s.last_kernel_ms)
         s.close()
+    if what == "prof":
+        # cycles per sweep (library built with CUIPM_DEFS=-DFK_PROFILE): python scripts/dev_fast.py prof <config> <batch>
+        import ctypes as C
+        cfg, nb = sys.argv[2], int(sys.argv[3])
+        b = problems.chain_mass(nb, N=40, seed=1234) if cfg == "c2" else problems.named_config(cfg, nb)
+        o = default_opts()
+        s = CuipmSolver(b.shape, nb)
+        d_qp = torch.from_numpy(b.qp).cuda()
+        d_sol = torch.zeros((nb, b.layout.sol_stride), dtype=torch.float64, device="cuda")
+        d_info = torch.zeros(nb * INFO_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+        s.solve_device(nb, d_qp.data_ptr(), d_sol.data_ptr(), d_info.data_ptr(), o, sync=True)
+        out = (C.c_ulonglong * 32)()
+        s.lib.cuipm_fast_prof_read(out, 1)
+        s.solve_device(nb, d_qp.data_ptr(), d_sol.data_ptr(), d_info.data_ptr(), o, sync=True)
+        s.lib.cuipm_fast_prof_read(out, 1)
+        v = [float(x) for x in out]
+        names = ["res", "fact", "fwd", "solve", "mu_aff", "wait_vec", "wait_mat", "total", "warps"]
+        print(f"kernel {s.last_main_kernel_ms:.2f} ms; cycles per warp: total {v[7]/v[8]:.3g}")
+        for i in range(7):
+            print(f"  {names[i]:9s} {100*v[i]/v[7]:6.2f} % of the warp time")
+        for i, nm in ((10, "fact: prologue + waits"), (11, "fact: gradient (alb, Pb)"), (12, "fact: TRMM"), (13, "fact: SYRK + update + H"), (14, "fact: panels"), (16, "fwd: issue + waits"), (17, "fwd: u"), (18, "fwd: H v"),
+                      (19, "fwd: x+"), (20, "fwd: constraint step"), (21, "fwd: pi"), (22, "fwd: residual rows")):
+            print(f"  {nm:26s} {100*v[i]/v[7]:6.2f} %")
+        s.close()
     if what == "time3":
         timing(problems.chain_mass(4096, N=40, seed=1234), "c2")
         timing(problems.named_config("c3", 16384), "c3")
