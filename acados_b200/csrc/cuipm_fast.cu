@@ -184,7 +184,7 @@ template <int NX, int NU, int G, int MINB>
 cudaError_t launch_one(const FastArgs &F, cudaStream_t stream)
 {
     using K = fastk::Ker<NX, NU, G>;
-    const size_t smem = sizeof(double) * ((size_t) F.gstride * K::QPW + (size_t) F.nmaps * F.nbe);
+    const size_t smem = sizeof(double) * ((size_t) F.gstride * K::QPW + 2 * (size_t) F.nmaps * F.nbe);
     if (((size_t) F.qpk | (size_t) F.sol | (size_t) F.work) & 15) return cudaErrorMisalignedAddress;      // bulk copies need 16-byte aligned records
     cudaError_t err = cudaFuncSetAttribute(cuipm_fast_kernel<NX, NU, G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (err != cudaSuccess) return err;
@@ -235,11 +235,11 @@ static int dev_g() { const char *e = getenv("CUIPM_FAST_G"); return e ? atoi(e) 
 bool fast_available(int nx, int nu, FastArgs &F, int *qp_per_warp)
 {
 #define X(NX_, NU_, G_, MB_) \
-    if (nx == NX_ && nu == NU_ && dev_g() == G_) { sizes<NX_, NU_, G_>(F, qp_per_warp); return sizeof(double) * ((size_t) F.gstride * (32 / G_) + (size_t) F.nmaps * F.nbe) <= 226 * 1024; }
+    if (nx == NX_ && nu == NU_ && dev_g() == G_) { sizes<NX_, NU_, G_>(F, qp_per_warp); return sizeof(double) * ((size_t) F.gstride * (32 / G_) + 2 * (size_t) F.nmaps * F.nbe) <= 226 * 1024; }
     CUIPM_FAST_DEV_INSTANCES(X)
 #undef X
 #define X(NX_, NU_, G_, MB_) \
-    if (nx == NX_ && nu == NU_) { sizes<NX_, NU_, G_>(F, qp_per_warp); return sizeof(double) * ((size_t) F.gstride * (32 / G_) + (size_t) F.nmaps * F.nbe) <= 226 * 1024; }
+    if (nx == NX_ && nu == NU_) { sizes<NX_, NU_, G_>(F, qp_per_warp); return sizeof(double) * ((size_t) F.gstride * (32 / G_) + 2 * (size_t) F.nmaps * F.nbe) <= 226 * 1024; }
     CUIPM_FAST_INSTANCES(X)
 #undef X
     return false;

@@ -37,6 +37,11 @@
 #define FK_PROF_ADD2(slot) do {} while (0)
 #endif
 
+// the constraints i softened by slack jj, in increasing order (inv: inverse of idxs_rev, see Ker::Ker)
+#define FK_FOR_SLACK(i, jj) \
+    for (int i_ = inv[jj], i = i_ >= 0 ? i_ : 0, e_ = i_ >= 0 ? i_ + 1 : (i_ == -2 ? nb : 0); i < e_; i++) \
+        if (i_ >= 0 || rev[i] == (jj))
+
 namespace cuipm {
 namespace fastk {
 
@@ -74,7 +79,7 @@ struct Ker
 
     const FastArgs &A;
     double *smem0;             // shared memory of the groups of the warp (after the index maps)
-    const int *IDX;            // index maps (idxb, idxs_rev), shared by the groups: entry e at IDX + 2*e*nbe (FastArgs::nmaps entries)
+    const int *IDX;            // index maps (idxb, idxs_rev), shared by the groups: entry e = (idxb | idxs_rev | its inverse) at IDX + 4*e*nbe (FastArgs::nmaps entries)
     fk_mbar_t *bars;           // [0]: vector images, [1]: matrices, [2..5]: ring of the mu_aff reduction
     int li, gq, q0;            // lane within the group, group within the warp, first QP of the warp
     double *MA, *ML, *LU, *DD, *V;
@@ -104,10 +109,25 @@ struct Ker
             const int k = a.nmaps == 3 ? (e == 0 ? 0 : (e == 1 ? 1 : a.N)) : e;
             const StageDesc &sdk_ = k == 0 ? a.s0 : (k == a.N ? a.sN : a.s1);
             const int off = sdk_.idx_off + ((k >= 1 && k < a.N) ? (k - 1) * a.is : 0);
-            for (int i = lane; i < 2 * sdk_.nb; i += 32) idx[2 * e * a.nbe + i] = a.ipool[off + i];
+            for (int i = lane; i < 2 * sdk_.nb; i += 32) idx[4 * e * a.nbe + i] = a.ipool[off + i];
+        }
+        fk_sync();
+        // inverse of idxs_rev: the constraint softened by slack j (-1: none, -2: several -- the loops then scan idxs_rev)
+        for (int e = 0; e < a.nmaps; e++)
+        {
+            const int k = a.nmaps == 3 ? (e == 0 ? 0 : (e == 1 ? 1 : a.N)) : e;
+            const StageDesc &sdk_ = k == 0 ? a.s0 : (k == a.N ? a.sN : a.s1);
+            const int *rev_ = idx + 4 * e * a.nbe + sdk_.nb;
+            for (int j = lane; j < sdk_.ns; j += 32)
+            {
+                int f = -1;
+                for (int i = 0; i < sdk_.nb; i++)
+                    if (rev_[i] == j) f = f == -1 ? i : -2;
+                idx[4 * e * a.nbe + 2 * sdk_.nb + j] = f;
+            }
         }
         IDX = idx;
-        smem += a.nmaps * a.nbe;
+        smem += 2 * a.nmaps * a.nbe;
         smem0 = smem;
         bars = b;
         double *S = smem + (size_t) gq * a.gstride;
@@ -362,7 +382,7 @@ struct Ker
         const StageDesc &sd = sdk<KIND>();
         const View v = view<KIND>(k);
         const int nb = sd.nb, ns = sd.ns, nc = sd.nc;
-        const int *idxb = IDX + 2 * (A.nmaps == 3 ? KIND : k) * A.nbe, *rev = idxb + nb;
+        const int *idxb = IDX + 4 * (A.nmaps == 3 ? KIND : k) * A.nbe, *rev = idxb + nb, *inv = rev + nb;
         const int nu1 = (nx1 > 0 && k + 1 < A.N) ? NU : 0, n1e = (nx1 + nu1 + 1) & ~1;
         // images
         const int solN = (int) (sd.sol.t - sd.sol.ux) + evn(nc), stpN = (int) (sd.step.t - sd.step.ux) + evn(nc);
@@ -508,8 +528,7 @@ struct Ker
                 R.a_gap += r * sj;
                 r -= lam[2 * nb + j];
                 const int jj = j < ns ? j : j - ns, offl = j < ns ? 0 : nb;
-                for (int i = 0; i < nb; i++)
-                    if (rev[i] == jj) r -= lam[offl + i];
+                FK_FOR_SLACK(i, jj) r -= lam[offl + i];
                 g_[n + j] = r;
             }
         }
@@ -588,7 +607,7 @@ struct Ker
     // slack elimination (x_ocp_qp_kkt.c:220-335, 431-520): tmp0/tmp1 = effective Gamma / gamma of the
     // softened constraints; ds = slack part of the step rhs; Zi = inverse of the slack Hessian.
     // ---------------------------------------------------------------------------------------------
-    FK_DEV void cond_slacks(int nb, int ns, const int *rev, const double *Z, int fact, const double *Gam, const double *gam,
+    FK_DEV void cond_slacks(int nb, int ns, const int *rev, const int *inv, const double *Z, int fact, const double *Gam, const double *gam,
                             const double *rgs, double *Zi, double *ds, double *tmp0, double *tmp1) const
     {
         for (int j = li; j < 2 * ns; j += G)
@@ -596,12 +615,11 @@ struct Ker
             const int jj = j < ns ? j : j - ns, offc = j < ns ? 0 : nb;
             double zi = 0.0, d = rgs[j] + gam[2 * nb + j];
             if (fact) zi = Z[j] + A.o.reg_prim + Gam[2 * nb + j];
-            for (int i = 0; i < nb; i++)
-                if (rev[i] == jj)
-                {
-                    if (fact) zi += Gam[offc + i];
-                    d += gam[offc + i];
-                }
+            FK_FOR_SLACK(i, jj)
+            {
+                if (fact) zi += Gam[offc + i];
+                d += gam[offc + i];
+            }
             if (fact) Zi[j] = 1.0 / zi;
             ds[j] = d;
         }
@@ -774,7 +792,7 @@ struct Ker
         const StageDesc &sd = sdk<KIND>();
         const View v = view<KIND>(k);
         const int nb = sd.nb, ns = sd.ns, nc = sd.nc;
-        const int *idxb = IDX + 2 * (A.nmaps == 3 ? KIND : k) * A.nbe, *rev = idxb + nb;
+        const int *idxb = IDX + 4 * (A.nmaps == 3 ? KIND : k) * A.nbe, *rev = idxb + nb, *inv = rev + nb;
         const int nu1 = (nx1 > 0 && k + 1 < A.N) ? NU : 0;
         double *RES = V, *LT = RES + (A.nve + NXe + 2 * A.nce), *ZQ = LT + 2 * A.nce, *Gam = ZQ + A.ns2e, *gam = Gam + A.nce;
         double *tmp0 = gam + A.nce, *tmp1 = tmp0 + A.nbe, *Zi = tmp1 + A.nbe, *ds = Zi + A.ns2e, *ddx = ds + A.ns2e;
@@ -812,7 +830,7 @@ struct Ker
         fk_sync();
         if (ns > 0)
         {
-            cond_slacks(nb, ns, rev, ZQ, 1, Gam, gam, rowv + n, Zi, ds, tmp0, tmp1);
+            cond_slacks(nb, ns, rev, inv, ZQ, 1, Gam, gam, rowv + n, Zi, ds, tmp0, tmp1);
             fk_sync();
             for (int j = li; j < 2 * ns; j += G)
             {
@@ -1060,7 +1078,7 @@ struct Ker
         const StageDesc &sd = sdk<KIND>();
         const View v = view<KIND>(k);
         const int nb = sd.nb, ns = sd.ns, nc = sd.nc;
-        const int *idxb = IDX + 2 * (A.nmaps == 3 ? KIND : k) * A.nbe, *rev = idxb + nb;
+        const int *idxb = IDX + 4 * (A.nmaps == 3 ? KIND : k) * A.nbe, *rev = idxb + nb, *inv = rev + nb;
         const int resN = (int) (sd.res.m - sd.res.g) + evn(nc), ltN = (int) (sd.sol.t - sd.sol.lam) + evn(nc);
         const int fvN = (int) (sd.w_Zsi - sd.w_Linv) + evn(2 * ns), stN = (int) (sd.step.t - sd.step.lam) + evn(nc);
         const int qmN = (int) (sd.q_Z - sd.q_dmask) + evn(2 * ns);
@@ -1102,7 +1120,7 @@ struct Ker
         fk_sync();
         if (ns > 0)
         {
-            cond_slacks(nb, ns, rev, qZ, 0, Gam, gam, vv + n, const_cast<double *>(Zi), ds, tmp0, tmp1);
+            cond_slacks(nb, ns, rev, inv, qZ, 0, Gam, gam, vv + n, const_cast<double *>(Zi), ds, tmp0, tmp1);
             fk_sync();
             double *o_ = v.w + sd.step.ux + n;
             for (int j = li; j < 2 * ns; j += G)
@@ -1204,7 +1222,7 @@ struct Ker
         const StageDesc &sd = sdk<KIND>();
         const View v = view<KIND>(k);
         const int nb = sd.nb, ns = sd.ns, nc = sd.nc;
-        const int *idxb = IDX + 2 * (A.nmaps == 3 ? KIND : k) * A.nbe, *rev = idxb + nb;
+        const int *idxb = IDX + 4 * (A.nmaps == 3 ? KIND : k) * A.nbe, *rev = idxb + nb, *inv = rev + nb;
         const int nu1 = (nx1 > 0 && k + 1 < A.N) ? NU : 0, n1 = nx1 + nu1, n1e = (n1 + 1) & ~1;
         const int resN = (int) (sd.res.m - sd.res.g) + evn(nc), ltN = (int) (sd.sol.t - sd.sol.lam) + evn(nc);
         const int fvN = (int) (sd.w_Zsi - sd.w_Linv) + evn(2 * ns), qmN = (int) (sd.q_Z - sd.q_dmask) + evn(2 * ns);
@@ -1339,8 +1357,7 @@ struct Ker
                 {
                     const int jj = j < ns ? j : j - ns, offc = j < ns ? 0 : nb;
                     double d = dsv[j];
-                    for (int i = 0; i < nb; i++)
-                        if (rev[i] == jj)
+                    FK_FOR_SLACK(i, jj)
                         {
                             const double l = lam[offc + i], tt = ts[offc + i];
                             const double Gm = A.o.t_lam_min == 1 ? (tt < A.o.t_min ? t_min_inv : tis[offc + i]) * (l < A.o.lam_min ? A.o.lam_min : l) : tis[offc + i] * l;
@@ -1454,8 +1471,7 @@ struct Ker
                 {
                     double r = qZ[j] * dsv[j] + zv[j] - dlm[2 * nb + j];
                     const int jj = j < ns ? j : j - ns, offl = j < ns ? 0 : nb;
-                    for (int i = 0; i < nb; i++)
-                        if (rev[i] == jj) r -= dlm[offl + i];
+                    FK_FOR_SLACK(i, jj) r -= dlm[offl + i];
                     g_[n + j] = r;
                 }
             }
@@ -1504,53 +1520,53 @@ struct Ker
     }
 
     // COMPUTE_MU_AFF_QP (x_core_qp_ipm_aux.c:636-668): a streaming reduction over (lam, t) of the solution record and
-    // (dlam, dt) of the step, four stages in flight (one transaction barrier per slot of the ring)
+    // (dlam, dt) of the step.  Nothing here depends on anything but the loads, so the sweep is limited by how many of them are in
+    // flight: the interior stages (same layout, record strides ss / ws) are taken two at a time, up to four constraints per lane
+    // each, all 32 loads of a lane issued before the first use; stages 0 and N, and shapes with more than 4 G constraints per
+    // stage, take the plain loop.
     FK_DEV double mu_aff_pass(double alpha)
     {
-        constexpr int D = 4;
-        const int N = A.N, slot_sz = 4 * A.nce;
+        const int N = A.N;
         double acc = 0.0;
-        auto issue = [&](int k, int slot) {
-            const StageDesc &s = sdr(k);
-            const unsigned kk = (k >= 1 && k < N) ? (unsigned) (k - 1) : 0u;
-            const int ltN = (int) (s.sol.t - s.sol.lam) + evn(s.nc), stN = (int) (s.step.t - s.step.lam) + evn(s.nc);
-            if (fk_lane() == 0)
-            {
-                const double *s1 = rbase[1] + ((size_t) kk * A.ss + s.sol.lam), *s2 = rbase[2] + ((size_t) kk * A.ws + s.step.lam);
-                double *dst = smem0 + voff(V) + slot * slot_sz;
-                for (int g = 0; g < QPW; g++)
-                {
-                    fk_bulk(dst, s1, (unsigned) ltN * 8u, bars + 2 + slot);
-                    fk_bulk(dst + 2 * A.nce, s2, (unsigned) stN * 8u, bars + 2 + slot);
-                    dst += A.gstride;
-                    if (g + 1 < nvalid) { s1 += rstep[1]; s2 += rstep[2]; }
-                }
-                fk_mbar_arrive_tx(bars + 2 + slot, (unsigned) (QPW * (ltN + stN)) * 8u);
-            }
-        };
-#ifndef FK_MU_RING        // the ring of bulk copies below was measured neutral on the headline shape, slower on small stages
-        for (int k = 0; k <= A.N; k++)
-        {
+        auto plain = [&](int k) {
             const StageDesc &s = sdr(k);
             const View v = viewr(k);
             const double *l = v.s + s.sol.lam, *t = v.s + s.sol.t, *dl = v.w + s.step.lam, *dt = v.w + s.step.t;
             for (int i = li; i < s.nc; i += G) acc += fabs((l[i] + alpha * dl[i]) * (t[i] + alpha * dt[i]));
-        }
-        return gsum(acc) * nc_mask_inv;
-#endif
-        stage_begin();
-        for (int d = 0; d < D && d <= N; d++) issue(d, d);
-        for (int k = 0; k <= N; k++)
+        };
+        plain(0);
+        const int nc1 = A.s1.nc, ni = N - 1;       // interior stages 1 .. N-1
+        if (ni > 0 && nc1 <= 4 * G)
         {
-            const int slot = k % D;
-            fk_mbar_wait(bars + 2 + slot, (phm >> slot) & 1u);
-            phm ^= 1u << slot;
-            const StageDesc &s = sdr(k);
-            const double *l = V + slot * slot_sz, *t = l + (s.sol.t - s.sol.lam), *dl = l + 2 * A.nce, *dt = dl + (s.step.t - s.step.lam);
-            for (int i = li; i < s.nc; i += G) acc += fabs((l[i] + alpha * dl[i]) * (t[i] + alpha * dt[i]));
-            fk_sync();
-            if (k + D <= N) issue(k + D, slot);
+            const double *l0 = sol + A.s1.sol.lam, *t0 = sol + A.s1.sol.t, *d0 = wk + A.s1.step.lam, *e0 = wk + A.s1.step.t;
+            int io[4];
+            bool iv[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { iv[j] = li + G * j < nc1; io[j] = iv[j] ? li + G * j : 0; }
+            for (int kk = 0; kk < ni; kk += 2)
+            {
+                double L[2][4], T[2][4], DL[2][4], DT[2][4];
+#pragma unroll
+                for (int u = 0; u < 2; u++)
+                {
+                    const unsigned k2 = (unsigned) (kk + u < ni ? kk + u : kk);
+                    const double *l = l0 + k2 * A.ss, *t = t0 + k2 * A.ss, *dl = d0 + k2 * A.ws, *dt = e0 + k2 * A.ws;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { L[u][j] = l[io[j]]; T[u][j] = t[io[j]]; DL[u][j] = dl[io[j]]; DT[u][j] = dt[io[j]]; }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                    {
+                        const double p = fabs((L[u][j] + alpha * DL[u][j]) * (T[u][j] + alpha * DT[u][j]));
+                        if (iv[j] && kk + u < ni) acc += p;
+                    }
+            }
         }
+        else
+            for (int k = 1; k < N; k++) plain(k);
+        if (N > 0) plain(N);
         return gsum(acc) * nc_mask_inv;
     }
 
@@ -1590,7 +1606,7 @@ struct Ker
             const StageDesc &s = sdr(k);
             const View v = viewr(k);
             const int n = s.n, nb = s.nb, ns = s.ns, nc = s.nc;
-            const int *idxb = IDX + 2 * (A.nmaps == 3 ? (k == 0 ? 0 : (k == A.N ? 2 : 1)) : k) * A.nbe, *rev = idxb + nb;
+            const int *idxb = IDX + 4 * (A.nmaps == 3 ? (k == 0 ? 0 : (k == A.N ? 2 : 1)) : k) * A.nbe, *rev = idxb + nb;
             const double *d = v.q + s.q_d;
             double *gux = v.s + s.sol.ux, *gpi = v.s + s.sol.pi, *gl = v.s + s.sol.lam, *gt = v.s + s.sol.t;
             for (int i = li; i < s.nx1; i += G) st(gpi + i, 0.0);

@@ -17,13 +17,29 @@ def shard_range(nbatch: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def scatter_records(records, root: int = 0):
+def _comm_device(device=None):
+    """Device the collectives run on: the caller's choice, else the current CUDA device under nccl (which moves CUDA
+    tensors only) and the CPU under gloo."""
+    import torch
+    import torch.distributed as dist
+    if device is not None:
+        return torch.device(device)
+    if dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def scatter_records(records, root: int = 0, device=None):
     """Root holds (nbatch, stride) records; every rank receives its shard_range slice.  Works on CPU tensors with
-    gloo and CUDA tensors with nccl (send/recv based, sizes known from nbatch)."""
+    gloo and CUDA tensors with nccl (send/recv based, sizes known from nbatch).  ``device``: where the shards live
+    (default: the current CUDA device under nccl, the CPU under gloo); the root's records must be there already."""
     import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
-    meta = torch.zeros(2, dtype=torch.int64, device=records.device if records is not None else "cpu")
+    dev = _comm_device(device)
+    if rank == root and records.device != dev:
+        raise ValueError(f"scatter_records: the root's records are on {records.device}, the collectives run on {dev}")
+    meta = torch.zeros(2, dtype=torch.int64, device=dev)
     if rank == root:
         meta[0], meta[1] = records.shape[0], records.shape[1]
     dist.broadcast(meta, root)
@@ -40,7 +56,7 @@ def scatter_records(records, root: int = 0):
         for q in reqs:
             q.wait()
         return mine
-    mine = torch.empty((hi - lo, stride), dtype=torch.float64, device=meta.device)
+    mine = torch.empty((hi - lo, stride), dtype=torch.float64, device=dev)
     dist.recv(mine, root)
     return mine
 

@@ -65,43 +65,57 @@ def flops_per_qp(b, iters: float) -> float:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every 10 ms by a thread (the timed region of
+    the default run lasts a fraction of a second, shorter than the start-up of an nvidia-smi process); the same fields as the
+    nvidia-smi line of the profiling recipe (clocks.sm, clocks.max.sm, clocks_event_reasons.*)."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index: int):
-        self.lines, self.proc, self.index = [], None, index
+        self.index, self.samples, self.thread, self.stop_flag, self.h, self.err = index, [], None, False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = index
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                phys = int(vis.split(",")[index])
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.smmax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.err = f"NVML unavailable: {e}"
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((mhz, rs))
+            except Exception as e:  # noqa: BLE001
+                self.err = str(e)
+                break
+            time.sleep(0.01)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        if self.h is None:
+            return
+        self.samples, self.stop_flag = [], False
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smmax, reasons = [], None, set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); smmax = float(f[2])
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smmax, "reasons": sorted(reasons), "samples": len(sm)}
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "NVML unavailable"], "samples": 0}
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        sm = [m for m, _ in self.samples]
+        reasons = sorted({name for _, r in self.samples for name, bit in self.REASONS if r & bit})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.smmax, "reasons": reasons, "samples": len(sm),
+                "source": "NVML, 10 ms period, timed region only"}
 
 
 def cpu_reference(batch_obj, opts, nqp: int, threads: int = 0):
@@ -139,6 +153,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="QPs in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--fast", type=int, default=1, help="0: keep the throughput kernel off (generic one-warp-per-QP kernel only)")
+    ap.add_argument("--no-scatter", action="store_true", help="N > 1: skip the scatter / solve / gather leg over NCCL")
+    ap.add_argument("--no-plugin", action="store_true", help="skip the end-to-end leg through the plugin's batched entry")
     ap.add_argument("--no-tight", action="store_true", help="skip the second parity pass (all tolerances 1e-12)")
     args = ap.parse_args()
 
@@ -273,6 +289,66 @@ def main():
     assert np.array_equal(h_info.numpy(), h_info2.numpy()) or steps < 2, "the two lanes solved the same batch: results must agree"
     hinfo = np.frombuffer(h_info.numpy().tobytes(), dtype=INFO_DTYPE)
 
+    # ---- end to end through the PLUGIN: n panel-major ocp_qp_in objects (the reference's structs, built once, untimed) handed to
+    # ocp_qp_cuipm_batch_solve of the patched libacados (integration/): per call, inside the timed region, the structs are
+    # unpacked into page-locked records by the host threads, copied to the device, solved, copied back and packed into
+    # ocp_qp_out objects -- the call a user of PARTIAL_CONDENSING_CUIPM makes.  Single process, N=1 only.
+    plugin = None
+    if world == 1 and not args.no_plugin:
+        try:
+            from integration import plugin_bench as pb
+            if pb.available():
+                pbatch = pb.PluginBatch(b, opts)
+                pst, psec = pbatch.run(2 + steps)
+                psol, pit, pstat = pbatch.solutions()
+                pbatch.close()
+                psec = psec[2:]
+                plugin = {"value": nb / float(psec.mean()), "unit": UNIT, "ms_per_call": 1e3 * float(psec.mean()), "calls": int(steps),
+                          "entry": "ocp_qp_cuipm_batch_solve(config, n, ocp_qp_in**, ocp_qp_out**, opts, mem, status) -- acados_b200/plugin/ocp_qp_cuipm.c",
+                          "worst_acados_status": int(pst), "host_threads": len(os.sched_getaffinity(0)),
+                          "max_abs_dsol_vs_record_path": float(np.max(np.abs(psol - h_sol.numpy()))),
+                          "iter_equal_record_path": bool(np.array_equal(pit, hinfo["iter"]))}
+            else:
+                plugin = {"value": None, "unavailable": "integration/_build/libplugin_bench.so not built (needs the reference sources at build time)"}
+        except Exception as e:  # noqa: BLE001
+            plugin = {"value": None, "unavailable": str(e)}
+
+    # ---- N > 1: the north_star's data path -- rank 0 holds the records of the WHOLE batch on its device, scatters the shards over
+    # NCCL (NVLink), every rank solves its shard, the solutions are gathered on rank 0.  Scatter, solve and gather are all inside
+    # the timed region (CUDA events on the current stream, which the NCCL operations are ordered with; max over ranks).
+    sg = None
+    if world > 1 and not args.no_scatter:
+        from acados_b200.sharding import gather_records, scatter_records
+        full = d_qp.repeat(world, 1) if rank == 0 else None          # world x batch records on rank 0 (copies of its own batch)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        seg = np.zeros((0, 3))
+        for it in range(1 + min(steps, 3)):
+            barrier()
+            evs[0].record()
+            mine = scatter_records(full)
+            evs[1].record()
+            torch.cuda.current_stream().synchronize()
+            solver.solve_device(nb, mine.data_ptr(), d_sol.data_ptr(), d_info.data_ptr(), opts, sync=True)
+            evs[2].record()
+            allsol = gather_records(d_sol, nb * world)
+            evs[3].record()
+            torch.cuda.synchronize()
+            if it > 0:     # first pass: NCCL channel set-up
+                seg = np.vstack([seg, [evs[0].elapsed_time(evs[1]), evs[1].elapsed_time(evs[2]), evs[2].elapsed_time(evs[3])]])
+            del mine
+        tt = torch.tensor(seg.mean(0), dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sc_ms, so_ms, ga_ms = (float(x) for x in tt.cpu())
+        if rank == 0:
+            sent = int(b.qp.nbytes) * (world - 1)
+            recvd = int(d_sol.numel() * 8) * (world - 1)
+            same = bool(torch.equal(allsol[:nb], allsol[nb:2 * nb]))       # every rank solved a copy of rank 0's batch
+            sg = {"value": nb * world / ((sc_ms + so_ms + ga_ms) * 1e-3), "unit": UNIT, "scatter_ms": sc_ms, "solve_ms": so_ms, "gather_ms": ga_ms,
+                  "bytes_scattered": sent, "bytes_gathered": recvd, "scatter_gbs_out_of_rank0": sent / (sc_ms * 1e-3) / 1e9,
+                  "gather_gbs_into_rank0": recvd / (ga_ms * 1e-3) / 1e9, "backend": "nccl send/recv (acados_b200/sharding.py)",
+                  "shards_identical_across_ranks": same}
+        del full
+
     t = torch.tensor([dev_ms, e2e_s * 1e3, kernel_ms, solve_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -375,6 +451,7 @@ def main():
                         "overlap the solve of step i, and the two batches in flight fill the partial last wave of a single "
                         "4096-QP launch (1.73 waves of 2368 resident QPs), which is why this can exceed the single-lane "
                         "device-resident value"},
+                "e2e_plugin": plugin, "scatter_gather": sg,
                 "gpu_launches": steps * launches_per_step,
                 "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
                 "solver": {"status_hist": np.bincount(hinfo["status"], minlength=5).tolist(), "iter_mean": iters_mean,

@@ -67,7 +67,7 @@ int run(cuipm::FastArgs F, int order)
     int gs = K::MATS + F.vsize;
     while (gs % 16 != 8) gs++;
     F.gstride = gs;
-    std::vector<double> smem((size_t) gs * K::QPW + (size_t) F.nmaps * F.nbe + 64);
+    std::vector<double> smem((size_t) gs * K::QPW + 2 * (size_t) F.nmaps * F.nbe + 64);
     // 16-byte aligned base
     double *base = smem.data();
     while ((size_t) base & 15) base++;
