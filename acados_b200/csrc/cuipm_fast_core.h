@@ -39,8 +39,36 @@
 
 // the constraints i softened by slack jj, in increasing order (inv: inverse of idxs_rev, see Ker::Ker)
 #define FK_FOR_SLACK(i, jj) \
-    for (int i_ = inv[jj], i = i_ >= 0 ? i_ : 0, e_ = i_ >= 0 ? i_ + 1 : (i_ == -2 ? nb : 0); i < e_; i++) \
+    _Pragma("unroll 1") for (int i_ = inv[jj], i = i_ >= 0 ? i_ : 0, e_ = i_ >= 0 ? i_ + 1 : (i_ == -2 ? nb : 0); i < e_; i++) \
         if (i_ >= 0 || rev[i] == (jj))
+
+// The short loops of a lane over its elements of a vector (run-time trip counts of 1..4) are kept as loops: the compiler's
+// unroll-by-four with a remainder chain executes more instructions than the loop it replaces at these trip counts, and
+// multiplies the instruction footprint of the sweeps (measured on the headline shape: 76.5k -> 88.4k QP/s, SASS 574 -> 337 KB).
+#define FK_PRAGMA_(x) _Pragma(#x)
+#define FK_PRAGMA(x) FK_PRAGMA_(x)
+#ifndef FK_VLOOP_N
+#define FK_VLOOP_N 1
+#endif
+#define FK_VLOOP FK_PRAGMA(unroll FK_VLOOP_N)
+// the loops over the 8-column tiles of a stage: unrolled (row slots above a tile vanish at compile time) or kept as loops
+#ifndef FK_TILE_N
+#define FK_TILE_LOOP _Pragma("unroll")
+#else
+#define FK_TILE_LOOP FK_PRAGMA(unroll FK_TILE_N)
+#endif
+#ifndef FK_U_DOT
+#define FK_U_DOT 4
+#endif
+#ifndef FK_U_TRMM
+#define FK_U_TRMM 4
+#endif
+#ifndef FK_U_SYRK
+#define FK_U_SYRK 3
+#endif
+#ifndef FK_U_UPD
+#define FK_U_UPD 2
+#endif
 
 namespace cuipm {
 namespace fastk {
@@ -233,6 +261,7 @@ struct Ker
     FK_DEV void vcopy(double *dst, size_t off, int nd)
     {
         const double *src = (REC == 0 ? qk : (REC == 1 ? sol : (REC == 2 ? wk : qp))) + off;
+FK_VLOOP
         for (int e = 2 * li; e < nd; e += 2 * G) fk_cp16(dst + e, src + e);
     }
     // all lanes are done with the buffers the next copies overwrite
@@ -283,7 +312,7 @@ struct Ker
 #pragma unroll
         for (int m = 0; m < RP; m++) o2[m] = 0.0;
         int j = 0;
-#pragma unroll 4
+FK_PRAGMA(unroll FK_U_DOT)
         for (; j + 1 < nc; j += 2)
         {
             const fk_double2 xx = fk_ld2(x + j);
@@ -320,7 +349,7 @@ struct Ker
 #pragma unroll
         for (int m = 0; m < CP; m++) { out[m] = 0.0; o2[m] = 0.0; }
         int i = 0;
-#pragma unroll 4
+FK_PRAGMA(unroll FK_U_DOT)
         for (; i + 1 < nr; i += 2)
         {
             const fk_double2 ww = fk_ld2(w + i);
@@ -413,12 +442,14 @@ struct Ker
         if (update)
         {
             double *gu = v.s + sd.sol.ux, *gp = v.s + sd.sol.pi;
+FK_VLOOP
             for (int i = li; i < n + 2 * ns; i += G)
             {
                 const double x = ux[i] + alpha_u * du[i];
                 ux[i] = x;
                 st(gu + i, x);
             }
+FK_VLOOP
             for (int j = li; j < nx1; j += G)
             {
                 const double p = pi[j] + alpha_u * dp[j];
@@ -426,10 +457,12 @@ struct Ker
                 st(gp + j, p);
             }
         }
+FK_VLOOP
         for (int j = li; j < nx1; j += G) x1[j] = update ? SOLN[nu1 + j] + alpha_u * STPN[nu1 + j] : SOLN[nu1 + j];
         {
             double *gl = v.s + sd.sol.lam, *gt = v.s + sd.sol.t;
             double *bl = wk + A.w_bkp + (sd.sol.lam + v.kk * A.ss), *bt = wk + A.w_bkp + (sd.sol.t + v.kk * A.ss);
+FK_VLOOP
             for (int i = li; i < nc; i += G)
             {
                 double l = lam[i], tt = t[i];
@@ -456,6 +489,7 @@ struct Ker
             }
         }
         fk_sync();
+FK_VLOOP
         for (int i = li; i < nb; i += G) tmp0[i] = lam[nb + i] - lam[i];
         wait_mat();
         fk_sync();
@@ -511,6 +545,7 @@ struct Ker
         else
             fk_sync();
         // ---- box scatter, slack rows
+FK_VLOOP
         for (int i = li; i < nb; i += G)
         {
             const int ix = idxb[i];
@@ -519,6 +554,7 @@ struct Ker
         }
         if (ns > 0)
         {
+FK_VLOOP
             for (int j = li; j < 2 * ns; j += G)
             {
                 const double sj = ux[n + j], zz = qz[j];
@@ -536,6 +572,7 @@ struct Ker
         // ---- res_d, res_m
         {
             double *od = v.w + sd.res.d, *om = v.w + sd.res.m, *obk = v.w + sd.w_rmb;
+FK_VLOOP
             for (int i = li; i < nc; i += G)
             {
                 const double dv = qd[i];
@@ -570,6 +607,7 @@ struct Ker
                 R.f3 |= (a != a);
             }
             double *og = v.w + sd.res.g;
+FK_VLOOP
             for (int i = li; i < n + 2 * ns; i += G)
             {
                 const double r = g_[i];
@@ -579,6 +617,7 @@ struct Ker
                 R.f0 |= (a != a);
             }
         }
+FK_VLOOP
         for (int j = li; j < nx1; j += G) pim[j] = pi[j];      // pi_k is "pi_{k-1}" of the next stage
     }
 
@@ -610,6 +649,7 @@ struct Ker
     FK_DEV void cond_slacks(int nb, int ns, const int *rev, const int *inv, const double *Z, int fact, const double *Gam, const double *gam,
                             const double *rgs, double *Zi, double *ds, double *tmp0, double *tmp1) const
     {
+FK_VLOOP
         for (int j = li; j < 2 * ns; j += G)
         {
             const int jj = j < ns ? j : j - ns, offc = j < ns ? 0 : nb;
@@ -624,6 +664,7 @@ struct Ker
             ds[j] = d;
         }
         fk_sync();
+FK_VLOOP
         for (int i = li; i < nb; i += G)
         {
             const int j = rev[i];
@@ -816,6 +857,7 @@ struct Ker
             // Gamma, gamma (COMPUTE_GAMMA_GAMMA_QP, x_core_qp_ipm_aux.c:38-86)
             const double t_min_inv = A.o.t_min > 0 ? 1.0 / A.o.t_min : 1e30;
             recip_vec(gt, Gam, nc);                  // same lane, same index below: no barrier needed
+FK_VLOOP
             for (int i = li; i < nc; i += G)
             {
                 const double l = gl[i], tt = gt[i], ti = Gam[i];
@@ -825,6 +867,7 @@ struct Ker
                     Gam[i] = ti * l;
                 gam[i] = ti * (rm[i] - l * rd[i]);
             }
+FK_VLOOP
             for (int i = li; i < n; i += G) dadd[i] = A.o.reg_prim;
         }
         fk_sync();
@@ -832,6 +875,7 @@ struct Ker
         {
             cond_slacks(nb, ns, rev, inv, ZQ, 1, Gam, gam, rowv + n, Zi, ds, tmp0, tmp1);
             fk_sync();
+FK_VLOOP
             for (int j = li; j < 2 * ns; j += G)
             {
                 st(v.w + sd.w_Zsi + j, Zi[j]);
@@ -840,6 +884,7 @@ struct Ker
         }
         else
         {
+FK_VLOOP
             for (int i = li; i < nb; i += G)
             {
                 tmp0[i] = Gam[i] + Gam[nb + i];
@@ -847,6 +892,7 @@ struct Ker
             }
             fk_sync();
         }
+FK_VLOOP
         for (int i = li; i < nb; i += G)
         {
             const int ix = idxb[i];
@@ -878,6 +924,7 @@ struct Ker
                     if (li + G * m < nx1) st(Pb + li + G * m, tt_[m]);
             }
             fk_sync();
+FK_VLOOP
             for (int j = li; j < nx1; j += G) alb[j] += lprev[j];
         }
         // the vector images are dead from here on (gradient and diagonal additions are in registers / in their own arrays):
@@ -892,7 +939,7 @@ struct Ker
             const double *Lx = ML + nu1 + LDW * nu1;
             FK_PROF_ADD2(11);      /* gradient */
             // ---- in place: AL = A * Lxx   (row slots x 8-column tiles)
-#pragma unroll
+FK_TILE_LOOP
             for (int jt = 0; jt < nx1; jt += 8)
             {
                 const int w = nx1 - jt < 8 ? nx1 - jt : 8;
@@ -918,7 +965,7 @@ struct Ker
                         for (int m = 0; m < RP; m++) acc[m][q] += a[m] * l;
                     }
                 }
-#pragma unroll 4
+FK_PRAGMA(unroll FK_U_TRMM)
                 for (int c = jt + 8; c < nx1; c++)
                 {
                     double a[RPM > 0 ? RPM : 1];
@@ -950,7 +997,7 @@ struct Ker
         // ---- column tiles: SYRK + left-looking Cholesky, rows r >= jt; gradient h = g + AL alb in the first tile
         const double *Hk = v.k + A.kH[KIND];
         double *Lg = v.w + sd.w_L, *lrow = v.w + sd.w_lrow;
-#pragma unroll
+FK_TILE_LOOP
         for (int jt = 0; jt < n; jt += 8)
         {
             const int w = n - jt < 8 ? n - jt : 8;
@@ -971,7 +1018,7 @@ struct Ker
             }
             if (nx1 > 0)
             {
-#pragma unroll 3
+FK_PRAGMA(unroll FK_U_SYRK)
                 for (int c = 0; c < nx1; c++)
                 {
                     double a[RPM > 0 ? RPM : 1], b[8];
@@ -1001,7 +1048,7 @@ struct Ker
                 stage_begin();
                 fact_issue_mat(k - 1);
             }
-#pragma unroll 2
+FK_PRAGMA(unroll FK_U_UPD)
             for (int c = 0; c < jt; c++)
             {
                 double a[RPM > 0 ? RPM : 1], b[8];
@@ -1033,19 +1080,17 @@ struct Ker
                 }
             FK_PROF_ADD2(13);      /* SYRK + update + H */
             // ---- the tile's columns: diagonal block, rows below, gradient
+            // (a stage has full tiles and at most one narrower tile, its last)
+            constexpr int WL = n % 8 ? n % 8 : 8;
             if (w >= 8) panel8<n, nu, RP, 8>(jt, m0, acc, hh, DD8, Lg, v.w + sd.w_Lxx, lrow, lvec, Linv);
-            else if (w == 7) panel8<n, nu, RP, 7>(jt, m0, acc, hh, DD8, Lg, v.w + sd.w_Lxx, lrow, lvec, Linv);
-            else if (w == 6) panel8<n, nu, RP, 6>(jt, m0, acc, hh, DD8, Lg, v.w + sd.w_Lxx, lrow, lvec, Linv);
-            else if (w == 5) panel8<n, nu, RP, 5>(jt, m0, acc, hh, DD8, Lg, v.w + sd.w_Lxx, lrow, lvec, Linv);
-            else if (w == 4) panel8<n, nu, RP, 4>(jt, m0, acc, hh, DD8, Lg, v.w + sd.w_Lxx, lrow, lvec, Linv);
-            else if (w == 3) panel8<n, nu, RP, 3>(jt, m0, acc, hh, DD8, Lg, v.w + sd.w_Lxx, lrow, lvec, Linv);
-            else if (w == 2) panel8<n, nu, RP, 2>(jt, m0, acc, hh, DD8, Lg, v.w + sd.w_Lxx, lrow, lvec, Linv);
-            else panel8<n, nu, RP, 1>(jt, m0, acc, hh, DD8, Lg, v.w + sd.w_Lxx, lrow, lvec, Linv);
+            else panel8<n, nu, RP, WL>(jt, m0, acc, hh, DD8, Lg, v.w + sd.w_Lxx, lrow, lvec, Linv);
             FK_PROF_ADD2(14);      /* panels */
         }
         {
             double *li_ = v.w + sd.w_Linv;
+FK_VLOOP
             for (int j = li; j < n; j += G) st(li_ + j, Linv[j]);
+FK_VLOOP
             for (int j = li; j < nx; j += G) lprev[j] = lvec[nu + j];
         }
     }
@@ -1055,6 +1100,7 @@ struct Ker
         // the factor is built in ML; its strict upper triangle must read as zero (the triangular products of the sweep run
         // over full rows / columns), and the other sweeps leave the Hessian there
         fk_sync();
+FK_VLOOP
         for (int e = li; e < SZL; e += G) ML[e] = 0.0;
         fk_fence_async_global();        // the records this sweep reads with bulk copies were written with plain stores by the sweeps before
 
@@ -1106,6 +1152,7 @@ struct Ker
             double *grm = v.w + sd.res.m;
             const double t_min_inv = A.o.t_min > 0 ? 1.0 / A.o.t_min : 1e30;
             recip_vec(gt, Gam, nc);
+FK_VLOOP
             for (int i = li; i < nc; i += G)
             {
                 const double l = gl[i], tt = gt[i], ti = Gam[i];
@@ -1123,15 +1170,19 @@ struct Ker
             cond_slacks(nb, ns, rev, inv, qZ, 0, Gam, gam, vv + n, const_cast<double *>(Zi), ds, tmp0, tmp1);
             fk_sync();
             double *o_ = v.w + sd.step.ux + n;
+FK_VLOOP
             for (int j = li; j < 2 * ns; j += G)
                 if (so) o_[j] = ds[j];
         }
         else
         {
+FK_VLOOP
             for (int i = li; i < nb; i += G) tmp1[i] = gam[i] - gam[nb + i];
             fk_sync();
         }
+FK_VLOOP
         for (int i = li; i < nb; i += G) vv[idxb[i]] += tmp1[i];
+FK_VLOOP
         for (int j = li; j < nx1; j += G) tmpx[j] = xprev[j] + pbs[j];
         wait_mat();
         fk_sync();
@@ -1258,8 +1309,10 @@ struct Ker
         const double *mks = QM, *qZ = QM + (sd.q_Z - sd.q_dmask);
         {
             const double *src = after_fact ? lrow_ : SUX;
+FK_VLOOP
             for (int i = li; i < nsolve; i += G) vv[i] = -src[i];
             // x part (k>0) was written into vv by the previous stage
+FK_VLOOP
             for (int j = li; j < 2 * ns; j += G) dsv[j] = SUX[n + j];
         }
         wait_mat();
@@ -1294,6 +1347,7 @@ struct Ker
         }
         {
             double *o_ = v.w + sd.step.ux;
+FK_VLOOP
             for (int i = li; i < n; i += G)
                 if (so) o_[i] = vv[i];
         }
@@ -1343,6 +1397,7 @@ struct Ker
             double *tis = dlm;                   // 1 / t; shares the array of the masked multiplier steps: entry i is read, then
                                                  // overwritten, by the same lane in the loop over the constraints below
             recip_vec(ts, tis, nc);
+FK_VLOOP
             for (int i = li; i < nb; i += G)
             {
                 const double a = vv[idxb[i]];
@@ -1353,6 +1408,7 @@ struct Ker
             {
                 fk_sync();
                 const double t_min_inv = A.o.t_min > 0 ? 1.0 / A.o.t_min : 1e30;
+FK_VLOOP
                 for (int j = li; j < 2 * ns; j += G)
                 {
                     const int jj = j < ns ? j : j - ns, offc = j < ns ? 0 : nb;
@@ -1368,17 +1424,20 @@ struct Ker
                     dt[2 * nb + j] = d;
                 }
                 fk_sync();
+FK_VLOOP
                 for (int i = li; i < 2 * nb; i += G)
                 {
                     const int up = i >= nb, ii = up ? i - nb : i;
                     if (rev[ii] >= 0) dt[i] += dsv[(up ? ns : 0) + rev[ii]];
                 }
                 double *o_ = v.w + sd.step.ux + n;
+FK_VLOOP
                 for (int j = li; j < 2 * ns; j += G)
                     if (so) o_[j] = dsv[j];
             }
             fk_sync();
             double *odl = v.w + sd.step.lam, *odt = v.w + sd.step.t, *ld_ = v.w + sd.ires.d, *lm_ = v.w + sd.ires.m;
+FK_VLOOP
             for (int i = li; i < nc; i += G)
             {
                 const double l = lam[i], tt = ts[i], ti = tis[i], rdi = rds[i], rmi = rms[i];
@@ -1447,6 +1506,7 @@ struct Ker
         if (do_lin)
         {
             // ---- res_g of the linear system (lane = row): H dux + rhs_g - dpi_{k-1} + A dpi_k + constraint multipliers
+FK_VLOOP
             for (int i = li; i < nb; i += G) tmp0[i] = dlm[nb + i] - dlm[i];
             double ap[RPM > 0 ? RPM : 1];
             if (nx1 > 0) rows_dot<n, nx1>(MA, LDK, pik, ap);
@@ -1463,10 +1523,12 @@ struct Ker
                 }
             }
             fk_sync();
+FK_VLOOP
             for (int i = li; i < nb; i += G) g_[idxb[i]] += tmp0[i];
             if (ns > 0)
             {
                 const double *zv = gv + n;
+FK_VLOOP
                 for (int j = li; j < 2 * ns; j += G)
                 {
                     double r = qZ[j] * dsv[j] + zv[j] - dlm[2 * nb + j];
@@ -1477,6 +1539,7 @@ struct Ker
             }
             fk_sync();
             double *og = v.w + sd.ires.g;
+FK_VLOOP
             for (int i = li; i < n + 2 * ns; i += G)
             {
                 const double r = g_[i];
@@ -1489,6 +1552,7 @@ struct Ker
         FK_PROF_ADD2(22);      /* residual rows */
         if (nx1 > 0)
         {
+FK_VLOOP
             for (int j = li; j < nx1; j += G)
             {
                 vv[nu1 + j] = x1[j];
@@ -1532,6 +1596,7 @@ struct Ker
             const StageDesc &s = sdr(k);
             const View v = viewr(k);
             const double *l = v.s + s.sol.lam, *t = v.s + s.sol.t, *dl = v.w + s.step.lam, *dt = v.w + s.step.t;
+FK_VLOOP
             for (int i = li; i < s.nc; i += G) acc += fabs((l[i] + alpha * dl[i]) * (t[i] + alpha * dt[i]));
         };
         plain(0);
@@ -1587,8 +1652,11 @@ struct Ker
                 double *l = v.s + s.sol.lam, *t = v.s + s.sol.t, *gux = v.s + s.sol.ux, *gpi = v.s + s.sol.pi;
                 // keep what the caller passed in for the case that this QP is handed back to the generic kernel
                 double *kl = v.w + s.itref.lam, *kt = v.w + s.itref.t, *kp = v.w + s.itref.pi;
+FK_VLOOP
                 for (int i = li; i < s.n + 2 * s.ns; i += G) st(gux + i, 0.0);
+FK_VLOOP
                 for (int i = li; i < s.nx1; i += G) st(kp + i, gpi[i]);
+FK_VLOOP
                 for (int i = li; i < s.nc; i += G)
                 {
                     st(kl + i, l[i]);
@@ -1609,16 +1677,21 @@ struct Ker
             const int *idxb = IDX + 4 * (A.nmaps == 3 ? (k == 0 ? 0 : (k == A.N ? 2 : 1)) : k) * A.nbe, *rev = idxb + nb;
             const double *d = v.q + s.q_d;
             double *gux = v.s + s.sol.ux, *gpi = v.s + s.sol.pi, *gl = v.s + s.sol.lam, *gt = v.s + s.sol.t;
+FK_VLOOP
             for (int i = li; i < s.nx1; i += G) st(gpi + i, 0.0);
             if (A.o.t0_init == 0 || A.o.t0_init == 1)
             {
                 const double l0 = A.o.t0_init == 0 ? sqrt(A.o.mu0) : A.o.mu0, t0 = A.o.t0_init == 0 ? sqrt(A.o.mu0) : 1.0;
+FK_VLOOP
                 for (int i = li; i < n + 2 * ns; i += G) st(gux + i, 0.0);
+FK_VLOOP
                 for (int i = li; i < nc; i += G) { st(gl + i, l0); st(gt + i, t0); }
                 continue;
             }
+FK_VLOOP
             for (int i = li; i < n + 2 * ns; i += G) ux[i] = 0.0;
             fk_sync();
+FK_VLOOP
             for (int j = li; j < 2 * ns; j += G)
             {
                 double tj = ux[n + j] - d[2 * nb + j];
@@ -1630,6 +1703,7 @@ struct Ker
                 tt[2 * nb + j] = tj;
             }
             fk_sync();
+FK_VLOOP
             for (int j = li; j < nb; j += G)
             {
                 const int ix = idxb[j];
@@ -1659,7 +1733,9 @@ struct Ker
                 tt[nb + j] = tu;
             }
             fk_sync();
+FK_VLOOP
             for (int i = li; i < n + 2 * ns; i += G) st(gux + i, ux[i]);
+FK_VLOOP
             for (int i = li; i < nc; i += G)
             {
                 st(gt + i, tt[i]);
@@ -1689,6 +1765,7 @@ struct Ker
         Q.mu = Q.obj = Q.gap = 0.0; Q.alpha = 1.0; Q.res_m_tau = 0.0;
         Q.res_max[0] = Q.res_max[1] = Q.res_max[2] = Q.res_max[3] = 0.0;
         if (stat && act)
+FK_VLOOP
             for (int i = li; i < SM * (A.o.stat_max + 1); i += G) stat[i] = 0.0;
 
         // constraint mask census (x_ocp_qp_ipm.c:2774-2806)
@@ -1697,6 +1774,7 @@ struct Ker
         {
             const StageDesc &s = sdr(k);
             const double *gm = viewr(k).q + s.q_dmask;
+FK_VLOOP
             for (int i = li; i < s.nc; i += G) cnt += fk_ldg(gm + i) != 0.0;
         }
         const int nc_mask = (int) (gsum((double) cnt) + 0.5);
@@ -1713,6 +1791,7 @@ struct Ker
             const View v = viewr(k);
             double *l = v.s + s.sol.lam;
             const double *gm = v.q + s.q_dmask;
+FK_VLOOP
             for (int i = li; i < s.nc; i += G) st(l + i, l[i] * fk_ldg(gm + i));
         }
         fk_sync();
