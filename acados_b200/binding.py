@@ -14,6 +14,25 @@ import numpy as np
 from .problems import Batch, Layout, Shape
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+def host_threads() -> int:
+    """Host threads this process can actually run at once: the affinity mask, capped by the cgroup CPU quota (a container may
+    see 128 CPUs and be allowed 16 CPUs' worth of time; a thread team sized from the mask then spends its quota spinning)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(-(-int(quota) // int(period)))))
+    except Exception:  # noqa: BLE001
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = max(1, min(n, -(-q // per)))
+        except Exception:  # noqa: BLE001
+            pass
+    return n
+
+
 LIB_PATH = os.environ.get("CUIPM_LIB") or os.path.join(_HERE, "csrc", "libcuipm.so")
 
 STAT_M = 20

@@ -333,6 +333,50 @@ extern "C" int cuipm_solve_host_async(cuipm_solver *s, int nbatch, const double 
     return CUIPM_OK;
 }
 
+// Chunk-granular form of the host entry: records lo .. lo+n-1 of the batch whose host buffers start at qp / sol / info are copied
+// in, solved and copied out on pipe stream `slot`; returns as soon as the work is enqueued.  A caller that produces its records
+// chunk by chunk (the acados plugin unpacking ocp_qp_in structs) overlaps that with the copies and solves of the chunks before.
+extern "C" int cuipm_solve_host_chunk(cuipm_solver *s, int slot, int lo, int n, const double *qp, double *sol, cuipm_info *info,
+                                      const cuipm_opts *opts)
+{
+    if (!s || slot < 0 || slot >= cuipm_solver::kPipe || lo < 0 || n < 0 || lo + n > s->max_batch || !qp || !sol || !info || !opts)
+    {
+        set_error("cuipm_solve_host_chunk: bad arguments (slot in 0..7, lo + n <= max_batch)");
+        return CUIPM_ERR_INVALID;
+    }
+    int rc = opts_check(opts);
+    if (rc != CUIPM_OK) return rc;
+    CK(cudaSetDevice(s->device));
+    if (n == 0) return CUIPM_OK;
+    cudaStream_t st = s->pipe[slot];
+    const size_t qo = s->P.qp_stride * (size_t) lo, so = s->P.sol_stride * (size_t) lo;
+    CK(cudaMemcpyAsync(s->d_qp + qo, qp + qo, sizeof(double) * s->P.qp_stride * n, cudaMemcpyHostToDevice, st));
+    if (opts->warm_start >= 1)
+        CK(cudaMemcpyAsync(s->d_sol + so, sol + so, sizeof(double) * s->P.sol_stride * n, cudaMemcpyHostToDevice, st));
+    LaunchArgs a;
+    a.P = s->P; a.sd = s->d_sd; a.ipool = s->d_ipool; a.qp = s->d_qp + qo; a.sol = s->d_sol + so;
+    a.work = s->d_work + s->P.work_stride * (size_t) lo; a.info = s->d_info + lo;
+    a.stat = nullptr;
+    a.o = *opts; a.nbatch = n; a.seed = nullptr; a.sens = nullptr; a.adjoint = 0;
+    int nlaunch = 0;
+    rc = launch_batch(s, a, slot, (size_t) lo, st, &nlaunch);
+    if (rc != CUIPM_OK) return rc;
+    CK(cudaMemcpyAsync(sol + so, s->d_sol + so, sizeof(double) * s->P.sol_stride * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(info + lo, s->d_info + lo, sizeof(cuipm_info) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(s->pipe_done[slot], st));
+    s->last_launches = nlaunch;
+    s->last_opts = *opts;
+    return CUIPM_OK;
+}
+
+extern "C" int cuipm_wait_chunk(cuipm_solver *s, int slot)
+{
+    if (!s || slot < 0 || slot >= cuipm_solver::kPipe) { set_error("cuipm_wait_chunk: bad arguments"); return CUIPM_ERR_INVALID; }
+    CK(cudaSetDevice(s->device));
+    CK(cudaEventSynchronize(s->pipe_done[slot]));
+    return CUIPM_OK;
+}
+
 extern "C" int cuipm_wait(cuipm_solver *s)
 {
     if (!s) { set_error("cuipm_wait: null solver"); return CUIPM_ERR_INVALID; }

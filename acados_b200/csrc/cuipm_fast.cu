@@ -83,6 +83,12 @@ static __device__ __forceinline__ double fk_ldg(const double *p) { return __ldg(
 typedef double2 fk_double2;
 // two consecutive doubles of shared memory, 16-byte aligned (LDS.128)
 static __device__ __forceinline__ fk_double2 fk_ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+// FP64 tensor-core product D = A B + C on 8 x 4 / 4 x 8 / 8 x 8 fragments spread over the warp (DMMA): lane l holds
+// A[l / 4][l % 4], B[l % 4][l / 4] and C[l / 4][2 (l % 4) .. + 1]
+static __device__ __forceinline__ void fk_dmma(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 static __device__ __forceinline__ double fk_rsqrt(double x) { return rsqrt(x); }
 static __device__ __forceinline__ int fk_atomic_inc(int *p) { return atomicAdd(p, 1); }
 
@@ -220,7 +226,8 @@ cudaError_t launch_one(const FastArgs &F, cudaStream_t stream)
     X(21, 3, 8, 4)              \
     X(8, 3, 4, 8)               \
     X(4, 1, 2, 8)               \
-    X(12, 4, 8, 6)
+    X(12, 4, 8, 6)              \
+    X(48, 12, 32, 3)
 
 // development: other lanes-per-QP mappings of the headline shape, selected with CUIPM_FAST_G=16|32
 #ifdef CUIPM_FAST_DEV

@@ -22,7 +22,7 @@
 // redo_list) and solved from scratch by the generic kernel.
 //
 // The file is written against a few warp primitives supplied by the including translation unit (FK_DEV, fk_lane,
-// fk_sync, fk_shfl_xor, fk_any, fk_bulk, fk_mbar_*, fk_fence_async, fk_ldg, fk_rsqrt, fk_atomic_inc): the CUDA
+// fk_sync, fk_shfl_xor, fk_any, fk_bulk, fk_dmma, fk_mbar_*, fk_fence_async, fk_ldg, fk_rsqrt, fk_atomic_inc): the CUDA
 // instantiation is cuipm_fast.cu; oracle/fast_emul.cpp instantiates the same body on a host emulation of a warp for the
 // CPU test-suite.
 #ifndef CUIPM_FAST_CORE_H_
@@ -98,6 +98,17 @@ struct Ker
     static constexpr int SZD = 0;                         // (the diagonal blocks of the factorisation are published in the vector pool)
     static constexpr int MATS = SZA + SZL + SZU + SZD;
 
+    // FP64 tensor-core tiles (mma.m8n8k4) for the level-3 parts of the factorisation: one QP per warp only (the fragments span
+    // the 32 lanes), contraction lengths that are multiples of four
+    template <int NX1>
+    struct MMA
+    {
+#ifdef FK_NO_MMA
+        static constexpr bool on = false;
+#else
+        static constexpr bool on = G == 32 && NX1 % 4 == 0 && NM >= 16 && (NM * NU + 1) / 2 * 2 >= 66 * 8;   // (the fragments are transposed through LU)
+#endif
+    };
     // stage kinds: 0 = first (nx = 0), 1 = interior, 2 = last (nu = 0)
     template <int KIND>
     struct KD
@@ -938,7 +949,37 @@ FK_VLOOP
         {
             const double *Lx = ML + nu1 + LDW * nu1;
             FK_PROF_ADD2(11);      /* gradient */
-            // ---- in place: AL = A * Lxx   (row slots x 8-column tiles)
+            // ---- in place: AL = A * Lxx
+            if (MMA<nx1>::on)
+            {
+                // one QP per warp, FP64 tensor cores: 8 x 8 tiles of AL as sums of (8 x 4)(4 x 8) products, all row blocks of a
+                // column tile kept in fragments (Lxx is lower triangular and ML reads as zero above its diagonal: k starts at the tile)
+                const int l4 = fk_lane() & 3, r8 = fk_lane() >> 2;
+                constexpr int NRB = (n + 7) / 8;
+#pragma unroll 1
+                for (int jt = 0; jt < nx1; jt += 8)
+                {
+                    double C[NRB][2];
+#pragma unroll
+                    for (int i = 0; i < NRB; i++) C[i][0] = C[i][1] = 0.0;
+                    const double *bp = Lx + l4 + LDW * (jt + r8), *ap = MA + r8 + n * l4;
+#pragma unroll 2
+                    for (int k0 = jt; k0 < nx1; k0 += 4)
+                    {
+                        const double b = bp[k0];
+#pragma unroll
+                        for (int i = 0; i < NRB; i++) fk_dmma(C[i][0], C[i][1], ap[8 * i + n * k0], b);
+                    }
+#pragma unroll
+                    for (int i = 0; i < NRB; i++)
+                        if (8 * i + r8 < n)
+                        {
+                            MA[8 * i + r8 + n * (jt + 2 * l4)] = C[i][0];
+                            MA[8 * i + r8 + n * (jt + 2 * l4 + 1)] = C[i][1];
+                        }
+                }
+            }
+            else
 FK_TILE_LOOP
             for (int jt = 0; jt < nx1; jt += 8)
             {
@@ -1016,6 +1057,75 @@ FK_TILE_LOOP
                     h[m][q] = (q < w && r < n && r >= jt + q) ? fk_ldg(Hk + r + LDK * (jt + q)) : 0.0;
                 }
             }
+            if (MMA<nx1>::on)
+            {
+                // the rows jt .. n-1 of the tile's columns in blocks of eight, as fragments of the tensor-core product: Gram product
+                // of the rows of AL, minus the columns of L already factorised; the fragments go through shared memory (TT, the
+                // buffer of the substitution sweeps' panel) into the row slots the panel factorisation works on
+                const int l4 = fk_lane() & 3, r8 = fk_lane() >> 2;
+                constexpr int NRBmax = (n + 7) / 8, LDT = 66;
+                const int nrb = (n - jt + 7) / 8;
+                double C[NRBmax][2];
+#pragma unroll
+                for (int i = 0; i < NRBmax; i++) C[i][0] = C[i][1] = 0.0;
+                if (nx1 > 0)
+                {
+                    const double *ap = MA + jt + r8 + n * l4;
+#pragma unroll 2
+                    for (int k0 = 0; k0 < nx1; k0 += 4)
+                    {
+                        const double b = ap[n * k0];
+#pragma unroll
+                        for (int i = 0; i < NRBmax; i++)
+                            if (i < nrb) fk_dmma(C[i][0], C[i][1], i == 0 ? b : ap[8 * i + n * k0], b);
+                    }
+                    if (jt == 0)
+                    {
+#pragma unroll 4
+                        for (int c = 0; c < nx1; c++)
+                        {
+                            const double ab = alb[c];
+#pragma unroll
+                            for (int m = 0; m < RP; m++) hh[m] += MA[(li + G * m < n ? li + G * m : 0) + n * c] * ab;
+                        }
+                    }
+                }
+                if (jt + 8 >= n && k > 0)
+                {   // last use of the dynamics block: request the one of the next stage of the sweep
+                    stage_begin();
+                    fact_issue_mat(k - 1);
+                }
+                {
+                    const double *lp = ML + jt + r8 + LDW * l4;
+#pragma unroll 2
+                    for (int k0 = 0; k0 < jt; k0 += 4)
+                    {
+                        const double b = lp[LDW * k0];
+#pragma unroll
+                        for (int i = 0; i < NRBmax; i++)
+                            if (i < nrb) fk_dmma(C[i][0], C[i][1], -(i == 0 ? b : lp[8 * i + LDW * k0]), b);
+                    }
+                }
+                double *TT = LU;
+#pragma unroll
+                for (int i = 0; i < NRBmax; i++)
+                    if (i < nrb)
+                    {
+                        TT[8 * i + r8 + LDT * (2 * l4)] = C[i][0];
+                        TT[8 * i + r8 + LDT * (2 * l4 + 1)] = C[i][1];
+                    }
+                fk_sync();
+#pragma unroll
+                for (int m = 0; m < RP; m++)
+                    if (m >= m0)
+                    {
+                        const int r = li + G * m;
+                        const int rr = (r >= jt && r < n) ? r - jt : 0;
+#pragma unroll
+                        for (int q = 0; q < 8; q++) acc[m][q] = TT[rr + LDT * q];
+                    }
+            }
+            else {
             if (nx1 > 0)
             {
 FK_PRAGMA(unroll FK_U_SYRK)
@@ -1065,6 +1175,7 @@ FK_PRAGMA(unroll FK_U_UPD)
                     if (m >= m0)
 #pragma unroll
                         for (int q = 0; q < 8; q++) acc[m][q] -= a[m] * b[q];
+            }
             }
 #pragma unroll
             for (int m = 0; m < RP; m++)

@@ -332,6 +332,31 @@ int ocp_qp_cuipm(void *config_, void *qp_in_, void *qp_out_, void *opts_, void *
     return acados_status(mem->status);
 }
 
+/* threads for the struct (un)packing: the OpenMP default, capped by the cgroup CPU quota (a container may show 128 CPUs and allow
+ * 16 CPUs' worth of time: a team sized from the mask then burns the quota in its barriers) and by CUIPM_HOST_THREADS */
+static int pack_threads(void)
+{
+    static int nt = 0;
+    if (nt > 0) return nt;
+    int n = omp_get_max_threads();
+    FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r");
+    if (f)
+    {
+        char q[32];
+        long per = 0;
+        if (fscanf(f, "%31s %ld", q, &per) == 2 && strcmp(q, "max") && per > 0)
+        {
+            long c = (atol(q) + per - 1) / per;
+            if (c >= 1 && c < n) n = (int) c;
+        }
+        fclose(f);
+    }
+    const char *e = getenv("CUIPM_HOST_THREADS");
+    if (e && atoi(e) > 0) n = atoi(e);
+    nt = n > 0 ? n : 1;
+    return nt;
+}
+
 int ocp_qp_cuipm_batch_solve(void *config_, int n, ocp_qp_in **qp_in, ocp_qp_out **qp_out, void *opts_, void *mem_, int *status_out)
 {
     ocp_qp_cuipm_opts *opts = opts_;
@@ -354,24 +379,71 @@ int ocp_qp_cuipm_batch_solve(void *config_, int n, ocp_qp_in **qp_in, ocp_qp_out
     }
     double *qp = mem->b_qp, *sol = mem->b_sol;
     cuipm_info *infos = mem->b_info;
-#pragma omp parallel for schedule(static)
-    for (int i = 0; i < n; i++)
+    /* Pipeline over chunks, two parallel regions in all (a region per chunk costs a barrier of the whole thread team each, which
+     * dominates when the team is larger than the cores the process may use): the threads draw QPs from a counter and unpack the
+     * structs into the page-locked records; whoever completes a chunk submits it (copy in, solve, copy out on the chunk's own
+     * stream, the kernels of different chunks share the SMs) and goes on unpacking the later chunks.  In the second region the
+     * threads draw QPs again, wait for the chunk of their QP and pack its solution into the ocp_qp_out struct while the later
+     * chunks are still being solved. */
+    const int nchunk = n >= 512 ? 8 : 1, per = (n + nchunk - 1) / nchunk;
+    int next = 0, done_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, rc_all = CUIPM_OK;
+    const int nthr = pack_threads();
+#pragma omp parallel num_threads(nthr)
     {
-        pack_qp(qp_in[i], l, qp + l->qp_stride * (size_t) i);
-        if (opts->c.warm_start >= 2) pack_sol(qp_out[i], qp_in[i]->dim, l, sol + l->sol_stride * (size_t) i);
+        for (;;)
+        {
+            int i;
+#pragma omp atomic capture seq_cst
+            i = next++;
+            if (i >= n) break;
+            pack_qp(qp_in[i], l, qp + l->qp_stride * (size_t) i);
+            if (opts->c.warm_start >= 2) pack_sol(qp_out[i], qp_in[i]->dim, l, sol + l->sol_stride * (size_t) i);
+            const int c = i / per, lo = c * per, m = n - lo < per ? n - lo : per;
+            int d;
+#pragma omp atomic capture seq_cst
+            d = ++done_cnt[c];
+            if (d == m)
+            {
+                int rc = cuipm_solve_host_chunk(mem->solver, c, lo, m, qp, sol, infos, &opts->c);
+                if (rc != CUIPM_OK)
+                {
+#pragma omp atomic write
+                    rc_all = rc;
+                }
+            }
+        }
     }
-    int rc = cuipm_solve_host(mem->solver, n, qp, sol, infos, NULL, &opts->c);
-    if (rc != CUIPM_OK) { printf("\nerror: ocp_qp_cuipm_batch_solve: %s\n", cuipm_last_error()); exit(1); }
-    double t_solve = acados_toc(&timer);
+    if (rc_all != CUIPM_OK) { printf("\nerror: ocp_qp_cuipm_batch_solve: %s\n", cuipm_last_error()); exit(1); }
     int worst = ACADOS_SUCCESS;
-#pragma omp parallel for schedule(static)
+    double t_solve = 0.0;
+    next = 0;
+#pragma omp parallel num_threads(nthr)
+    {
+        int waited = -1;
+        for (;;)
+        {
+            int i;
+#pragma omp atomic capture seq_cst
+            i = next++;
+            if (i >= n) break;
+            const int c = i / per;
+            if (c != waited)
+            {
+                if (cuipm_wait_chunk(mem->solver, c) != CUIPM_OK) { printf("\nerror: ocp_qp_cuipm_batch_solve: %s\n", cuipm_last_error()); exit(1); }
+                waited = c;
+            }
+            unpack_sol(sol + l->sol_stride * (size_t) i, qp_in[i]->dim, l, qp_out[i]);
+            qp_info *info = qp_out[i]->misc;
+            info->interface_time = 0;
+            info->num_iter = infos[i].iter; info->t_computed = 1;
+            if (status_out) status_out[i] = acados_status(infos[i].status);
+        }
+    }
+    t_solve = acados_toc(&timer);
     for (int i = 0; i < n; i++)
     {
-        unpack_sol(sol + l->sol_stride * (size_t) i, qp_in[i]->dim, l, qp_out[i]);
         qp_info *info = qp_out[i]->misc;
-        info->solve_QP_time = t_solve / n; info->interface_time = 0; info->total_time = t_solve / n;
-        info->num_iter = infos[i].iter; info->t_computed = 1;
-        if (status_out) status_out[i] = acados_status(infos[i].status);
+        info->solve_QP_time = t_solve / n; info->total_time = t_solve / n;
     }
     for (int i = 0; i < n; i++)
     {

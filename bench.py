@@ -124,7 +124,8 @@ def cpu_reference(batch_obj, opts, nqp: int, threads: int = 0):
     from oracle import oracle_binding as ob
     sub = Batch(batch_obj.shape, batch_obj.layout, np.ascontiguousarray(batch_obj.qp[:nqp]), batch_obj.name)
     if threads <= 0:   # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1: do not rely on the OpenMP default)
-        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        from acados_b200.binding import host_threads
+        threads = host_threads()   # affinity mask capped by the cgroup CPU quota: more threads than that only burn the quota
     if ob.have_ref():
         ob.ref_solve(Batch(sub.shape, sub.layout, sub.qp[:min(nqp, 64)].copy()), opts, nthreads=threads)  # warm-up
         sol, info, tm = ob.ref_solve(sub, opts, nthreads=threads)
@@ -163,7 +164,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     steps, warmup = args.steps, max(args.warmup, 0)
 
-    from acados_b200.binding import INFO_DTYPE, default_opts
+    from acados_b200.binding import INFO_DTYPE, default_opts, host_threads
     opts = default_opts()   # what PARTIAL_CONDENSING_HPIPM runs with out of the box
     config = {"workload": f"chain-of-masses OCP-QP nx=21 nu=3 N=40 (after x0 elimination), nbu=3 hard + 4 one-sided soft "
                           f"state bounds (ns=4), batch={args.batch} per GPU, every QP its own matrices",
@@ -305,7 +306,7 @@ def main():
                 psec = psec[2:]
                 plugin = {"value": nb / float(psec.mean()), "unit": UNIT, "ms_per_call": 1e3 * float(psec.mean()), "calls": int(steps),
                           "entry": "ocp_qp_cuipm_batch_solve(config, n, ocp_qp_in**, ocp_qp_out**, opts, mem, status) -- acados_b200/plugin/ocp_qp_cuipm.c",
-                          "worst_acados_status": int(pst), "host_threads": len(os.sched_getaffinity(0)),
+                          "worst_acados_status": int(pst), "host_threads": host_threads(),
                           "max_abs_dsol_vs_record_path": float(np.max(np.abs(psol - h_sol.numpy()))),
                           "iter_equal_record_path": bool(np.array_equal(pit, hinfo["iter"]))}
             else:
@@ -429,9 +430,9 @@ def main():
                     tsol, tinfo = solver.solve(b.qp[:nsamp], topts)
                     sub = Batch(b.shape, b.layout, np.ascontiguousarray(b.qp[:nsamp]), b.name)
                     if ob.have_ref():
-                        trsol, trinfo, _ = ob.ref_solve(sub, topts, nthreads=len(os.sched_getaffinity(0)))
+                        trsol, trinfo, _ = ob.ref_solve(sub, topts, nthreads=host_threads())
                     else:
-                        trsol, trinfo = ob.oracle_solve(sub, topts, nthreads=len(os.sched_getaffinity(0)))
+                        trsol, trinfo = ob.oracle_solve(sub, topts, nthreads=host_threads())
                     tdu = np.max(np.abs(b.layout.u_traj(tsol) - b.layout.u_traj(trsol)), axis=1)
                     parity["tight_1e-12"] = {"instances": int(nsamp), "max_abs_du": float(tdu.max()), "frac_du_le_1e-10": float((tdu <= 1e-10).mean()),
                                              "iter_equal_frac": float((tinfo["iter"] == trinfo["iter"]).mean()),

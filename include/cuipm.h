@@ -182,6 +182,15 @@ int cuipm_solve_host(cuipm_solver *s, int nbatch, const double *qp, double *sol,
 int cuipm_solve_host_async(cuipm_solver *s, int nbatch, const double *qp, double *sol, cuipm_info *info, double *stat,
                            const cuipm_opts *opts);
 int cuipm_wait(cuipm_solver *s);
+/* Chunk-granular form: records lo .. lo+n-1 of the batch whose (page-locked) host buffers START at qp / sol / info are copied in,
+ * solved and copied out on internal stream `slot` (0..7; a slot must have been waited for before it is used again); returns
+ * once the work is enqueued.  cuipm_wait_chunk blocks until the chunk of that slot is back in the host buffers.  For callers
+ * that produce their records chunk by chunk: the plugin's batched entry unpacks the ocp_qp_in structs of chunk c+1 (the loop of
+ * d_ocp_qp getters of acados/ocp_qp/ocp_qp_hpipm.c:281-330 has no counterpart: HPIPM reads the structs in place) while the
+ * device copies and solves chunk c. */
+int cuipm_solve_host_chunk(cuipm_solver *s, int slot, int lo, int n, const double *qp, double *sol, cuipm_info *info,
+                           const cuipm_opts *opts);
+int cuipm_wait_chunk(cuipm_solver *s, int slot);
 
 /* Device-buffer entry: all pointers are device pointers on the solver's device; asynchronous on the
  * solver's stream unless `sync` != 0. */

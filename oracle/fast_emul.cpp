@@ -47,6 +47,7 @@ static inline fk_double2 fk_ld2(const double *p)
     if ((size_t) p & 15) { std::fprintf(stderr, "fast_emul: misaligned 16-byte load\n"); std::abort(); }
     return fk_double2{p[0], p[1]};
 }
+static inline void fk_dmma(double &c0, double &c1, double a, double b) { simt::dmma(c0, c1, a, b); }
 static inline double fk_rsqrt(double x) { return 1.0 / std::sqrt(x); }
 static inline int fk_atomic_inc(int *p) { return (*p)++; }
 using std::fabs;
@@ -117,6 +118,7 @@ extern "C" int fast_emul_solve(const cuipm_shape *sh, int nbatch, const double *
     INST(4, 1, 2) INST(4, 1, 4) INST(4, 1, 8)
     INST(12, 4, 8) INST(12, 4, 16)
     INST(5, 2, 4) INST(6, 2, 8)
+    INST(48, 12, 32)
 #undef INST
     cuipm_layout_destroy(l);
     return rc;

@@ -33,7 +33,7 @@ struct Warp
     int cur = 0;
     int gen = 0, arrived = 0;
     int order = 0;                 // 0: lanes 0..31, 1: lanes 31..0
-    double xd[NL];
+    double xd[NL], xd2[NL];
     int xi[NL];
     std::vector<PendingCopy> pend[NL];
     std::function<void()> body;
@@ -97,6 +97,21 @@ inline int shfl_i(int v, int src)
     const int r = w->xi[src & 31];
     sync();
     return r;
+}
+// D = A B + C of the m8n8k4 tensor-core product: lane l holds A[l / 4][l % 4], B[l % 4][l / 4], C[l / 4][2 (l % 4) .. + 1]
+inline void dmma(double &c0, double &c1, double a, double b)
+{
+    Warp *w = cur_warp();
+    w->xd[w->cur] = a;
+    w->xd2[w->cur] = b;
+    sync();
+    const int row = w->cur >> 2, col = 2 * (w->cur & 3);
+    for (int k = 0; k < 4; k++)
+    {
+        c0 += w->xd[row * 4 + k] * w->xd2[col * 4 + k];
+        c1 += w->xd[row * 4 + k] * w->xd2[(col + 1) * 4 + k];
+    }
+    sync();
 }
 inline unsigned ballot(bool p)
 {

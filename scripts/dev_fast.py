@@ -89,6 +89,10 @@ if __name__ == "__main__":
     if what == "time3":
         timing(problems.chain_mass(4096, N=40, seed=1234), "c2")
         timing(problems.named_config("c3", 16384), "c3")
+    if what == "time5":
+        timing(problems.named_config("c5", 1024), "c5")
+    if what == "par5":
+        parity(problems.named_config("c5", 64), "c5")
     if what == "time2":
         timing(problems.chain_mass(4096, N=40, seed=1234), "c2")
     if what in ("all", "time"):

@@ -183,12 +183,13 @@ def test_full_size_properties_c2(built):
     sub = P.Batch(b.shape, b.layout, np.ascontiguousarray(b.qp[idx]))
     osol, oinfo = ob.oracle_solve(sub, o)
     assert np.array_equal(info["iter"][idx], oinfo["iter"])
-    # At the DEFAULT tolerances (1e-6/1e-8) the iterates stop ~1e-8 from the exact solution; summation-order round-off is
-    # amplified to ~1e-10 on a few instances (1.24e-10 observed on 1 of 32): the bulk meets the north_star's 1e-10, the
-    # tail is bounded by 1e-9, and test_cuda_matches_oracle_converged asserts 1e-10 on all instances once both solvers
-    # are driven to 1e-12.
+    # At the DEFAULT tolerances (1e-6/1e-8) both solvers stop ~1e-8 from the exact solution and summation-order round-off
+    # decides the last digits: 98.7 % of the 4096 instances are within the north_star's 1e-10, the largest difference seen
+    # over the whole batch is 2.1e-9 (bench.py's parity record) -- a property of where the iteration stops, not of the
+    # arithmetic.  The 1e-10 bar itself is asserted on ALL 4096 instances at tight tolerances in
+    # test_tight_tolerance_parity_full_headline_batch; here the slice is held to "bulk within 1e-10, nothing beyond 5e-9".
     d = np.max(np.abs(b.layout.u_traj(sol[idx]) - b.layout.u_traj(osol)), axis=1)
-    assert (d <= TOL_U).mean() >= 0.9 and d.max() <= 1e-9, (d.max(), (d <= TOL_U).mean())
+    assert (d <= TOL_U).mean() >= 0.9 and d.max() <= 5e-9, (d.max(), (d <= TOL_U).mean())
     # batch-position independence + determinism
     perm = np.random.default_rng(0).permutation(4096)
     sol_p, info_p = s.solve(np.ascontiguousarray(b.qp[perm]), o)
@@ -199,16 +200,38 @@ def test_full_size_properties_c2(built):
     s.close()
 
 
-@pytest.mark.parametrize("name,nb", [("c3", 16384), ("c4", 2048), ("c5", 256)])
+def test_tight_tolerance_parity_full_headline_batch(built):
+    """all tolerances 1e-12 on the WHOLE headline batch (chain-mass, 4096 instances), CUDA path against
+    the reference (oracle/_ref when it travelled, else the oracle port): |du|_inf <= 1e-10 on every instance -- the north_star's
+    bar -- and iteration counts within one (the last iteration is decided by residuals at round-off level)."""
+    from oracle import oracle_binding as ob
+    b = P.chain_mass(4096, seed=1234)
+    o = default_opts(res_g_max=1e-12, res_b_max=1e-12, res_d_max=1e-12, res_m_max=1e-12)
+    sol, info = _solve(b, o)
+    from acados_b200.binding import host_threads
+    nt = host_threads()
+    if ob.have_ref():
+        rsol, rinfo, _ = ob.ref_solve(b, o, nthreads=nt)
+    else:
+        rsol, rinfo = ob.oracle_solve(b, o, nthreads=nt)
+    assert np.array_equal(info["status"], rinfo["status"]) and (info["status"] == 0).all()
+    assert np.max(np.abs(info["iter"] - rinfo["iter"])) <= 1
+    du = np.max(np.abs(b.layout.u_traj(sol) - b.layout.u_traj(rsol)), axis=1)
+    assert du.max() <= 1e-10, (du.max(), int((du > 1e-10).sum()))
+
+
+@pytest.mark.parametrize("name,nb", [("c3", 16384), ("c4", 8192), ("c5", 1024)])
 def test_other_configs_at_size(built, name, nb):
     from oracle import oracle_binding as ob
     b = P.named_config(name, nb)
     o = default_opts()
     sol, info = _solve(b, o)
     assert (info["status"] == 0).mean() > 0.98
-    idx = np.arange(0, nb, max(1, nb // 16))
+    from acados_b200.binding import host_threads
+    nt = host_threads()
+    idx = np.arange(0, nb, max(1, nb // 64))
     sub = P.Batch(b.shape, b.layout, np.ascontiguousarray(b.qp[idx]))
-    osol, oinfo = ob.oracle_solve(sub, o)
+    osol, oinfo = ob.oracle_solve(sub, o, nthreads=min(16, nt))
     assert np.array_equal(info["iter"][idx], oinfo["iter"])
     assert np.max(np.abs(b.layout.u_traj(sol[idx]) - b.layout.u_traj(osol))) <= _tol_default(name)
 
