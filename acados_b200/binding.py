@@ -130,6 +130,9 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.cuipm_condenser_condensed_shape.restype = vp
     lib.cuipm_condense_device.argtypes = [vp, ip, vp, vp, vp]
     lib.cuipm_condense_device.restype = ip
+    for f in (lib.cuipm_condense_lhs_device, lib.cuipm_condense_rhs_device):
+        f.argtypes = [vp, ip, vp, vp, vp]
+        f.restype = ip
     lib.cuipm_expand_device.argtypes = [vp, ip, vp, vp, vp, vp]
     lib.cuipm_expand_device.restype = ip
     lib.cuipm_set_tuning.argtypes = [vp, C.c_char_p, ip]
@@ -300,6 +303,18 @@ class CuipmCondenser:
 
     def condense(self, nbatch: int, d_qp: int, d_qp_cond: int, stream: int = 0):
         if self.lib.cuipm_condense_device(self.handle, nbatch, d_qp, d_qp_cond, stream or None) != 0:
+            raise RuntimeError(self.lib.cuipm_last_error().decode())
+
+    def condense_lhs(self, nbatch: int, d_qp: int, d_qp_cond: int, stream: int = 0):
+        """Condenses the QPs and keeps the prediction matrices of every stage on the device (the preparation phase of an SQP-RTI
+        step: ``condense_lhs`` of the reference's xcond solver)."""
+        if self.lib.cuipm_condense_lhs_device(self.handle, nbatch, d_qp, d_qp_cond, stream or None) != 0:
+            raise RuntimeError(self.lib.cuipm_last_error().decode())
+
+    def condense_rhs(self, nbatch: int, d_qp: int, d_qp_cond: int, stream: int = 0):
+        """Refreshes the vectors of the condensed records from records with the same matrices and new vectors (the feedback
+        phase: ``condense_rhs`` of the reference's xcond solver)."""
+        if self.lib.cuipm_condense_rhs_device(self.handle, nbatch, d_qp, d_qp_cond, stream or None) != 0:
             raise RuntimeError(self.lib.cuipm_last_error().decode())
 
     def expand(self, nbatch: int, d_qp: int, d_sol_cond: int, d_sol: int, stream: int = 0):

@@ -148,18 +148,15 @@ extern "C" cuipm_solver *cuipm_create(const cuipm_shape *shape, int max_batch, i
     if (!alloc((void **) &s->d_work, sizeof(double) * s->P.work_stride * max_batch)) return fail();
     if (!alloc((void **) &s->d_info, sizeof(cuipm_info) * max_batch)) return fail();
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(); }
-    cudaEventCreate(&s->ev0);
-    cudaEventCreate(&s->ev1);
-    cudaEventCreate(&s->evk0);
-    cudaEventCreate(&s->evk1);
-    for (int i = 0; i < cuipm_solver::kPipe; i++)
-    {
-        cudaStreamCreateWithFlags(&s->pipe[i], cudaStreamNonBlocking);
-        cudaEventCreateWithFlags(&s->pipe_done[i], cudaEventDisableTiming);
-    }
-    cudaMemsetAsync(s->d_work, 0, sizeof(double) * s->P.work_stride * max_batch, s->stream);
-    cudaMemsetAsync(s->d_sol, 0, sizeof(double) * s->P.sol_stride * max_batch, s->stream);
-    cudaStreamSynchronize(s->stream);
+    bool ok = cudaEventCreate(&s->ev0) == cudaSuccess && cudaEventCreate(&s->ev1) == cudaSuccess
+              && cudaEventCreate(&s->evk0) == cudaSuccess && cudaEventCreate(&s->evk1) == cudaSuccess;
+    for (int i = 0; ok && i < cuipm_solver::kPipe; i++)
+        ok = cudaStreamCreateWithFlags(&s->pipe[i], cudaStreamNonBlocking) == cudaSuccess
+             && cudaEventCreateWithFlags(&s->pipe_done[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMemsetAsync(s->d_work, 0, sizeof(double) * s->P.work_stride * max_batch, s->stream) == cudaSuccess
+         && cudaMemsetAsync(s->d_sol, 0, sizeof(double) * s->P.sol_stride * max_batch, s->stream) == cudaSuccess
+         && cudaStreamSynchronize(s->stream) == cudaSuccess;
+    if (!ok) { set_error(std::string("cuipm_create: streams / events / initial clears: ") + cudaGetErrorString(cudaGetLastError())); return fail(); }
     // default warps per QP: one warp owns one QP unless the stage block is large
     s->warps = s->P.nmax > 40 ? 4 : 1;
     return s;
@@ -285,7 +282,11 @@ extern "C" int cuipm_solve_host_async(cuipm_solver *s, int nbatch, const double 
     int rc = opts_check(opts);
     if (rc != CUIPM_OK) return rc;
     CK(cudaSetDevice(s->device));
-    s->pending = 0;
+    if (s->pending)
+    {   // a previous asynchronous solve of this object is still in flight: its device buffers (and d_stat) are in use
+        rc = cuipm_wait(s);
+        if (rc != CUIPM_OK) return rc;
+    }
     if (nbatch == 0) return CUIPM_OK;
     const size_t stat_n = (size_t) nbatch * CUIPM_STAT_M * (opts->stat_max + 1);
     if (stat && s->stat_cap < stat_n)

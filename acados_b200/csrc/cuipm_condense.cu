@@ -26,13 +26,15 @@ struct CtaExec
     }
 };
 
-__global__ void condense_kernel(Plan P, const double *qp, double *qp2, int nbatch)
+template <int MODE>
+__global__ void condense_kernel(Plan P, const double *qp, double *qp2, double *tbuf, int nbatch)
 {
     extern __shared__ double scr[];
     const int q = blockIdx.x;
     if (q >= nbatch) return;
     CtaExec ex;
-    condense_one(ex, P, qp + (size_t) q * P.o.qp_stride, qp2 + (size_t) q * P.c.qp_stride, scr);
+    condense_one<MODE>(ex, P, qp + (size_t) q * P.o.qp_stride, qp2 + (size_t) q * P.c.qp_stride, scr,
+                       MODE == COND_ALL ? nullptr : tbuf + (size_t) q * P.t_stride);
 }
 
 __global__ void expand_kernel(Plan P, const double *qp, const double *sol2, double *sol, int nbatch)
@@ -54,6 +56,8 @@ struct cuipm_condenser
     int *d_i = nullptr;
     unsigned *d_u = nullptr;
     size_t smem = 0;
+    double *d_t = nullptr;        // T_j of the QPs of the last lhs pass (t_stride doubles per QP)
+    int t_cap = 0, t_valid = 0;   // QPs the buffer holds / QPs the last lhs pass filled
 };
 
 #define CKC(call)                                                                                       \
@@ -72,6 +76,7 @@ extern "C" void cuipm_condenser_destroy(cuipm_condenser *c)
     cudaSetDevice(c->device);
     cudaFree(c->d_i);
     cudaFree(c->d_u);
+    cudaFree(c->d_t);
     delete c;
 }
 
@@ -98,7 +103,9 @@ extern "C" cuipm_condenser *cuipm_condenser_create(const cuipm_shape *shape, int
     c->P = c->hp.plan(c->d_i, c->d_u);
     c->smem = sizeof(double) * (size_t) scratch_doubles(c->P);
     if (c->smem > 227 * 1024) { set_error("condensed stage too large for the shared-memory scratch"); cuipm_condenser_destroy(c); return nullptr; }
-    cudaFuncSetAttribute(condense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->smem);
+    cudaFuncSetAttribute(condense_kernel<COND_ALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->smem);
+    cudaFuncSetAttribute(condense_kernel<COND_LHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->smem);
+    cudaFuncSetAttribute(condense_kernel<COND_RHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->smem);
     cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c->smem);
     return c;
 }
@@ -112,7 +119,42 @@ extern "C" int cuipm_condense_device(cuipm_condenser *c, int nbatch, const doubl
     CKC(cudaSetDevice(c->device));
     // the masks of a fresh record are 1 and untouched entries of d / Z / z are 0 in the reference's layout: clear, then fill
     CKC(cudaMemsetAsync(d_qp_cond, 0, sizeof(double) * c->hp.lc->qp_stride * (size_t) nbatch, (cudaStream_t) stream));
-    condense_kernel<<<nbatch, 128, c->smem, (cudaStream_t) stream>>>(c->P, d_qp, d_qp_cond, nbatch);
+    condense_kernel<COND_ALL><<<nbatch, 128, c->smem, (cudaStream_t) stream>>>(c->P, d_qp, d_qp_cond, nullptr, nbatch);
+    CKC(cudaGetLastError());
+    return CUIPM_OK;
+}
+
+// The split of acados' xcond solver (ocp_qp_xcond_solver.c:591-669: condense_lhs in the preparation phase of an SQP-RTI step,
+// condense_rhs_and_solve in its feedback phase): the lhs pass condenses the whole QP and keeps the prediction matrices T_j of
+// every stage per QP on the device; the rhs pass recomputes the vectors of the condensed records (gradient, dynamics offset,
+// shifted bounds, slack gradient) for new b, rq, d, z of the same matrices -- O(nx^2 + nx n2) per stage instead of O(nx^2 n2).
+extern "C" int cuipm_condense_lhs_device(cuipm_condenser *c, int nbatch, const double *d_qp, double *d_qp_cond, void *stream)
+{
+    if (!c || nbatch < 0 || !d_qp || !d_qp_cond) { set_error("cuipm_condense_lhs_device: bad arguments"); return CUIPM_ERR_INVALID; }
+    if (nbatch == 0) return CUIPM_OK;
+    CKC(cudaSetDevice(c->device));
+    if (c->t_cap < nbatch)
+    {
+        CKC(cudaStreamSynchronize((cudaStream_t) stream));
+        cudaFree(c->d_t);
+        c->d_t = nullptr; c->t_cap = 0; c->t_valid = 0;
+        CKC(cudaMalloc(&c->d_t, sizeof(double) * (size_t) c->P.t_stride * (size_t) nbatch));
+        c->t_cap = nbatch;
+    }
+    CKC(cudaMemsetAsync(d_qp_cond, 0, sizeof(double) * c->hp.lc->qp_stride * (size_t) nbatch, (cudaStream_t) stream));
+    condense_kernel<COND_LHS><<<nbatch, 128, c->smem, (cudaStream_t) stream>>>(c->P, d_qp, d_qp_cond, c->d_t, nbatch);
+    CKC(cudaGetLastError());
+    c->t_valid = nbatch;
+    return CUIPM_OK;
+}
+
+extern "C" int cuipm_condense_rhs_device(cuipm_condenser *c, int nbatch, const double *d_qp, double *d_qp_cond, void *stream)
+{
+    if (!c || nbatch < 0 || !d_qp || !d_qp_cond) { set_error("cuipm_condense_rhs_device: bad arguments"); return CUIPM_ERR_INVALID; }
+    if (nbatch > c->t_valid) { set_error("cuipm_condense_rhs_device: no lhs pass for this many QPs (call cuipm_condense_lhs_device first)"); return CUIPM_ERR_INVALID; }
+    if (nbatch == 0) return CUIPM_OK;
+    CKC(cudaSetDevice(c->device));
+    condense_kernel<COND_RHS><<<nbatch, 128, c->smem, (cudaStream_t) stream>>>(c->P, d_qp, d_qp_cond, c->d_t, nbatch);
     CKC(cudaGetLastError());
     return CUIPM_OK;
 }

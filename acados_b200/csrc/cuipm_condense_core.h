@@ -39,16 +39,25 @@ struct Plan
     const int *box_ptr, *box_stage, *box_i;   // condensed box p of block b (p in box_ptr[b]..box_ptr[b+1]): original (stage, bound index)
     const int *gen_ptr, *gen_stage, *gen_kind, *gen_i;   // condensed general constraint: kind 0 = state bound i of an inner stage, 1 = general constraint i
     int nxmax, n2max;                         // scratch sizing: max of nx and nu over stages, max (nu2 + nx) over blocks
+    // lhs / rhs split (condense_lhs / condense_rhs of acados/ocp_qp/ocp_qp_partial_condensing.c:575-630): the matrices T_j =
+    // [Gam_j | Phi_j] of every original stage (nx_j x n2 of its block) kept per QP by the lhs pass at t_off[j] of a resident buffer
+    // of t_stride doubles per QP, read by the rhs pass
+    const unsigned *t_off;
+    unsigned t_stride;
 };
+
+// what a pass computes: everything; everything + T_j kept (lhs); the vectors only, with the T_j of an earlier lhs pass (rhs)
+enum { COND_ALL = 0, COND_LHS = 1, COND_RHS = 2 };
 
 CC_HD inline int scratch_doubles(const Plan &P) { return 2 * P.nxmax * P.n2max + 4 * P.nxmax + 2 * P.n2max + 16; }
 
 // symmetric access to the lower-stored Hessian block of the ORIGINAL record (column-major, ld n)
 CC_HD inline double hsym(const double *H, int n, int i, int j) { return i >= j ? H[i + n * j] : H[j + n * i]; }
 
-template <class Exec>
-CC_HD void condense_one(Exec &ex, const Plan &P, const double *q, double *o, double *scr)
+template <int MODE, class Exec>
+CC_HD void condense_one(Exec &ex, const Plan &P, const double *q, double *o, double *scr, double *tbuf)
 {
+    constexpr bool MAT = MODE != COND_RHS;    // the matrices of the condensed QP are (re)computed
     const LayoutTab &L = P.o, &C = P.c;
     const int NT = ex.nthreads();
     double *T = scr, *T2 = T + P.nxmax * P.n2max, *cv = T2 + P.nxmax * P.n2max, *cv2 = cv + P.nxmax, *qc = cv2 + P.nxmax;
@@ -59,9 +68,12 @@ CC_HD void condense_one(Exec &ex, const Plan &P, const double *q, double *o, dou
         double *H2 = o + C.RSQ[b], *g2 = o + C.rq[b], *d2 = o + C.d[b], *m2 = o + C.dmask[b];
         // T_0 = [0 | I], c_0 = 0 (T is nx_j x n2, column-major, ld = nx_j); H2, g2 cleared
         ex.phase([&](int t) {
-            for (int e = t; e < nx0 * n2; e += NT) T[e] = (e / nx0 - nuu == e % nx0) ? 1.0 : 0.0;
+            if (MAT)
+            {
+                for (int e = t; e < nx0 * n2; e += NT) T[e] = (e / nx0 - nuu == e % nx0) ? 1.0 : 0.0;
+                for (int e = t; e < n2 * n2; e += NT) H2[e] = 0.0;
+            }
             for (int e = t; e < nx0; e += NT) cv[e] = 0.0;
-            for (int e = t; e < n2 * n2; e += NT) H2[e] = 0.0;
             for (int e = t; e < n2; e += NT) g2[e] = 0.0;
         });
         int nxj = nx0;
@@ -69,8 +81,13 @@ CC_HD void condense_one(Exec &ex, const Plan &P, const double *q, double *o, dou
         {
             const int j = k0 + jj, nu = L.nu[j], n = nu + nxj, nx1 = L.nx[j + 1], ou = P.st_offu[j];
             const double *Hj = q + L.RSQ[j], *rqj = q + L.rq[j], *BA = q + L.BAt[j], *bj = q + L.b[j];
+            // T_j: in the scratch (computed by this pass) or in the resident buffer (rhs pass); the lhs pass keeps it
+            const double *Tj = MODE == COND_RHS ? tbuf + P.t_off[j] : T;
+            if (MODE == COND_LHS)
+                ex.phase([&](int t) { for (int e = t; e < nxj * n2; e += NT) tbuf[P.t_off[j] + e] = T[e]; });
             // T2 = Q_j T (nx_j x n2); qc = Q_j c + q_j
             ex.phase([&](int t) {
+                if (MAT)
                 for (int e = t; e < nxj * n2; e += NT)
                 {
                     const int i = e % nxj, c = e / nxj;
@@ -87,6 +104,7 @@ CC_HD void condense_one(Exec &ex, const Plan &P, const double *q, double *o, dou
             });
             // H2 += T' (Q T);  g2 += T' qc
             ex.phase([&](int t) {
+                if (MAT)
                 for (int e = t; e < n2 * n2; e += NT)
                 {
                     const int r = e % n2, c = e / n2;
@@ -97,13 +115,14 @@ CC_HD void condense_one(Exec &ex, const Plan &P, const double *q, double *o, dou
                 for (int r = t; r < n2; r += NT)
                 {
                     double acc = 0.0;
-                    for (int i = 0; i < nxj; i++) acc += T[i + nxj * r] * qc[i];
+                    for (int i = 0; i < nxj; i++) acc += Tj[i + nxj * r] * qc[i];
                     g2[r] += acc;
                 }
             });
             // input part: ST = S_j T (nu x n2) added to rows / columns ou.., R_j on the diagonal block, S_j c + r_j on the gradient
             if (nu > 0)
             {
+                if (MAT) {
                 ex.phase([&](int t) {
                     for (int e = t; e < nu * n2; e += NT)
                     {
@@ -130,7 +149,9 @@ CC_HD void condense_one(Exec &ex, const Plan &P, const double *q, double *o, dou
                         H2[c + n2 * (ou + a)] += T2[e];
                     }
                 });
+                }
                 ex.phase([&](int t) {
+                    if (MAT)
                     for (int e = t; e < nu * nu; e += NT)
                     {
                         const int a = e % nu, a2 = e / nu;
@@ -156,6 +177,7 @@ CC_HD void condense_one(Exec &ex, const Plan &P, const double *q, double *o, dou
                     const int pl = p - P.gen_ptr[b], kind = P.gen_kind[p], i = P.gen_i[p];
                     const int xi = kind == 0 ? L.idxb[L.idxb_ptr[j] + i] - nu : 0, pos = kind == 0 ? i : nbj + i;
                     ex.phase([&](int t) {
+                        if (MAT)
                         for (int r = t; r < n2; r += NT)
                         {
                             double acc;
@@ -204,6 +226,7 @@ CC_HD void condense_one(Exec &ex, const Plan &P, const double *q, double *o, dou
             }
             // transition: T <- A_j T (+ B_j in the columns of u_j), c <- A_j c + b_j   (BAt_j = [B'; A'], (nu+nx) x nx1, ld n)
             ex.phase([&](int t) {
+                if (MAT)
                 for (int e = t; e < nx1 * n2; e += NT)
                 {
                     const int i = e % nx1, c = e / nx1;
@@ -220,7 +243,8 @@ CC_HD void condense_one(Exec &ex, const Plan &P, const double *q, double *o, dou
                 }
             });
             ex.phase([&](int t) {
-                for (int e = t; e < nx1 * n2; e += NT) T[e] = T2[e];
+                if (MAT)
+                    for (int e = t; e < nx1 * n2; e += NT) T[e] = T2[e];
                 for (int i = t; i < nx1; i += NT) cv[i] = cv2[i];
             });
             nxj = nx1;
@@ -230,6 +254,7 @@ CC_HD void condense_one(Exec &ex, const Plan &P, const double *q, double *o, dou
             double *BA2 = o + C.BAt[b], *b2 = o + C.b[b];
             const int nx1 = nxj;
             ex.phase([&](int t) {
+                if (MAT)
                 for (int e = t; e < n2 * nx1; e += NT)
                 {
                     const int r = e % n2, c = e / n2;
@@ -252,8 +277,11 @@ CC_HD void condense_one(Exec &ex, const Plan &P, const double *q, double *o, dou
     {
         const int kN = L.N, k2 = C.N, n = L.nu[kN] + L.nx[kN], ng = L.ng[kN], nc = 2 * (L.nb[kN] + ng + L.ns[kN]), ns2 = 2 * L.ns[kN];
         ex.phase([&](int t) {
-            for (int e = t; e < n * n; e += NT) o[C.RSQ[k2] + e] = q[L.RSQ[kN] + e];
-            for (int e = t; e < n * ng; e += NT) o[C.DCt[k2] + e] = q[L.DCt[kN] + e];
+            if (MAT)
+            {
+                for (int e = t; e < n * n; e += NT) o[C.RSQ[k2] + e] = q[L.RSQ[kN] + e];
+                for (int e = t; e < n * ng; e += NT) o[C.DCt[k2] + e] = q[L.DCt[kN] + e];
+            }
             for (int e = t; e < n; e += NT) o[C.rq[k2] + e] = q[L.rq[kN] + e];
             for (int e = t; e < nc; e += NT) { o[C.d[k2] + e] = q[L.d[kN] + e]; o[C.dmask[k2] + e] = q[L.dmask[kN] + e]; }
             for (int e = t; e < ns2; e += NT) { o[C.Z[k2] + e] = q[L.Z[kN] + e]; o[C.z[k2] + e] = q[L.z[kN] + e]; }

@@ -23,7 +23,8 @@ struct HostPlan
     // flat pools: every table of Plan is a slice of one of these (so that they can be uploaded in two copies)
     std::vector<int> ipool;
     std::vector<unsigned> upool;
-    struct Slices { size_t o_dims[5], c_dims[5], o_ibp, o_ib, c_ibp, c_ib, blk_k0, blk_m, offu, offs, box_ptr, box_stage, box_i, gen_ptr, gen_stage, gen_kind, gen_i; size_t o_off[13], c_off[13]; } sl{};
+    struct Slices { size_t o_dims[5], c_dims[5], o_ibp, o_ib, c_ibp, c_ib, blk_k0, blk_m, offu, offs, box_ptr, box_stage, box_i, gen_ptr, gen_stage, gen_kind, gen_i; size_t o_off[13], c_off[13]; size_t t_off; } sl{};
+    unsigned t_stride = 0;                    // doubles per QP of the resident T_j buffer of the lhs / rhs split
     int nxmax = 0, n2max = 0;
 
     ~HostPlan() { cuipm_layout_destroy(lo); cuipm_layout_destroy(lc); }
@@ -48,6 +49,7 @@ struct HostPlan
         P.box_ptr = ib + sl.box_ptr; P.box_stage = ib + sl.box_stage; P.box_i = ib + sl.box_i;
         P.gen_ptr = ib + sl.gen_ptr; P.gen_stage = ib + sl.gen_stage; P.gen_kind = ib + sl.gen_kind; P.gen_i = ib + sl.gen_i;
         P.nxmax = nxmax; P.n2max = n2max;
+        P.t_off = ub + sl.t_off; P.t_stride = t_stride;
         return P;
     }
 };
@@ -135,6 +137,19 @@ inline bool build_plan(const cuipm_shape *sh, int cond_N, HostPlan &hp)
     };
     offs13(hp.lo, N, hp.sl.o_off);
     offs13(hp.lc, cond_N, hp.sl.c_off);
+    // T_j of every original stage (nx_j x n2 of its block), kept per QP between the lhs and the rhs pass
+    hp.sl.t_off = hp.upool.size();
+    {
+        size_t off = 0;
+        for (int b = 0; b < cond_N; b++)
+            for (int j = blk_k0[b]; j < blk_k0[b] + blk_m[b]; j++)
+            {
+                hp.upool.push_back((unsigned) off);
+                off += (size_t) sh->nx[j] * (size_t) (hp.nu2[b] + hp.nx2[b]);
+            }
+        hp.upool.push_back((unsigned) off);
+        hp.t_stride = (unsigned) ((off + 1) & ~(size_t) 1);
+    }
     return true;
 }
 

@@ -415,6 +415,7 @@ class OcpQpBatchSolver:
 
     def _load(self, qps):
         N = qps[0].N
+        self._idxe0 = [int(i) for i in qps[0].idxe[0]]
         cond_N = self.opts.cond_N if self.opts.cond_N is not None else N
         self._cond = None
         if self.device_reduce:
@@ -438,11 +439,39 @@ class OcpQpBatchSolver:
         return self.packed.N
 
     def update(self, qps: Sequence[OcpQp]):
-        """New data, same structure (an SQP / RL sweep re-solving with updated linearisations)."""
+        """New data, same structure (an SQP / RL sweep re-solving with updated linearisations).  The reducer, the condenser
+        and the solver hold index maps and buffers of the structure they were built for: a batch of another size, other
+        dimensions, bound / slack index maps or stage-0 equalities is refused rather than solved with stale maps."""
+        old, old_idxe, old_nb = self.packed.shape, [int(i) for i in self._idxe0], self.packed.nbatch
         self._load(qps)
+        new = self.packed.shape
+        same = (len(qps) == old_nb and [int(i) for i in qps[0].idxe[0]] == old_idxe and new.N == old.N
+                and all(list(getattr(new, f)) == list(getattr(old, f)) for f in ("nx", "nu", "nb", "ng", "ns"))
+                and all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(new.idxb, old.idxb))
+                and all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(new.idxs_rev, old.idxs_rev)))
+        if not same:
+            raise ValueError("OcpQpBatchSolver.update: the new batch does not have the structure (batch size, dimensions, idxb, "
+                             "idxs_rev, idxe) this solver was built for; create a new solver")
 
-    def solve(self) -> np.ndarray:
+    def condense_lhs(self) -> None:
+        """Preparation phase of an SQP-RTI step (``ocp_qp_xcond_solver``'s condense_lhs, ocp_qp_xcond_solver.c:591-627): the QPs
+        loaded last are reduced and condensed on the device and the condensed records -- with the prediction matrices of every
+        stage -- stay there.  Device path with cond_N < N only."""
+        if not (self.device_reduce and self._dcond is not None):
+            raise RuntimeError("condense_lhs: needs the device path with cond_N < N")
+        self.solve(_lhs_only=True)
+
+    def condense_rhs_and_solve(self) -> np.ndarray:
+        """Feedback phase (``condense_rhs_and_solve``, ocp_qp_xcond_solver.c:629-669): the QPs loaded last (``update``: same
+        matrices as at ``condense_lhs``, new vectors) refresh the vectors of the resident condensed records, which are then solved
+        and expanded.  Returns the acados status per QP."""
+        if not (self.device_reduce and self._dcond is not None and getattr(self, "_d_cond", None) is not None):
+            raise RuntimeError("condense_rhs_and_solve: call condense_lhs first (device path, cond_N < N)")
+        return self.solve(_rhs_only=True)
+
+    def solve(self, _lhs_only: bool = False, _rhs_only: bool = False) -> np.ndarray:
         """Returns the acados status per QP (0 success, 2 max iter, 3 min step, 1 NaN; ocp_qp_hpipm.c:398-404)."""
+        lhs_only, rhs_only = _lhs_only, _rhs_only
         warm = self._sol if (self.c_opts.warm_start >= 2 and self._sol is not None) else None
         if self._cond is not None:
             self._sol, self.info, self.stat = self._solver.solve(self._cqp, self.c_opts, sol0=warm, want_stat=True)
@@ -468,7 +497,17 @@ class OcpQpBatchSolver:
             torch.cuda.synchronize(dev)
             red.reduce(nb, d_full.data_ptr(), d_red.data_ptr(), st)
             if dc is not None:
-                dc.condense(nb, d_red.data_ptr(), d_qp.data_ptr(), st)
+                if rhs_only:
+                    # feedback phase: the condensed records of the preparation phase stay on the device, only their vectors
+                    # are refreshed (cuipm_condense_rhs_device, O(nx^2 + nx n2) per stage)
+                    d_qp = self._d_cond
+                    dc.condense_rhs(nb, d_red.data_ptr(), d_qp.data_ptr(), st)
+                else:
+                    dc.condense_lhs(nb, d_red.data_ptr(), d_qp.data_ptr(), st)
+                    self._d_cond = d_qp
+            if lhs_only:
+                torch.cuda.synchronize(dev)
+                return None
             self._solver.solve_device(nb, d_qp.data_ptr(), d_sol.data_ptr(), d_info.data_ptr(), o, sync=False, d_stat=d_stat.data_ptr())
             if dc is not None:
                 dc.expand(nb, d_red.data_ptr(), d_sol.data_ptr(), d_sol_red.data_ptr(), st)

@@ -252,6 +252,14 @@ void cuipm_condenser_destroy(cuipm_condenser *c);
 const cuipm_shape *cuipm_condenser_condensed_shape(const cuipm_condenser *c);     /* owned by c */
 int cuipm_condense_device(cuipm_condenser *c, int nbatch, const double *d_qp, double *d_qp_cond, void *stream);
 int cuipm_expand_device(cuipm_condenser *c, int nbatch, const double *d_qp, const double *d_sol_cond, double *d_sol, void *stream);
+/* The lhs / rhs split of the reference's condensing module (ocp_qp_partial_condensing.c:575-630 condense_lhs / condense_rhs ->
+ * d_part_cond_qp_cond_lhs / _rhs, x_part_cond.c:410,564; used by ocp_qp_xcond_solver.c:591-669 and the SQP-RTI preparation /
+ * feedback phases, ocp_nlp_sqp_rti.c:461-520): cuipm_condense_lhs_device condenses the QPs and keeps the prediction matrices of
+ * every stage per QP on the device; cuipm_condense_rhs_device then refreshes only the vectors of the SAME condensed records
+ * (gradients, dynamics offsets, shifted bounds) from records whose matrices are unchanged and whose vectors (b, rq, d, z --
+ * e.g. a new x0 folded in by the stage-0 elimination) are new.  Same arguments as cuipm_condense_device. */
+int cuipm_condense_lhs_device(cuipm_condenser *c, int nbatch, const double *d_qp, double *d_qp_cond, void *stream);
+int cuipm_condense_rhs_device(cuipm_condenser *c, int nbatch, const double *d_qp, double *d_qp_cond, void *stream);
 
 /* Riccati quantities of the last factorisation (reference: ocp_qp_hpipm_solver_get, ocp_qp_hpipm.c:417-478).
  * field in {"P","p","K","k","Lr"}; copies column-major data of QP `iqp`, stage `stage` into `value`. */

@@ -43,8 +43,35 @@ int emul_condense(const cuipm_shape *sh, int cond_N, int nbatch, const double *q
     for (int q = 0; q < nbatch; q++)
     {
         double *o = qp2 + (size_t) q * hp.lc->qp_stride;
-        condense_one(ex, P, qp + (size_t) q * hp.lo->qp_stride, o, scr.data());
+        condense_one<COND_ALL>(ex, P, qp + (size_t) q * hp.lo->qp_stride, o, scr.data(), nullptr);
     }
+    return 0;
+}
+
+// the lhs / rhs split: lhs pass on the records qp (condensed records qp2 written in full, T_j kept in tbuf, t_stride doubles per
+// QP as emul_t_stride says), then -- if qp_new is given -- the rhs pass on qp_new (same matrices, new vectors) refreshing qp2
+size_t emul_t_stride(const cuipm_shape *sh, int cond_N)
+{
+    HostPlan hp;
+    if (!build_plan(sh, cond_N, hp)) return 0;
+    return hp.t_stride;
+}
+
+int emul_condense_split(const cuipm_shape *sh, int cond_N, int nbatch, const double *qp, const double *qp_new, double *qp2, int nthreads)
+{
+    HostPlan hp;
+    if (!build_plan(sh, cond_N, hp)) return -1;
+    const Plan P = hp.plan(hp.ipool.data(), hp.upool.data());
+    std::vector<double> scr(scratch_doubles(P)), tb((size_t) hp.t_stride * nbatch);
+    SeqExec ex{nthreads};
+    for (int q = 0; q < nbatch; q++)
+        condense_one<COND_LHS>(ex, P, qp + (size_t) q * hp.lo->qp_stride, qp2 + (size_t) q * hp.lc->qp_stride, scr.data(), tb.data() + (size_t) q * hp.t_stride);
+    if (qp_new)
+        for (int q = 0; q < nbatch; q++)
+        {
+            for (double &x : scr) x = 1e300;      // the rhs pass must not depend on what the lhs pass left in the scratch
+            condense_one<COND_RHS>(ex, P, qp_new + (size_t) q * hp.lo->qp_stride, qp2 + (size_t) q * hp.lc->qp_stride, scr.data(), tb.data() + (size_t) q * hp.t_stride);
+        }
     return 0;
 }
 

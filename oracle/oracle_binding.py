@@ -132,6 +132,21 @@ def ref_solve_xcond(batch: Batch, idxe0, cond_N: int, opts: CuipmOpts):
 EMUL_LIB = os.path.join(_HERE, "libcondense_emul.so")
 
 
+def emul_condense_split(batch: Batch, new_qp, cond_N: int, nthreads: int = 128):
+    """lhs pass on ``batch`` then rhs pass on the records ``new_qp`` (same matrices, other vectors; None: lhs only) of the
+    product's condensing kernel body, run sequentially on the host (oracle/condense_emul.cpp).  Returns the condensed records."""
+    lib = _load(EMUL_LIB)
+    qs, ss = C.c_size_t(0), C.c_size_t(0)
+    if not lib.emul_condensed_strides(C.byref(batch.shape.as_ctypes()), C.c_int(cond_N), C.byref(qs), C.byref(ss)):
+        raise ValueError("bad cond_N")
+    out = np.zeros((batch.nbatch, qs.value))
+    nq = None if new_qp is None else np.ascontiguousarray(new_qp)
+    rc = lib.emul_condense_split(C.byref(batch.shape.as_ctypes()), C.c_int(cond_N), C.c_int(batch.nbatch), C.c_void_p(batch.qp.ctypes.data),
+                                 C.c_void_p(nq.ctypes.data if nq is not None else None), C.c_void_p(out.ctypes.data), C.c_int(nthreads))
+    assert rc == 0
+    return out
+
+
 def emul_condense(batch: Batch, cond_N: int, nthreads: int = 128):
     """The product's block-condensing kernel body run sequentially on the host (oracle/condense_emul.cpp): returns the
     condensed records.  ``nthreads`` is the emulated CTA size (results must not depend on it)."""
