@@ -57,6 +57,12 @@
 #else
 #define FK_TILE_LOOP FK_PRAGMA(unroll FK_TILE_N)
 #endif
+// (the same for the tile loop of the Gram product / panel factorisation alone)
+#ifndef FK_TILE2_N
+#define FK_TILE_LOOP2 FK_TILE_LOOP
+#else
+#define FK_TILE_LOOP2 FK_PRAGMA(unroll FK_TILE2_N)
+#endif
 #ifndef FK_U_DOT
 #define FK_U_DOT 4
 #endif
@@ -1038,7 +1044,7 @@ FK_PRAGMA(unroll FK_U_TRMM)
         // ---- column tiles: SYRK + left-looking Cholesky, rows r >= jt; gradient h = g + AL alb in the first tile
         const double *Hk = v.k + A.kH[KIND];
         double *Lg = v.w + sd.w_L, *lrow = v.w + sd.w_lrow;
-FK_TILE_LOOP
+FK_TILE_LOOP2
         for (int jt = 0; jt < n; jt += 8)
         {
             const int w = n - jt < 8 ? n - jt : 8;

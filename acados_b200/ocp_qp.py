@@ -206,9 +206,15 @@ class OcpQpOptions:
     print_level: int = 0
 
     def make_consistent(self, N: int):
-        if self.qp_solver not in ("PARTIAL_CONDENSING_CUIPM", "PARTIAL_CONDENSING_HPIPM"):
-            raise ValueError(f"qp_solver {self.qp_solver} is not served by this backend (PARTIAL_CONDENSING_CUIPM; "
-                             "PARTIAL_CONDENSING_HPIPM is accepted as an alias so that existing scripts switch over).")
+        if self.qp_solver in ("FULL_CONDENSING_CUIPM", "FULL_CONDENSING_HPIPM"):
+            # full condensing = one block: every state but the terminal one is eliminated (cond_N = 1; the reference's
+            # ocp_qp_full_condensing.c:450-645 -> d_cond_qp_cond also drops x_N and hands a dense_qp to dense_qp_hpipm; here the
+            # 2-stage QP [all inputs | x_N] goes through the same OCP interior-point kernel, so the QP and its solution are the
+            # same, the iterates -- and hence iteration counts -- are not those of the dense solver)
+            self.cond_N = 1
+        elif self.qp_solver not in ("PARTIAL_CONDENSING_CUIPM", "PARTIAL_CONDENSING_HPIPM"):
+            raise ValueError(f"qp_solver {self.qp_solver} is not served by this backend (PARTIAL_CONDENSING_CUIPM, FULL_CONDENSING_CUIPM; "
+                             "the *_HPIPM names are accepted as aliases so that existing scripts switch over).")
         if self.cond_N is not None and not 1 <= self.cond_N <= N:
             raise ValueError(f"cond_N must be in 1..N={N}")
         if self.hpipm_mode != "BALANCE":

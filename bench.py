@@ -35,9 +35,23 @@ METRIC = "OCP-QP solves/sec (fp64, batch) chain-mass N=40"
 UNIT = "QP/s"
 
 
+# BASELINE.json configs: (metric suffix, default batch per GPU, description).  c2 is the configuration the metric is quoted on and
+# the default; the others are the parity-test shapes, measurable with --config for the per-shape lines of DESIGN.md section 5b.
+CONFIGS = {
+    "c2": ("chain-mass N=40", 4096, "chain-of-masses OCP-QP nx=21 nu=3 N=40 (after x0 elimination), nbu=3 hard + 4 one-sided soft state bounds (ns=4)"),
+    "c1": ("mass-spring N=15", 16384, "mass_spring_example OCP-QP nx=8 nu=3 N=15 (after x0 elimination), input and state boxes"),
+    "c3": ("pendulum-sized N=20", 16384, "pendulum-on-cart sized OCP-QP nx=4 nu=1 N=20, input box"),
+    "c4": ("quadrotor-sized N=50", 8192, "quadrotor sized OCP-QP nx=12 nu=4 N=50 (uncondensed), input boxes + 6 soft state bounds"),
+    "c5": ("legged-sized N=30", 1024, "legged-robot sized OCP-QP nx=48 nu=12 N=30, input boxes + 12 soft state bounds"),
+}
+_CONFIG = "c2"
+
+
 def workload(batch: int, seed: int):
     from acados_b200 import problems
-    return problems.chain_mass(batch, n_mass=5, N=40, seed=seed)
+    if _CONFIG == "c2":
+        return problems.chain_mass(batch, n_mass=5, N=40, seed=seed)
+    return problems.named_config(_CONFIG, batch, seed=seed)
 
 
 def algorithmic_bytes_per_qp(b) -> dict:
@@ -144,12 +158,17 @@ def cpu_reference(batch_obj, opts, nqp: int, threads: int = 0):
 
 
 def main():
+    # the contract is ONE line on stdout: keep the real stdout aside and send everything else that writes to file descriptor 1
+    # (NCCL prints its version banner there when a communicator is created) to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuipm", choices=["cuipm", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="QPs per GPU")
+    ap.add_argument("--batch", type=int, default=0, help="QPs per GPU (default: the configuration's, 4096 for c2)")
     ap.add_argument("--warps", type=int, default=0, help="warps per QP (0 = solver default)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="QPs in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -158,7 +177,13 @@ def main():
     ap.add_argument("--no-scatter", action="store_true", help="N > 1: skip the scatter / solve / gather leg over NCCL")
     ap.add_argument("--no-plugin", action="store_true", help="skip the end-to-end leg through the plugin's batched entry")
     ap.add_argument("--no-tight", action="store_true", help="skip the second parity pass (all tolerances 1e-12)")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json configuration (default c2: the one the metric is quoted on)")
     args = ap.parse_args()
+    global _CONFIG, METRIC
+    _CONFIG = args.config
+    if args.batch <= 0:
+        args.batch = CONFIGS[_CONFIG][1]
+    METRIC = "OCP-QP solves/sec (fp64, batch) " + CONFIGS[_CONFIG][0]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -167,11 +192,10 @@ def main():
 
     from acados_b200.binding import INFO_DTYPE, default_opts, host_threads
     opts = default_opts()   # what PARTIAL_CONDENSING_HPIPM runs with out of the box
-    config = {"workload": f"chain-of-masses OCP-QP nx=21 nu=3 N=40 (after x0 elimination), nbu=3 hard + 4 one-sided soft "
-                          f"state bounds (ns=4), batch={args.batch} per GPU, every QP its own matrices",
+    config = {"workload": f"{CONFIGS[_CONFIG][2]}, batch={args.batch} per GPU, every QP its own matrices", "name": _CONFIG,
               "batch_per_gpu": args.batch, "global_batch": args.batch * max(world, 1), "parallelism": f"batch-sharded x{max(world,1)}",
               "solver_opts": "acados defaults: BALANCE mode, iter_max=50, tol 1e-6/1e-8/1e-8/1e-8, mu0=1, cold start",
-              "l2": "inputs (1.5 GB per batch) exceed the 126 MB L2; no explicit flush"}
+              "l2": "inputs (hundreds of MB to GB per batch) exceed the 126 MB L2; no explicit flush"}
 
     # ------------------------------------------------------------------------------------------------
     if args.impl == "reference":
@@ -193,7 +217,7 @@ def main():
                 "dtype": "f64", "data": "synthetic", "impl": "reference", "config": config,
                 "cpu_baseline": base, "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n"); real_stdout.flush()
         return 0
 
     # ------------------------------------------------------------------------------------------------
@@ -425,6 +449,8 @@ def main():
                 ncu = {}
         if traffic is None:
             traffic = ncu.get("dram_bytes_per_launch")
+        if _CONFIG != "c2" or nb != 4096:       # the committed ncu capture is of the headline configuration
+            traffic, ncu = None, {}
         # the path is bounded by the FP64 pipe or by HBM; frac = the larger of the two fractions.  HBM term on
         # ALGORITHMIC bytes (B_min: every record read once, the solution written once), FP64 term on algorithmic flops against
         # the DFMA rate measured on this GPU type (scripts/ubench_fp64.cu -> profiles/r02_ubench_fp64.txt).
@@ -493,7 +519,7 @@ def main():
                            "iter_max": int(info["iter"].max()), "lq_count": int(info["lq_count"].sum()),
                            "throughput_kernel": bool(args.fast and launches_per_step > 1), "launches_per_step": launches_per_step,
                            "handed_back_to_generic_kernel": handed_back}}
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n"); real_stdout.flush()
     solver.close()
     solver2.close()
     if world > 1:
