@@ -333,6 +333,62 @@ class CuipmCondenser:
             pass
 
 
+class CuipmXcond:
+    """The whole xcond chain on the device behind one object (``cuipm_xcond_*``, include/cuipm.h): records of the shape the
+    user poses in, solutions of that shape out; one pass, or the SQP-RTI split ``condense_lhs`` / ``condense_rhs_and_solve``."""
+
+    def __init__(self, full_shape: Shape, idxe0, cond_N: int, max_batch: int, device: int = 0):
+        self.lib = load_library()
+        lib = self.lib
+        lib.cuipm_xcond_create.restype = C.c_void_p
+        lib.cuipm_xcond_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        lib.cuipm_xcond_destroy.argtypes = [C.c_void_p]
+        lib.cuipm_xcond_solve_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.cuipm_xcond_condense_lhs_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        lib.cuipm_xcond_condense_rhs_and_solve_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.full_shape, self.layout = full_shape, Layout(full_shape)
+        self._cshape = full_shape.as_ctypes()
+        idx = (C.c_int * max(1, len(idxe0)))(*[int(i) for i in idxe0])
+        self.handle = lib.cuipm_xcond_create(C.byref(self._cshape), len(idxe0), idx, cond_N, max_batch, device)
+        if not self.handle:
+            raise RuntimeError("cuipm_xcond_create failed: " + lib.cuipm_last_error().decode())
+
+    def _run(self, fn, qp_full, opts, with_out=True):
+        qp_full = np.ascontiguousarray(qp_full, dtype=np.float64)
+        nb = qp_full.shape[0]
+        if not with_out:
+            rc = fn(self.handle, nb, qp_full.ctypes.data)
+            if rc != 0:
+                raise RuntimeError(self.lib.cuipm_last_error().decode())
+            return None
+        sol = np.zeros((nb, self.layout.sol_stride))
+        info = np.zeros(nb, dtype=INFO_DTYPE)
+        rc = fn(self.handle, nb, qp_full.ctypes.data, sol.ctypes.data, info.ctypes.data, C.byref(opts))
+        if rc != 0:
+            raise RuntimeError(self.lib.cuipm_last_error().decode())
+        return sol, info
+
+    def solve(self, qp_full, opts):
+        return self._run(self.lib.cuipm_xcond_solve_host, qp_full, opts)
+
+    def condense_lhs(self, qp_full):
+        return self._run(self.lib.cuipm_xcond_condense_lhs_host, qp_full, None, with_out=False)
+
+    def condense_rhs_and_solve(self, qp_full, opts):
+        return self._run(self.lib.cuipm_xcond_condense_rhs_and_solve_host, qp_full, opts)
+
+    def close(self):
+        if self.handle:
+            self.lib.cuipm_xcond_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class CuipmReducer:
     """Stage-0 equality elimination / restore on the device (``cuipm_reducer_*``, include/cuipm.h): maps QP records of
     the shape the user poses (x0 a stage-0 equality) to records of the reduced shape and solutions back."""

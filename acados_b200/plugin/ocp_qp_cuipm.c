@@ -454,6 +454,102 @@ int ocp_qp_cuipm_batch_solve(void *config_, int n, ocp_qp_in **qp_in, ocp_qp_out
     return worst;
 }
 
+/************************************************
+ * the xcond chain as a batched entry (device condensing behind the C plugin)
+ ************************************************/
+
+struct ocp_qp_cuipm_xcond_batch
+{
+    cuipm_xcond *x;
+    int n_max, N;
+    int *pool, **idxb_p, **rev_p;
+    double *b_qp, *b_sol;
+    cuipm_info *b_info;
+};
+
+void ocp_qp_cuipm_xcond_batch_destroy(ocp_qp_cuipm_xcond_batch *c)
+{
+    if (!c) return;
+    if (c->x) cuipm_xcond_destroy(c->x);
+    cuipm_host_free(c->b_qp); cuipm_host_free(c->b_sol); cuipm_host_free(c->b_info);
+    free(c->pool); free(c->idxb_p); free(c->rev_p);
+    free(c);
+}
+
+ocp_qp_cuipm_xcond_batch *ocp_qp_cuipm_xcond_batch_create(ocp_qp_in *in, int n_max, int cond_N, int device)
+{
+    const ocp_qp_dims *d = in->dim;
+    const int N = d->N;
+    if (d->nbue[0] > 0 || d->nge[0] > 0)
+    {
+        printf("\nerror: ocp_qp_cuipm_xcond_batch_create: only state-bound equalities at stage 0 are eliminated on the device\n");
+        return NULL;
+    }
+    ocp_qp_cuipm_xcond_batch *c = calloc(1, sizeof(*c));
+    c->n_max = n_max; c->N = N;
+    c->pool = calloc(idx_pool_len(d) + 1, sizeof(int));
+    c->idxb_p = calloc(N + 1, sizeof(int *));
+    c->rev_p = calloc(N + 1, sizeof(int *));
+    int o = 0;
+    for (int k = 0; k <= N; k++)
+    {
+        c->idxb_p[k] = c->pool + o;
+        for (int i = 0; i < d->nb[k]; i++) c->pool[o++] = in->idxb[k][i];
+        c->rev_p[k] = c->pool + o;
+        for (int i = 0; i < d->nb[k] + d->ng[k]; i++) c->pool[o++] = d->ns[k] > 0 ? in->idxs_rev[k][i] : -1;
+    }
+    cuipm_shape sh;
+    shape_from_dims(d, &sh);
+    sh.idxb = (const int *const *) c->idxb_p;
+    sh.idxs_rev = (const int *const *) c->rev_p;
+    /* equalities of stage 0: positions within [bu, bx, g] (d_ocp_qp.idxe, hpipm_d_ocp_qp.h:68) = positions in the bound list */
+    c->x = cuipm_xcond_create(&sh, d->nbxe[0], in->idxe[0], cond_N, n_max, device);
+    if (!c->x) { printf("\nerror: ocp_qp_cuipm_xcond_batch_create: %s\n", cuipm_last_error()); ocp_qp_cuipm_xcond_batch_destroy(c); return NULL; }
+    const cuipm_layout *l = cuipm_xcond_full_layout(c->x);
+    c->b_qp = cuipm_host_alloc(sizeof(double) * l->qp_stride * (size_t) n_max);
+    c->b_sol = cuipm_host_alloc(sizeof(double) * l->sol_stride * (size_t) n_max);
+    c->b_info = cuipm_host_alloc(sizeof(cuipm_info) * (size_t) n_max);
+    if (!c->b_qp || !c->b_sol || !c->b_info) { printf("\nerror: ocp_qp_cuipm_xcond_batch_create: %s\n", cuipm_last_error()); ocp_qp_cuipm_xcond_batch_destroy(c); return NULL; }
+    return c;
+}
+
+int ocp_qp_cuipm_xcond_batch_solve(ocp_qp_cuipm_xcond_batch *c, int n, ocp_qp_in **qp_in, ocp_qp_out **qp_out, void *opts_, int phase,
+                                   int *status_out)
+{
+    ocp_qp_cuipm_opts *opts = opts_;
+    if (!c || n < 0 || n > c->n_max) { printf("\nerror: ocp_qp_cuipm_xcond_batch_solve: bad arguments\n"); exit(1); }
+    if (n == 0) return ACADOS_SUCCESS;
+    acados_timer timer;
+    acados_tic(&timer);
+    const cuipm_layout *l = cuipm_xcond_full_layout(c->x);
+    const int nthr = pack_threads();
+#pragma omp parallel for schedule(static) num_threads(nthr)
+    for (int i = 0; i < n; i++) pack_qp(qp_in[i], l, c->b_qp + l->qp_stride * (size_t) i);
+    int rc;
+    if (phase == 1) rc = cuipm_xcond_condense_lhs_host(c->x, n, c->b_qp);
+    else if (phase == 2) rc = cuipm_xcond_condense_rhs_and_solve_host(c->x, n, c->b_qp, c->b_sol, c->b_info, &opts->c);
+    else rc = cuipm_xcond_solve_host(c->x, n, c->b_qp, c->b_sol, c->b_info, &opts->c);
+    if (rc != CUIPM_OK) { printf("\nerror: ocp_qp_cuipm_xcond_batch_solve: %s\n", cuipm_last_error()); exit(1); }
+    if (phase == 1) return ACADOS_SUCCESS;
+    const double t_solve = acados_toc(&timer);
+#pragma omp parallel for schedule(static) num_threads(nthr)
+    for (int i = 0; i < n; i++)
+    {
+        unpack_sol(c->b_sol + l->sol_stride * (size_t) i, qp_in[i]->dim, l, qp_out[i]);
+        qp_info *info = qp_out[i]->misc;
+        info->solve_QP_time = t_solve / n; info->interface_time = 0; info->total_time = t_solve / n;
+        info->num_iter = c->b_info[i].iter; info->t_computed = 1;
+        if (status_out) status_out[i] = acados_status(c->b_info[i].status);
+    }
+    int worst = ACADOS_SUCCESS;
+    for (int i = 0; i < n; i++)
+    {
+        int st = acados_status(c->b_info[i].status);
+        if (st != ACADOS_SUCCESS && worst == ACADOS_SUCCESS) worst = st;
+    }
+    return worst;
+}
+
 void ocp_qp_cuipm_memory_reset(void *config_, void *qp_in_, void *qp_out_, void *opts_, void *mem_, void *work_)
 {
     ocp_qp_cuipm_memory *mem = mem_;

@@ -73,6 +73,19 @@ void ocp_qp_cuipm_config_initialize_default(void *config);
  * at the QP level.  Returns the worst acados status. */
 int ocp_qp_cuipm_batch_solve(void *config, int n, ocp_qp_in **qp_in, ocp_qp_out **qp_out, void *opts_, void *mem_, int *status_out);
 
+/* The xcond chain as a batched entry: n structurally identical UNCONDENSED QPs as ocp_qp_xcond_solver holds them (x0 as stage-0
+ * equality bounds, dims->nbxe[0] / qp_in->idxe[0]) in, solutions of the same shape out; the stage-0 elimination, the block
+ * condensing to cond_N stages (1..N; <= 0: N), the interior-point solve, the expansion and the restore all run on the device
+ * (cuipm_xcond_*, include/cuipm.h) -- the batched counterpart of ocp_qp_xcond_solver's evaluate (ocp_qp_xcond_solver.c:523-589)
+ * with acados' CPU condensing module taken out of the path.  phase: 0 = one pass; 1 = condense_lhs only (:591-627, nothing is
+ * written to qp_out); 2 = condense_rhs_and_solve (:629-669) on QPs whose matrices are those of the last phase-1 call.
+ * The context owns the device objects and the page-locked staging. */
+typedef struct ocp_qp_cuipm_xcond_batch ocp_qp_cuipm_xcond_batch;
+ocp_qp_cuipm_xcond_batch *ocp_qp_cuipm_xcond_batch_create(ocp_qp_in *qp_in0, int n_max, int cond_N, int device);
+int ocp_qp_cuipm_xcond_batch_solve(ocp_qp_cuipm_xcond_batch *ctx, int n, ocp_qp_in **qp_in, ocp_qp_out **qp_out, void *opts_, int phase,
+                                   int *status_out);
+void ocp_qp_cuipm_xcond_batch_destroy(ocp_qp_cuipm_xcond_batch *ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -283,6 +283,63 @@ int main(void)
         fails += !(rc == 0 && worst <= 1e-10);
         cfg_g.terminate(&cfg_g, mg, NULL);
     }
+    {
+        /* the xcond chain as a batched entry: uncondensed QPs with x0 as stage-0 equality bounds (as ocp_qp_xcond_solver holds
+         * them), elimination + block condensing + solve + expansion + restore on the device, against the reference chain
+         * (PARTIAL_CONDENSING_HPIPM behind ocp_qp_xcond_solver with acados' CPU condensing) instance by instance; then the
+         * SQP-RTI split: condense_lhs on the batch, new x0 (vectors only), condense_rhs_and_solve */
+        enum { NBX = 5 };
+        int conds[2] = {NN, 5};
+        for (int t = 0; t < 2; t++)
+        {
+            chain h = make_chain(0, conds[t]);
+            ocp_qp_in *ins[NBX], *ins2[NBX];
+            ocp_qp_out *outs[NBX], *ref[NBX], *ref2[NBX];
+            int status[NBX];
+            for (int i = 0; i < NBX; i++)
+            {
+                double xa[NX], xb[NX];
+                for (int j = 0; j < NX; j++) { xa[j] = x0[j] + 0.3 * sin(1.0 + i + 2.0 * j); xb[j] = xa[j] + 0.1 * cos(3.0 + i + j); }
+                ins[i] = make_qp(&h, xa); ins2[i] = make_qp(&h, xb);
+                outs[i] = ocp_qp_out_create(h.dims->orig_dims); ref[i] = ocp_qp_out_create(h.dims->orig_dims); ref2[i] = ocp_qp_out_create(h.dims->orig_dims);
+                fails += ocp_qp_solve(h.solver, ins[i], ref[i]) != 0;
+                fails += ocp_qp_solve(h.solver, ins2[i], ref2[i]) != 0;
+            }
+            qp_solver_config cfg_g;
+            ocp_qp_cuipm_config_initialize_default(&cfg_g);
+            ocp_qp_dims *od = h.dims->orig_dims;
+            void *og = cfg_g.opts_assign(&cfg_g, od, calloc(1, cfg_g.opts_calculate_size(&cfg_g, od)));
+            cfg_g.opts_initialize_default(&cfg_g, od, og);
+            ocp_qp_cuipm_xcond_batch *ctx = ocp_qp_cuipm_xcond_batch_create(ins[0], NBX, conds[t], 0);
+            if (!ctx) { printf("xcond batch entry: create failed FAIL\n"); fails++; continue; }
+            int rc = ocp_qp_cuipm_xcond_batch_solve(ctx, NBX, ins, outs, og, 0, status);
+            double worst = 0.0, wall = 0.0;
+            for (int i = 0; i < NBX; i++)
+            {
+                double du, dall = diff_out(od, ref[i], outs[i], &du);
+                worst = fmax(worst, du); wall = fmax(wall, dall);
+                fails += status[i] != 0;
+            }
+            int ok = rc == 0 && worst <= 1e-10 && wall <= 1e-6;
+            printf("xcond batch entry N2=%2d: %d QPs, rc %d, max |du| %.2e |dsol| %.2e vs the reference chain %s\n", conds[t], NBX, rc, worst, wall, ok ? "OK" : "FAIL");
+            fails += !ok;
+            /* RTI split */
+            rc = ocp_qp_cuipm_xcond_batch_solve(ctx, NBX, ins, outs, og, 1, status);
+            rc |= ocp_qp_cuipm_xcond_batch_solve(ctx, NBX, ins2, outs, og, 2, status);
+            worst = 0.0; wall = 0.0;
+            for (int i = 0; i < NBX; i++)
+            {
+                double du, dall = diff_out(od, ref2[i], outs[i], &du);
+                worst = fmax(worst, du); wall = fmax(wall, dall);
+                fails += status[i] != 0;
+            }
+            ok = rc == 0 && worst <= 1e-10 && wall <= 1e-6;
+            printf("xcond batch entry N2=%2d, condense_lhs then condense_rhs_and_solve with new x0: max |du| %.2e |dsol| %.2e %s\n", conds[t], worst, wall, ok ? "OK" : "FAIL");
+            fails += !ok;
+            ocp_qp_cuipm_xcond_batch_destroy(ctx);
+            h.config->terminate(h.config, h.solver->mem, h.solver->work);
+        }
+    }
     printf(fails ? "PLUGIN TEST FAILED (%d)\n" : "PLUGIN TEST PASSED\n", fails);
     return fails != 0;
 }

@@ -261,6 +261,24 @@ int cuipm_expand_device(cuipm_condenser *c, int nbatch, const double *d_qp, cons
 int cuipm_condense_lhs_device(cuipm_condenser *c, int nbatch, const double *d_qp, double *d_qp_cond, void *stream);
 int cuipm_condense_rhs_device(cuipm_condenser *c, int nbatch, const double *d_qp, double *d_qp_cond, void *stream);
 
+/* ---- the whole xcond chain behind one object -------------------------------------------------------------------------
+ * Reference: ocp_qp_xcond_solver (acados/ocp_qp/ocp_qp_xcond_solver.c:523-669): condensing module + QP solver + expansion,
+ * evaluate() in one piece or split into condense_lhs (:591-627, preparation phase of SQP-RTI) and condense_rhs_and_solve
+ * (:629-669, feedback phase).  `full` is the shape as the user poses it, idxe0 as for cuipm_reducer_create; cond_N in 1..N
+ * (<= 0 or N: no block condensing).  Records of the full shape come from (page-locked) host memory, solutions of the full
+ * shape and the per-QP summaries go back; the reduced / condensed records, the prediction matrices of the lhs pass and all
+ * intermediate solutions live on the device.  warm_start >= 2 is refused (the chain does not map a full-shape iterate forward). */
+typedef struct cuipm_xcond cuipm_xcond;
+cuipm_xcond *cuipm_xcond_create(const cuipm_shape *full, int nbxe0, const int *idxe0, int cond_N, int max_batch, int device);
+void cuipm_xcond_destroy(cuipm_xcond *x);
+const cuipm_layout *cuipm_xcond_full_layout(const cuipm_xcond *x);
+int cuipm_xcond_cond_N(const cuipm_xcond *x);
+cuipm_solver *cuipm_xcond_solver(cuipm_xcond *x);      /* the solver of the reduced / condensed shape (statistics, getters); owned by x */
+int cuipm_xcond_solve_host(cuipm_xcond *x, int nbatch, const double *qp_full, double *sol_full, cuipm_info *info, const cuipm_opts *opts);
+int cuipm_xcond_condense_lhs_host(cuipm_xcond *x, int nbatch, const double *qp_full);
+int cuipm_xcond_condense_rhs_and_solve_host(cuipm_xcond *x, int nbatch, const double *qp_full, double *sol_full, cuipm_info *info,
+                                            const cuipm_opts *opts);
+
 /* Riccati quantities of the last factorisation (reference: ocp_qp_hpipm_solver_get, ocp_qp_hpipm.c:417-478).
  * field in {"P","p","K","k","Lr"}; copies column-major data of QP `iqp`, stage `stage` into `value`. */
 int cuipm_get_ric(cuipm_solver *s, int iqp, const char *field, int stage, double *value, int size1, int size2);
