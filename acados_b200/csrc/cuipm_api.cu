@@ -96,7 +96,9 @@ static int launch_batch(cuipm_solver *s, const LaunchArgs &a0, int slot, size_t 
     a.redo_list = nullptr;
     a.redo_count = nullptr;
     const cuipm_opts &o = a.o;
-    if (s->fast_ok && s->use_fast && o.lq_fact <= 1 && !(((size_t) a.sol | (size_t) a.work) & 15))
+    // (m != 0 -- acados' tau_min option -- changes the ratio test into the quadratic rule: generic kernel only, the hot code of
+    // the throughput kernel stays as it is)
+    if (s->fast_ok && s->use_fast && o.lq_fact <= 1 && o.m_relax == 0.0 && !(((size_t) a.sol | (size_t) a.work) & 15))
     {
         FastArgs F = s->F;
         F.nbatch = a.nbatch; F.ipool = a.ipool; F.qp = a.qp; F.sol = a.sol; F.work = a.work; F.info = a.info; F.stat = a.stat;

@@ -151,7 +151,7 @@ int cuipm::opts_check(const cuipm_opts *o)
     // m != 0 changes more than the complementarity residual: COMPUTE_MU_AFF_QP subtracts m and COMPUTE_ALPHA_QP switches to a
     // SEQUENTIAL ratio test with a quadratic root per violated constraint (x_core_qp_ipm_aux.c:397-436), which the fused,
     // parallel ratio test of the kernels does not reproduce
-    if (o->m_relax != 0.0) { set_error("tau_min/m relaxation (m != 0) is not supported"); return CUIPM_ERR_INVALID; }
+    if (o->m_relax < 0.0) { set_error("tau_min / m relaxation must be >= 0"); return CUIPM_ERR_INVALID; }
     if (o->itref_pred_max != 0) { set_error("itref_pred_max must be 0"); return CUIPM_ERR_INVALID; }
     // stat_max may be smaller than iter_max: the kernels write row kk+1 of the statistics table only while kk+1 < stat_max
     if (o->iter_max < 0 || o->stat_max < 0) { set_error("need iter_max >= 0 and stat_max >= 0"); return CUIPM_ERR_INVALID; }

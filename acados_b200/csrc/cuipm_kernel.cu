@@ -1436,8 +1436,13 @@ struct Ker
                     dlm[i] = CX.mask_constr ? dl * mk : dl;     // masked step multipliers (tmp_lam_mask of the linear residual)
                     if (dst == 1)
                     {   // ratio test on the main step (min over constraints, see COMPUTE_ALPHA_QP)
-                        if (l + dl < 0.0) alpha = fmin(alpha, -l / dl);
-                        if (tt + dti < 0.0) alpha = fmin(alpha, -tt / dti);
+                        if (CX.o.m_relax == 0.0)
+                        {
+                            if (l + dl < 0.0) alpha = fmin(alpha, -l / dl);
+                            if (tt + dti < 0.0) alpha = fmin(alpha, -tt / dti);
+                        }
+                        else
+                            alpha = fmin(alpha, crit_step_m(l, tt, dl, dti, m_safe() * CX.o.m_relax * mk));
                     }
                     if (do_lin)
                     {
@@ -1526,6 +1531,30 @@ struct Ker
         return rmin(alpha);
     }
 
+    // m != 0 (acados' tau_min option): largest step of one constraint that keeps lam, t >= 0 and lam*t >= m1 = m_safe*m, by
+    // COMPUTE_ALPHA_QP's rule (x_core_qp_ipm_aux.c:398-440; evaluated from alpha = 1 per constraint, the minimum over the
+    // constraints equals the reference's sequential pass because each test is monotone in the step length)
+    __device__ __forceinline__ double m_safe() const { return (CX.o.mode == CUIPM_SPEED_ABS || CX.o.mode == CUIPM_SPEED) ? 0.3 : 0.5; }
+    __device__ __noinline__ double crit_step_m(double l, double t, double dl, double dt, double m1) const
+    {
+        double a = 1.0, l1 = l + dl, t1 = t + dt;
+        if (l1 < 0.0) { a = -l / dl; l1 = l + a * dl; }
+        if (t1 < 0.0) { a = -t / dt; t1 = t + a * dt; }
+        if (l1 * t1 - m1 < -1e-12)
+        {
+            const double c = l * t - m1;
+            if (c > 0.0)
+            {
+                const double aa = dl * dt, b = dl * t + l * dt;
+                const double d = b * b - 4.0 * aa * c, sd = sqrt(d), tmp = 0.5 / aa;
+                a = (-b - sd) * tmp;
+            }
+            else
+                a = 0.0;
+        }
+        return a;
+    }
+
     // step length of the main step from global memory (after iterative refinement changed it)
     __device__ __noinline__ double alpha_pass()
     {
@@ -1536,8 +1565,13 @@ struct Ker
             const double *l = CX.sol + s.sol.lam, *t = CX.sol + s.sol.t, *dl = CX.wk + s.step.lam, *dt = CX.wk + s.step.t;
             for (int i = tid; i < s.nc; i += NT)
             {
-                if (l[i] + dl[i] < 0.0) alpha = fmin(alpha, -l[i] / dl[i]);
-                if (t[i] + dt[i] < 0.0) alpha = fmin(alpha, -t[i] / dt[i]);
+                if (CX.o.m_relax == 0.0)
+                {
+                    if (l[i] + dl[i] < 0.0) alpha = fmin(alpha, -l[i] / dl[i]);
+                    if (t[i] + dt[i] < 0.0) alpha = fmin(alpha, -t[i] / dt[i]);
+                }
+                else
+                    alpha = fmin(alpha, crit_step_m(l[i], t[i], dl[i], dt[i], m_safe() * CX.o.m_relax * __ldg(CX.qp + s.q_dmask + i)));
             }
         }
         return rmin(alpha);
@@ -1551,7 +1585,11 @@ struct Ker
         {
             const StageDesc s = CX.SD[k];
             const double *l = CX.sol + s.sol.lam, *t = CX.sol + s.sol.t, *dl = CX.wk + s.step.lam, *dt = CX.wk + s.step.t;
-            for (int i = tid; i < s.nc; i += NT) acc += fabs((l[i] + alpha * dl[i]) * (t[i] + alpha * dt[i]));
+            if (CX.o.m_relax == 0.0)
+                for (int i = tid; i < s.nc; i += NT) acc += fabs((l[i] + alpha * dl[i]) * (t[i] + alpha * dt[i]));
+            else        // m != 0 (tau_min option): |(lam + alpha dlam)(t + alpha dt) - m|, m = qp->m * d_mask
+                for (int i = tid; i < s.nc; i += NT)
+                    acc += fabs(-CX.o.m_relax * __ldg(CX.qp + s.q_dmask + i) + (l[i] + alpha * dl[i]) * (t[i] + alpha * dt[i]));
         }
         return rsum(acc) * CX.nc_mask_inv;
     }

@@ -113,6 +113,7 @@ typedef struct
     double *tmp0, *tmp1, *tmp2, *tmp3, *tmpx, *tmpl; /* nb+ng / nx scratch */
     int mask_constr;
     double m_relax;     /* entries of qp->m (all equal) */
+    double m_safe;      /* share of m the ratio test keeps lam*t above (x_ocp_qp_ipm.c:104-209: 0.3 SPEED modes, 0.5 BALANCE / ROBUST) */
     double nc_mask_inv;
     char *arena;
 } work;
@@ -931,17 +932,38 @@ static void solve_kkt_step(work *w, const rset *rhs, vset *step, int use_Pb, int
 /* IPM vector kernels (x_core_qp_ipm_aux.c)                                                         */
 /* ------------------------------------------------------------------------------------------------ */
 
-/* COMPUTE_ALPHA_QP, single step, m == 0 (:375-398) */
+/* COMPUTE_ALPHA_QP, single step: m == 0 (:375-398) and m != 0 (:398-440: the step is also limited by lam*t >= m_safe*m, the
+ * smaller root of the quadratic; every test uses the step length the tests before it left) */
 static double compute_alpha(const work *w, const vset *step)
 {
     double alpha = 1.0;
     for (int k = 0; k <= w->N; k++)
     {
-        const double *lam = w->sol.lam[k], *t = w->sol.t[k], *dlam = step->lam[k], *dt = step->t[k];
+        const double *lam = w->sol.lam[k], *t = w->sol.t[k], *dlam = step->lam[k], *dt = step->t[k], *mask = w->dmask[k];
         for (int i = 0; i < w->nc[k]; i++)
         {
-            if (lam[i] + alpha * dlam[i] < 0.0) alpha = -lam[i] / dlam[i];
-            if (t[i] + alpha * dt[i] < 0.0) alpha = -t[i] / dt[i];
+            if (w->m_relax == 0.0)
+            {
+                if (lam[i] + alpha * dlam[i] < 0.0) alpha = -lam[i] / dlam[i];
+                if (t[i] + alpha * dt[i] < 0.0) alpha = -t[i] / dt[i];
+                continue;
+            }
+            double lam1 = lam[i] + alpha * dlam[i], t1 = t[i] + alpha * dt[i];
+            if (lam1 < 0.0) { alpha = -lam[i] / dlam[i]; lam1 = lam[i] + alpha * dlam[i]; }
+            if (t1 < 0.0) { alpha = -t[i] / dt[i]; t1 = t[i] + alpha * dt[i]; }
+            const double m1 = w->m_safe * w->m_relax * mask[i];         /* cws->m = qp->m * d_mask (x_ocp_qp_ipm.c:2722) */
+            if (lam1 * t1 - m1 < -1e-12)
+            {
+                const double c = lam[i] * t[i] - m1;
+                if (c > 0.0)
+                {
+                    const double a = dlam[i] * dt[i], b = dlam[i] * t[i] + lam[i] * dt[i];
+                    const double d = b * b - 4.0 * a * c, sd = sqrt(d), tmp = 0.5 / a;
+                    alpha = (-b - sd) * tmp;
+                }
+                else
+                    alpha = 0.0;
+            }
         }
     }
     return alpha;
@@ -954,7 +976,11 @@ static double compute_mu_aff(const work *w, const vset *step, double alpha)
     for (int k = 0; k <= w->N; k++)
     {
         const double *lam = w->sol.lam[k], *t = w->sol.t[k], *dlam = step->lam[k], *dt = step->t[k];
-        for (int i = 0; i < w->nc[k]; i++) mu += fabs((lam[i] + alpha * dlam[i]) * (t[i] + alpha * dt[i]));
+        /* (:636-668: |(lam + alpha dlam)(t + alpha dt) - m|, m = qp->m * d_mask) */
+        if (w->m_relax == 0.0)
+            for (int i = 0; i < w->nc[k]; i++) mu += fabs((lam[i] + alpha * dlam[i]) * (t[i] + alpha * dt[i]));
+        else
+            for (int i = 0; i < w->nc[k]; i++) mu += fabs(-w->m_relax * w->dmask[k][i] + (lam[i] + alpha * dlam[i]) * (t[i] + alpha * dt[i]));
     }
     return mu * w->nc_mask_inv;
 }
@@ -1100,6 +1126,7 @@ static int itref_ok(const double nrm[4], const double resmax[4], const cuipm_opt
 static void solve_one(work *w, const cuipm_opts *o, cuipm_info *info, double *stat)
 {
     w->m_relax = o->m_relax;
+    w->m_safe = (o->mode == CUIPM_SPEED_ABS || o->mode == CUIPM_SPEED) ? 0.3 : 0.5;
     int N = w->N;
     const int SM = CUIPM_STAT_M;
     double res_max[4] = {0, 0, 0, 0}, mu = 0, obj = 0, gap = 0;
@@ -1293,7 +1320,7 @@ fill:
 static int opts_supported(const cuipm_opts *o)
 {
     return o->abs_form == 0 && o->split_step == 0 && o->comp_dual_sol_eq == 1 && o->comp_res_exit == 1
-           && o->var_init_scheme == 1 && o->m_relax == 0.0 && o->itref_pred_max == 0;
+           && o->var_init_scheme == 1 && o->itref_pred_max == 0;
 }
 
 int oracle_solve(const cuipm_shape *shape, int nbatch, const double *qp, double *sol, cuipm_info *info, double *stat,

@@ -65,6 +65,28 @@ def test_oracle_matches_reference(built, name, lq):
     _compare_with_reference(CASES[name](), default_opts(lq_fact=lq), allow_lq_shift=(lq == 1))
 
 
+@pytest.mark.parametrize("name", ["c1_mass_spring", "c2_chain_mass", "rand_soft", "rand_masked"])
+@pytest.mark.parametrize("tau", [1e-4, 1e-2])
+def test_oracle_matches_reference_with_tau_min(built, name, tau):
+    """acados' ``tau_min`` option (ocp_qp_hpipm.c:170-174, 338-342): every entry of qp->m is set to it, the complementarity
+    residual becomes lam*t - m and the ratio test switches to the quadratic rule that keeps lam*t >= m_safe*m
+    (x_core_qp_ipm_aux.c:398-440).  Same iteration counts, same solution."""
+    from oracle import oracle_binding as ob
+    if not ob.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    b = CASES[name]()
+    o = default_opts(m_relax=tau)
+    s1, i1 = ob.oracle_solve(b, o)
+    s2, i2, _ = ob.ref_solve(b, o, nthreads=1)
+    assert np.array_equal(i1["iter"], i2["iter"]), (i1["iter"], i2["iter"])
+    assert np.array_equal(i1["status"], i2["status"])
+    conv = i2["status"] == 0
+    assert np.max(np.abs(b.layout.u_traj(s1) - b.layout.u_traj(s2))[conv], initial=0.0) <= TOL_U
+    # and the option does something: the relaxed problem stops at another point than the unrelaxed one
+    s0, _ = ob.oracle_solve(b, default_opts())
+    assert np.max(np.abs(s1 - s0)) > 1e-8
+
+
 LQ_CASES = {
     "infeasible_box": lambda: P.random_qp(P.random_shape(8, 5, 2, nbx=3), 16, seed=18, umax=0.3, xmax=0.4, x0_scale=2.0),
     "infeasible_general": lambda: P.random_qp(P.random_shape(10, 6, 2, nbx=3, ng=2), 16, seed=28, umax=0.2, xmax=0.3, x0_scale=3.0),

@@ -31,6 +31,13 @@ def _tol_default(name):
     return TOL_U if name.startswith(("c1", "c2", "unconstrained")) else 1e-9
 
 
+def _tol_default_at_size(name):
+    """The same at the configurations' full batch sizes, where 64 instances are compared instead of a handful: the tail of the
+    synthetic families reaches 1.1e-9 (c4, 8192) at the default tolerances; test_other_configs_at_size then drives the same
+    instances to 1e-12 residuals and holds them to 1e-10."""
+    return TOL_U if name.startswith(("c1", "c2")) else 5e-9
+
+
 @pytest.mark.parametrize("name", list(CASES))
 @pytest.mark.parametrize("warps", [1, 2, 4])
 def test_cuda_matches_oracle(built, name, warps):
@@ -149,6 +156,20 @@ def test_warm_start_parity(built, ws):
     assert np.max(np.abs(b.layout.u_traj(sol) - b.layout.u_traj(osol))) <= (1e-9 if ws == 2 else 1e-7)
 
 
+@pytest.mark.parametrize("name", ["c1_mass_spring", "c2_chain_mass", "rand_soft"])
+def test_tau_min_parity(built, name):
+    """acados' ``tau_min`` option (m != 0: relaxed complementarity target and the quadratic ratio test): CUDA path (generic kernel:
+    the throughput kernel is bypassed for this option) against the oracle, which test_oracle_vs_reference pins to the reference."""
+    from oracle import oracle_binding as ob
+    b = CASES[name]()
+    o = default_opts(m_relax=1e-3)
+    sol, info = _solve(b, o)
+    osol, oinfo = ob.oracle_solve(b, o)
+    assert np.array_equal(info["status"], oinfo["status"]) and np.array_equal(info["iter"], oinfo["iter"]), (info["iter"], oinfo["iter"])
+    conv = oinfo["status"] == 0
+    assert np.max(np.abs(b.layout.u_traj(sol) - b.layout.u_traj(osol))[conv], initial=0.0) <= _tol_default(name)
+
+
 def test_tight_tolerance_parity(built):
     """Both solvers driven to 1e-12 residuals: solutions agree far below the 1e-10 bar (iteration count may flip by one)."""
     from oracle import oracle_binding as ob
@@ -233,7 +254,14 @@ def test_other_configs_at_size(built, name, nb):
     sub = P.Batch(b.shape, b.layout, np.ascontiguousarray(b.qp[idx]))
     osol, oinfo = ob.oracle_solve(sub, o, nthreads=min(16, nt))
     assert np.array_equal(info["iter"][idx], oinfo["iter"])
-    assert np.max(np.abs(b.layout.u_traj(sol[idx]) - b.layout.u_traj(osol))) <= _tol_default(name)
+    assert np.max(np.abs(b.layout.u_traj(sol[idx]) - b.layout.u_traj(osol))) <= _tol_default_at_size(name)
+    # the north_star's bar on the same instances with both solvers driven to 1e-12 residuals
+    ot = default_opts(res_g_max=1e-12, res_b_max=1e-12, res_d_max=1e-12, res_m_max=1e-12)
+    tsol, tinfo = _solve(sub, ot)
+    tosol, toinfo = ob.oracle_solve(sub, ot, nthreads=min(16, nt))
+    conv = (tinfo["status"] == 0) & (toinfo["status"] == 0)
+    assert conv.mean() > 0.9 and np.max(np.abs(tinfo["iter"] - toinfo["iter"])[conv]) <= 1
+    assert np.max(np.abs(b.layout.u_traj(tsol) - b.layout.u_traj(tosol))[conv]) <= TOL_U
 
 
 def test_edge_cases(built):
