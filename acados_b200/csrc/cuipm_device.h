@@ -102,6 +102,11 @@ struct FastArgs
     int *redo_list;                // QPs that need a cold path (LQ refactorisation, iterative refinement, no active constraint):
     int *redo_count;               //   handed to the generic kernel, which solves them from scratch
     int *next_qp;                  // work counter of the persistent warps (zero at launch)
+    // iteration-sliced scheduling (cuipm_fast_core.h, rr_first / rr_loop): scalar state of every QP between iterations, the ring of
+    // QPs that go on (nbatch slots, -1 = empty) and its counters {head, tail, stopped, -}
+    double *rr_state;
+    int *rr_ring;
+    int *rr_ctr;
     cuipm_opts o;
 };
 
@@ -114,8 +119,12 @@ int launch_solve(const LaunchArgs &a, int warps, void *stream);
 bool fast_available(int nx, int nu, FastArgs &F, int *qp_per_warp);
 // caller's QP records -> kernel-side records (F.qpk) for F.nbatch QPs on `stream`; sd = device stage table; returns cudaError_t as int
 int launch_repack(const FastArgs &F, const StageDesc *sd, void *stream);
-// launches the throughput kernel for F on `stream`; returns cudaError_t as int
-int launch_fast(const FastArgs &F, void *stream);
+// launches the throughput kernel for F on `stream`; returns cudaError_t as int.  mode 0: a QP stays with its warp; 1 then 2: the two
+// launches of the iteration-sliced scheduling (fast_rr_available says whether the instance has them)
+int launch_fast(const FastArgs &F, void *stream, int mode);
+bool fast_rr_available(int nx, int nu);
+// QPs the device holds at once with the throughput kernel of F's shape (0 if unknown)
+int fast_resident_qps(const FastArgs &F);
 // launches the sensitivity kernel (one substitution with the factorisation the last solve left in the work records)
 int launch_sens(const LaunchArgs &a, int warps, void *stream);
 // dynamic shared memory (bytes) the kernel needs for P

@@ -91,6 +91,12 @@ static __device__ __forceinline__ void fk_dmma(double &c0, double &c1, double a,
 }
 static __device__ __forceinline__ double fk_rsqrt(double x) { return rsqrt(x); }
 static __device__ __forceinline__ int fk_atomic_inc(int *p) { return atomicAdd(p, 1); }
+static __device__ __forceinline__ int fk_atomic_add(int *p, int v) { return atomicAdd(p, v); }
+static __device__ __forceinline__ int fk_atomic_cas(int *p, int cmp, int v) { return atomicCAS(p, cmp, v); }
+static __device__ __forceinline__ int fk_ld_volatile(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+static __device__ __forceinline__ void fk_st_volatile(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
+static __device__ __forceinline__ void fk_threadfence() { __threadfence(); }
+static __device__ __forceinline__ void fk_nanosleep(unsigned ns) { __nanosleep(ns); }
 
 #ifdef FK_PROFILE
 // development: cycles per sweep and per kind of wait, accumulated by lane 0 of every warp into cuipm_fast_prof[16]
@@ -112,7 +118,9 @@ namespace {
 
 extern __shared__ __align__(16) double g_fsmem[];
 
-template <int NX, int NU, int G, int MINB>
+// MODE 0: a QP stays with its warp for the whole solve; 1 / 2: iteration-sliced scheduling, first launch (initial points, ring
+// filled) / loop over the ring (cuipm_fast_core.h, rr_first / rr_loop)
+template <int NX, int NU, int G, int MINB, int MODE>
 __global__ void __launch_bounds__(32, MINB) cuipm_fast_kernel(const __grid_constant__ FastArgs A)
 {
     using K = fastk::Ker<NX, NU, G>;
@@ -124,14 +132,18 @@ __global__ void __launch_bounds__(32, MINB) cuipm_fast_kernel(const __grid_const
     K k(A, g_fsmem, bars);
     // persistent warps: each one fetches the next 32/G QPs of the batch until none is left (QPs need 6..18 iterations, and
     // a launch is a few waves of resident warps: a fixed assignment leaves SMs idle at the end of every wave)
-    for (;;)
-    {
-        int first = 0;
-        if (fk_lane() == 0) first = atomicAdd(A.next_qp, K::QPW);
-        first = __shfl_sync(0xffffffffu, first, 0);
-        if (first >= A.nbatch) break;
-        k.run(first);
-    }
+    if (MODE == 2)
+        k.rr_loop();
+    else
+        for (;;)
+        {
+            int first = 0;
+            if (fk_lane() == 0) first = atomicAdd(A.next_qp, K::QPW);
+            first = __shfl_sync(0xffffffffu, first, 0);
+            if (first >= A.nbatch) break;
+            if (MODE == 1) k.rr_first(first);
+            else k.run(first);
+        }
 #ifdef FK_PROFILE
     if (fk_lane() == 0)
     {
@@ -186,22 +198,22 @@ void sizes(FastArgs &F, int *qpw)
     *qpw = K::QPW;
 }
 
-template <int NX, int NU, int G, int MINB>
+template <int NX, int NU, int G, int MINB, int MODE>
 cudaError_t launch_one(const FastArgs &F, cudaStream_t stream)
 {
     using K = fastk::Ker<NX, NU, G>;
     const size_t smem = sizeof(double) * ((size_t) F.gstride * K::QPW + 2 * (size_t) F.nmaps * F.nbe);
     if (((size_t) F.qpk | (size_t) F.sol | (size_t) F.work) & 15) return cudaErrorMisalignedAddress;      // bulk copies need 16-byte aligned records
-    cudaError_t err = cudaFuncSetAttribute(cuipm_fast_kernel<NX, NU, G, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaError_t err = cudaFuncSetAttribute(cuipm_fast_kernel<NX, NU, G, MINB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (err != cudaSuccess) return err;
     // the CTAs of one SM together need most of its shared memory: ask for the largest carve-out (the default heuristic
     // sized it for a single CTA, which left one warp per SM resident)
-    err = cudaFuncSetAttribute(cuipm_fast_kernel<NX, NU, G, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    err = cudaFuncSetAttribute(cuipm_fast_kernel<NX, NU, G, MINB, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (err != cudaSuccess) return err;
     if (getenv("CUIPM_DEBUG"))
     {
         int nblk = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, cuipm_fast_kernel<NX, NU, G, MINB>, 32, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, cuipm_fast_kernel<NX, NU, G, MINB, MODE>, 32, smem);
         fprintf(stderr, "cuipm_fast_kernel<%d,%d,%d>: %zu bytes of shared memory per CTA, %d CTAs (%d QPs) per SM\n", NX, NU, G, smem, nblk, nblk * K::QPW);
     }
     static int resident = 0;        // CTAs per SM x SMs of this instance
@@ -210,12 +222,12 @@ cudaError_t launch_one(const FastArgs &F, cudaStream_t stream)
         int nblk = 0, dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, cuipm_fast_kernel<NX, NU, G, MINB>, 32, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, cuipm_fast_kernel<NX, NU, G, MINB, MODE>, 32, smem);
         resident = (nblk > 0 ? nblk : 1) * (sms > 0 ? sms : 1);
     }
     const int want = (F.nbatch + K::QPW - 1) / K::QPW;
-    const int grid = want < resident ? want : resident;
-    cuipm_fast_kernel<NX, NU, G, MINB><<<grid, 32, smem, stream>>>(F);
+    const int grid = want < resident ? want : resident;       // (the ring loop too: more warps than QP groups would only poll)
+    cuipm_fast_kernel<NX, NU, G, MINB, MODE><<<grid, 32, smem, stream>>>(F);
     return cudaGetLastError();
 }
 
@@ -269,16 +281,62 @@ extern "C" void cuipm_fast_prof_read(unsigned long long *out, int reset)
 }
 #endif
 
-int launch_fast(const FastArgs &F, void *stream_)
+// instances with the iteration-sliced scheduling compiled in (two more kernels each)
+#define CUIPM_FAST_RR_INSTANCES(X) CUIPM_FAST_INSTANCES(X)
+
+// QPs the device holds at once with the throughput kernel of this shape (CTAs per SM x SMs x QPs per warp); 0 if unknown
+template <int NX, int NU, int G, int MINB>
+static int resident_qps(const FastArgs &F)
+{
+    using K = fastk::Ker<NX, NU, G>;
+    const size_t smem = sizeof(double) * ((size_t) F.gstride * K::QPW + 2 * (size_t) F.nmaps * F.nbe);
+    int nblk = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(cuipm_fast_kernel<NX, NU, G, MINB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaFuncSetAttribute(cuipm_fast_kernel<NX, NU, G, MINB, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, cuipm_fast_kernel<NX, NU, G, MINB, 0>, 32, smem) != cudaSuccess) return 0;
+    return nblk * sms * K::QPW;
+}
+
+int fast_resident_qps(const FastArgs &F)
+{
+    const int nx = F.s1.nx, nu = F.s1.nu;
+#define X(NX_, NU_, G_, MB_) \
+    if (nx == NX_ && nu == NU_) return resident_qps<NX_, NU_, G_, MB_>(F);
+    CUIPM_FAST_INSTANCES(X)
+#undef X
+    return 0;
+}
+
+bool fast_rr_available(int nx, int nu)
+{
+    if (dev_g()) return false;
+#define X(NX_, NU_, G_, MB_) \
+    if (nx == NX_ && nu == NU_) return true;
+    CUIPM_FAST_RR_INSTANCES(X)
+#undef X
+    return false;
+}
+
+int launch_fast(const FastArgs &F, void *stream_, int mode)
 {
     cudaStream_t stream = (cudaStream_t) stream_;
     const int nx = F.s1.nx, nu = F.s1.nu;
+    if (mode != 0)
+    {
 #define X(NX_, NU_, G_, MB_) \
-    if (nx == NX_ && nu == NU_ && dev_g() == G_) return (int) launch_one<NX_, NU_, G_, MB_>(F, stream);
+        if (nx == NX_ && nu == NU_) return (int) (mode == 1 ? launch_one<NX_, NU_, G_, MB_, 1>(F, stream) : launch_one<NX_, NU_, G_, MB_, 2>(F, stream));
+        CUIPM_FAST_RR_INSTANCES(X)
+#undef X
+        return (int) cudaErrorInvalidValue;
+    }
+#define X(NX_, NU_, G_, MB_) \
+    if (nx == NX_ && nu == NU_ && dev_g() == G_) return (int) launch_one<NX_, NU_, G_, MB_, 0>(F, stream);
     CUIPM_FAST_DEV_INSTANCES(X)
 #undef X
 #define X(NX_, NU_, G_, MB_) \
-    if (nx == NX_ && nu == NU_) return (int) launch_one<NX_, NU_, G_, MB_>(F, stream);
+    if (nx == NX_ && nu == NU_) return (int) launch_one<NX_, NU_, G_, MB_, 0>(F, stream);
     CUIPM_FAST_INSTANCES(X)
 #undef X
     return (int) cudaErrorInvalidValue;

@@ -22,7 +22,7 @@
 // redo_list) and solved from scratch by the generic kernel.
 //
 // The file is written against a few warp primitives supplied by the including translation unit (FK_DEV, fk_lane,
-// fk_sync, fk_shfl_xor, fk_any, fk_bulk, fk_dmma, fk_mbar_*, fk_fence_async, fk_ldg, fk_rsqrt, fk_atomic_inc): the CUDA
+// fk_sync, fk_shfl_xor, fk_any, fk_bulk, fk_dmma, fk_atomic_add / _cas, fk_ld_volatile, fk_threadfence, fk_mbar_*, fk_fence_async, fk_ldg, fk_rsqrt, fk_atomic_inc): the CUDA
 // instantiation is cuipm_fast.cu; oracle/fast_emul.cpp instantiates the same body on a host emulation of a warp for the
 // CPU test-suite.
 #ifndef CUIPM_FAST_CORE_H_
@@ -1867,20 +1867,20 @@ FK_VLOOP
     // driver (OCP_QP_IPM_SOLVE x_ocp_qp_ipm.c:2684-3120 + OCP_QP_IPM_DELTA_STEP :2208-2682) for the QPs of this warp;
     // q = index of this group's QP (clamped to a valid one; valid = it exists)
     // ---------------------------------------------------------------------------------------------
-    FK_DEV void solve(int q, bool valid)
+    FK_DEV void bind(int q, bool valid)
     {
-        const int N = A.N;
-        const int SM = CUIPM_STAT_M;
         qp = A.qp + (size_t) q * A.qp_stride;
         qk = A.qpk + (size_t) q * A.qpk_stride;
         sol = A.sol + (size_t) q * A.sol_stride;
         wk = A.work + (size_t) q * A.work_stride;
         act = valid;
-        cuipm_info *info = A.info + q;
-        double *stat = A.stat ? A.stat + (size_t) q * SM * (A.o.stat_max + 1) : nullptr;
-        QpState Q;
-        Q.mu = Q.obj = Q.gap = 0.0; Q.alpha = 1.0; Q.res_m_tau = 0.0;
-        Q.res_max[0] = Q.res_max[1] = Q.res_max[2] = Q.res_max[3] = 0.0;
+    }
+
+    // start of a solve: statistics cleared, mask census, initial point; the QP is handed back if no constraint is active
+    FK_DEV void prologue(int q, cuipm_info *info, double *stat)
+    {
+        const int N = A.N;
+        const int SM = CUIPM_STAT_M;
         if (stat && act)
 FK_VLOOP
             for (int i = li; i < SM * (A.o.stat_max + 1); i += G) stat[i] = 0.0;
@@ -1912,104 +1912,276 @@ FK_VLOOP
             for (int i = li; i < s.nc; i += G) st(l + i, l[i] * fk_ldg(gm + i));
         }
         fk_sync();
-        // Every sweep has exactly one call site (everything is inlined into the kernel, and the hot code should exist once):
-        // the residual sweep opens each pass of the loop (pass 0: residuals of the initial point; pass kk: move along the
-        // step of iteration kk-1, then residuals), the predictor / corrector / conditional corrector are phases 0 / 1 / 2 of
-        // one inner loop.
+    }
+
+    // statistics row of pass kk, loop condition of the QP (x_ocp_qp_ipm.c:3017-3031); a QP that stops gets its summary written
+    // and its stores disabled
+    FK_DEV void close_pass(int kk, const QpState &Q, cuipm_info *info, double *stat)
+    {
+        const int SM = CUIPM_STAT_M;
+        if (stat && act && kk < A.o.stat_max && li == 0)
+        {
+            double *sr = stat + SM * (size_t) kk;
+            if (kk > 0) sr[6] = Q.mu;
+            sr[7] = Q.res_max[0]; sr[8] = Q.res_max[1]; sr[9] = Q.res_max[2]; sr[10] = Q.res_max[3];
+            sr[11] = Q.gap; sr[12] = Q.obj;
+        }
+        const bool go = kk < A.o.iter_max && Q.alpha > A.o.alpha_min
+                        && (Q.res_max[0] > A.o.res_g_max || Q.res_max[1] > A.o.res_b_max || Q.res_max[2] > A.o.res_d_max
+                            || Q.res_m_tau > A.o.res_m_max || Q.gap > A.o.dual_gap_max);
+        if (act && !go)
+        {
+            int status;
+            if (kk == A.o.iter_max) status = CUIPM_MAX_ITER;
+            else if (Q.alpha <= A.o.alpha_min) status = CUIPM_MIN_STEP;
+            else if (Q.mu != Q.mu) status = CUIPM_NAN_SOL;
+            else status = CUIPM_SUCCESS;
+            if (li == 0)
+            {
+                info->status = status;
+                info->iter = kk;
+                for (int i = 0; i < 4; i++) info->res_max[i] = Q.res_max[i];
+                info->mu = Q.mu;
+                info->obj = Q.obj;
+                info->dual_gap = Q.gap;
+                info->lq_count = 0;
+                info->reserved = 0;
+            }
+            act = false;
+        }
+    }
+
+    // one interior-point iteration after pass kk: predictor / corrector / conditional corrector (OCP_QP_IPM_DELTA_STEP); leaves
+    // the step length in Q.alpha.  Every sweep has exactly one call site (everything is inlined into the kernel, and the hot code
+    // should exist once): the phases 0 / 1 / 2 of one inner loop.
+    FK_DEV void iteration(int q, int kk, QpState &Q, cuipm_info *info, double *stat)
+    {
+        const int SM = CUIPM_STAT_M;
+        double *stt = (stat && kk + 1 < A.o.stat_max) ? stat + SM * (size_t) (kk + 1) : nullptr;
+        double nrm[4] = {0, 0, 0, 0};
+        double alpha = 1.0, mu_aff = 0.0, sigma_mu = 0.0;
+        bool need = true;
+        // affine direction: res_m already holds lam*t - tau_min (written by the residual sweep)
+        for (int ph = 0; ph < 3; ph++)
+        {
+            const bool stw = ph < 2 ? true : need;
+            { FK_PROF_T0(); if (ph == 0) fact_backward(); else solve_backward(ph, sigma_mu, stw); FK_PROF_ADD(ph == 0 ? 1 : 3); }
+            const int do_lin = ph == 0 ? A.o.lq_fact == 1 : A.o.itref_corr_max > 0;
+            double nr[4] = {0, 0, 0, 0};
+            double al; { FK_PROF_T0(); al = forward_pass(ph == 0, do_lin, stw, nr); FK_PROF_ADD(2); }
+            if (stw) { alpha = al; nrm[0] = nr[0]; nrm[1] = nr[1]; nrm[2] = nr[2]; nrm[3] = nr[3]; }
+            if (ph == 0)
+            {
+                if (A.o.lq_fact == 1)
+                {
+                    // a Cholesky step that leaves a large residual in the linear system switches the solve to the LQ
+                    // refactorisation (x_ocp_qp_ipm.c:2246-2346): cold path, generic kernel
+                    const double g00 = (wk + A.s0.ires.g)[0];
+                    if ((nrm[0] == 0.0 && g00 != g00) || nrm[0] > 1e-5 || nrm[1] > 1e-5 || nrm[2] > 1e-5 || nrm[3] > 1e-5)
+                        if (act) { hand_back(q, info); act = false; }
+                }
+                if (stt && act && li == 0) { stt[13] = 0; stt[0] = alpha; stt[1] = alpha; }
+                if (A.o.pred_corr != 1) break;
+            }
+            else if (ph == 2 || A.o.cond_pred_corr != 1)
+                break;
+            const double mu_aff0 = mu_aff;
+            { FK_PROF_T0(); mu_aff = mu_aff_pass(alpha); FK_PROF_ADD(4); }
+            if (ph == 0)
+            {
+                const double tmp = mu_aff / Q.mu;
+                const double sigma = tmp * tmp * tmp;
+                sigma_mu = sigma * Q.mu;
+                sigma_mu = sigma_mu > A.o.tau_min ? sigma_mu : A.o.tau_min;
+                if (stt && act && li == 0) { stt[2] = mu_aff; stt[3] = sigma; }
+            }
+            else
+            {
+                need = mu_aff > 2.0 * mu_aff0;
+                if (!fk_any(act && need)) break;
+            }
+        }
+        if (A.o.pred_corr == 1)
+        {
+            if (A.o.itref_corr_max > 0)
+            {
+                // iterative refinement is needed when the residual of the corrector system is not small
+                // (x_ocp_qp_ipm.c:2540-2620): cold path, generic kernel
+                const bool small_ = (nrm[0] < A.o.res_g_max || nrm[0] < 1e-3 * Q.res_max[0]) && (nrm[1] < A.o.res_b_max || nrm[1] < 1e-3 * Q.res_max[1])
+                                    && (nrm[2] < A.o.res_d_max || nrm[2] < 1e-3 * Q.res_max[2]) && (nrm[3] < A.o.res_m_max || nrm[3] < 1e-3 * Q.res_max[3]);
+                if (!small_ && act) { hand_back(q, info); act = false; }
+                if (stt && act && li == 0) { stt[16] = nrm[0]; stt[17] = nrm[1]; stt[18] = nrm[2]; stt[19] = nrm[3]; }
+            }
+            if (stt && act && li == 0) { stt[4] = alpha; stt[5] = alpha; }
+        }
+        if (stt && act && li == 0) stt[15] = 0;
+        Q.alpha = alpha;
+    }
+
+    FK_DEV void solve(int q, bool valid)
+    {
+        const int SM = CUIPM_STAT_M;
+        bind(q, valid);
+        cuipm_info *info = A.info + q;
+        double *stat = A.stat ? A.stat + (size_t) q * SM * (A.o.stat_max + 1) : nullptr;
+        QpState Q;
+        Q.mu = Q.obj = Q.gap = 0.0; Q.alpha = 1.0; Q.res_m_tau = 0.0;
+        Q.res_max[0] = Q.res_max[1] = Q.res_max[2] = Q.res_max[3] = 0.0;
+        prologue(q, info, stat);
+        // the residual sweep opens each pass of the loop (pass 0: residuals of the initial point; pass kk: move along the step
+        // of iteration kk-1, then residuals)
         for (int kk = 0;; kk++)
         {
             { FK_PROF_T0(); res_pass(kk > 0, Q.alpha, Q); FK_PROF_ADD(0); }
-            if (stat && act && kk < A.o.stat_max && li == 0)
-            {
-                double *sr = stat + SM * (size_t) kk;
-                if (kk > 0) sr[6] = Q.mu;
-                sr[7] = Q.res_max[0]; sr[8] = Q.res_max[1]; sr[9] = Q.res_max[2]; sr[10] = Q.res_max[3];
-                sr[11] = Q.gap; sr[12] = Q.obj;
-            }
-            // loop condition per QP; the warp leaves when none of its QPs continues
-            const bool go = kk < A.o.iter_max && Q.alpha > A.o.alpha_min
-                            && (Q.res_max[0] > A.o.res_g_max || Q.res_max[1] > A.o.res_b_max || Q.res_max[2] > A.o.res_d_max
-                                || Q.res_m_tau > A.o.res_m_max || Q.gap > A.o.dual_gap_max);
-            if (act && !go)
-            {
-                int status;
-                if (kk == A.o.iter_max) status = CUIPM_MAX_ITER;
-                else if (Q.alpha <= A.o.alpha_min) status = CUIPM_MIN_STEP;
-                else if (Q.mu != Q.mu) status = CUIPM_NAN_SOL;
-                else status = CUIPM_SUCCESS;
-                if (li == 0)
-                {
-                    info->status = status;
-                    info->iter = kk;
-                    for (int i = 0; i < 4; i++) info->res_max[i] = Q.res_max[i];
-                    info->mu = Q.mu;
-                    info->obj = Q.obj;
-                    info->dual_gap = Q.gap;
-                    info->lq_count = 0;
-                    info->reserved = 0;
-                }
-                act = false;
-            }
+            close_pass(kk, Q, info, stat);
+            // the warp leaves when none of its QPs continues
             if (!fk_any(act)) break;
-            double *stt = (stat && kk + 1 < A.o.stat_max) ? stat + SM * (size_t) (kk + 1) : nullptr;
-            double nrm[4] = {0, 0, 0, 0};
-            double alpha = 1.0, mu_aff = 0.0, sigma_mu = 0.0;
-            bool need = true;
-            // affine direction: res_m already holds lam*t - tau_min (written by the residual sweep)
-            for (int ph = 0; ph < 3; ph++)
+            iteration(q, kk, Q, info, stat);
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // Iteration-sliced scheduling.  A 4096-QP batch is 1.73 waves of the QPs an SM array can hold; with a QP bound to its warp for
+    // the whole solve every slot serves one or two QPs and the launch lasts two of the longest solves.  Here a QP is bound to a
+    // warp for ONE iteration: all its state between iterations lives in its records (plus a dozen scalars in rr_state), so the QPs
+    // that are not finished circulate through a FIFO ring -- every group pops one QP per pass, runs the iteration and the residual
+    // sweep, and pushes the QP back unless it stopped.  All QPs advance at the same rate, the slots stay filled until fewer QPs
+    // than slots are alive.  Two launches: rr_first (initial point + residual sweep 0 of every QP, fills the ring), rr_loop.
+    //   rr_ctr[0] head, [1] tail (positions, monotonic; ring slot = position mod nbatch, -1 = empty), [2] QPs that stopped
+    // ---------------------------------------------------------------------------------------------
+    static constexpr int RRS = 12;             // doubles of a QP's scalar state
+    FK_DEV void rr_save(int q, int kk, const QpState &Q) const
+    {
+        double *r = A.rr_state + (size_t) q * RRS;
+        r[0] = Q.mu; r[1] = Q.obj; r[2] = Q.gap; r[3] = Q.alpha; r[4] = Q.res_m_tau;
+        r[5] = Q.res_max[0]; r[6] = Q.res_max[1]; r[7] = Q.res_max[2]; r[8] = Q.res_max[3];
+        r[9] = nc_mask_inv; r[10] = (double) kk;
+    }
+    FK_DEV int rr_load(int q, QpState &Q)
+    {
+        const double *r = A.rr_state + (size_t) q * RRS;
+        Q.mu = r[0]; Q.obj = r[1]; Q.gap = r[2]; Q.alpha = r[3]; Q.res_m_tau = r[4];
+        Q.res_max[0] = r[5]; Q.res_max[1] = r[6]; Q.res_max[2] = r[7]; Q.res_max[3] = r[8];
+        nc_mask_inv = r[9];
+        return (int) r[10];
+    }
+    FK_DEV int wmax_i(int v) const
+    {
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1)
+        {
+            const int o = fk_shfl_xor_i(v, m);
+            v = o > v ? o : v;
+        }
+        return v;
+    }
+    FK_DEV int gmax_i(int v) const
+    {
+#pragma unroll
+        for (int m = G / 2; m > 0; m >>= 1)
+        {
+            const int o = fk_shfl_xor_i(v, m);
+            v = o > v ? o : v;
+        }
+        return v;
+    }
+    // the QP of this group stopped (or was handed back) / goes on: count it / put it back into the ring.  All lanes have made their
+    // stores of the pass visible before lane 0 of the group publishes the index.
+    FK_DEV void rr_publish(int q, bool have, int kk, const QpState &Q)
+    {
+        fk_threadfence();
+        fk_sync();
+        if (have && li == 0)
+        {
+            if (!act)
+                fk_atomic_add(A.rr_ctr + 2, 1);
+            else
             {
-                const bool stw = ph < 2 ? true : need;
-                { FK_PROF_T0(); if (ph == 0) fact_backward(); else solve_backward(ph, sigma_mu, stw); FK_PROF_ADD(ph == 0 ? 1 : 3); }
-                const int do_lin = ph == 0 ? A.o.lq_fact == 1 : A.o.itref_corr_max > 0;
-                double nr[4] = {0, 0, 0, 0};
-                double al; { FK_PROF_T0(); al = forward_pass(ph == 0, do_lin, stw, nr); FK_PROF_ADD(2); }
-                if (stw) { alpha = al; nrm[0] = nr[0]; nrm[1] = nr[1]; nrm[2] = nr[2]; nrm[3] = nr[3]; }
-                if (ph == 0)
-                {
-                    if (A.o.lq_fact == 1)
-                    {
-                        // a Cholesky step that leaves a large residual in the linear system switches the solve to the LQ
-                        // refactorisation (x_ocp_qp_ipm.c:2246-2346): cold path, generic kernel
-                        const double g00 = (wk + A.s0.ires.g)[0];
-                        if ((nrm[0] == 0.0 && g00 != g00) || nrm[0] > 1e-5 || nrm[1] > 1e-5 || nrm[2] > 1e-5 || nrm[3] > 1e-5)
-                            if (act) { hand_back(q, info); act = false; }
-                    }
-                    if (stt && act && li == 0) { stt[13] = 0; stt[0] = alpha; stt[1] = alpha; }
-                    if (A.o.pred_corr != 1) break;
-                }
-                else if (ph == 2 || A.o.cond_pred_corr != 1)
-                    break;
-                const double mu_aff0 = mu_aff;
-                { FK_PROF_T0(); mu_aff = mu_aff_pass(alpha); FK_PROF_ADD(4); }
-                if (ph == 0)
-                {
-                    const double tmp = mu_aff / Q.mu;
-                    const double sigma = tmp * tmp * tmp;
-                    sigma_mu = sigma * Q.mu;
-                    sigma_mu = sigma_mu > A.o.tau_min ? sigma_mu : A.o.tau_min;
-                    if (stt && act && li == 0) { stt[2] = mu_aff; stt[3] = sigma; }
-                }
-                else
-                {
-                    need = mu_aff > 2.0 * mu_aff0;
-                    if (!fk_any(act && need)) break;
-                }
+                rr_save(q, kk, Q);
+                fk_threadfence();
+                const int pos = fk_atomic_add(A.rr_ctr + 1, 1);
+                int *slot = A.rr_ring + (pos % A.nbatch);
+                while (fk_ld_volatile(slot) >= 0) {}          // (the previous lap's entry has been popped; its reader clears it at once)
+                fk_st_volatile(slot, q);
             }
-            if (A.o.pred_corr == 1)
+        }
+        fk_sync();
+    }
+
+    // first launch: QPs first_qp .. first_qp + QPW - 1
+    FK_DEV void rr_first(int first_qp)
+    {
+        const int SM = CUIPM_STAT_M;
+        int q = first_qp + gq;
+        const bool valid = q < A.nbatch;
+        if (!valid) q = A.nbatch - 1;
+        bind(q, valid);
+        cuipm_info *info = A.info + q;
+        double *stat = A.stat ? A.stat + (size_t) q * SM * (A.o.stat_max + 1) : nullptr;
+        QpState Q;
+        Q.mu = Q.obj = Q.gap = 0.0; Q.alpha = 1.0; Q.res_m_tau = 0.0;
+        Q.res_max[0] = Q.res_max[1] = Q.res_max[2] = Q.res_max[3] = 0.0;
+        prologue(q, info, stat);
+        res_pass(0, 1.0, Q);
+        close_pass(0, Q, info, stat);
+        rr_publish(q, valid, 0, Q);
+        fk_sync();
+    }
+
+    // second launch: the loop over the ring
+    FK_DEV void rr_loop()
+    {
+        const int SM = CUIPM_STAT_M;
+        unsigned nap = 4000;        // nanoseconds between two looks at an empty ring: doubled up to 128 us while nothing turns up (a
+                                    // thousand idle warps polling the counters every few microseconds starve the atomics of the
+                                    // warps that still work: measured 4.6x on a batch with a handful of 50-iteration stragglers)
+        for (;;)
+        {
+            // one lane reserves positions for all groups of the warp (a compare-and-swap per group made thousands of lanes retry
+            // against each other on shapes with many QPs per warp); a position below the tail counter has a writer on its way
+            int base = -1, cnt = 0;
+            if (fk_lane() == 0)
+                for (;;)
+                {
+                    const int h = fk_ld_volatile(A.rr_ctr), t = fk_ld_volatile(A.rr_ctr + 1);
+                    if (h >= t) break;                               // nothing queued right now
+                    const int want = t - h < QPW ? t - h : QPW;
+                    if (fk_atomic_cas(A.rr_ctr, h, h + want) == h) { base = h; cnt = want; break; }
+                }
+            base = wmax_i(base);
+            cnt = wmax_i(cnt);
+            int q = -1;
+            if (li == 0 && gq < cnt)
             {
-                if (A.o.itref_corr_max > 0)
-                {
-                    // iterative refinement is needed when the residual of the corrector system is not small
-                    // (x_ocp_qp_ipm.c:2540-2620): cold path, generic kernel
-                    const bool small_ = (nrm[0] < A.o.res_g_max || nrm[0] < 1e-3 * Q.res_max[0]) && (nrm[1] < A.o.res_b_max || nrm[1] < 1e-3 * Q.res_max[1])
-                                        && (nrm[2] < A.o.res_d_max || nrm[2] < 1e-3 * Q.res_max[2]) && (nrm[3] < A.o.res_m_max || nrm[3] < 1e-3 * Q.res_max[3]);
-                    if (!small_ && act) { hand_back(q, info); act = false; }
-                    if (stt && act && li == 0) { stt[16] = nrm[0]; stt[17] = nrm[1]; stt[18] = nrm[2]; stt[19] = nrm[3]; }
-                }
-                if (stt && act && li == 0) { stt[4] = alpha; stt[5] = alpha; }
+                int *slot = A.rr_ring + ((base + gq) % A.nbatch);
+                while ((q = fk_ld_volatile(slot)) < 0) {}
+                fk_st_volatile(slot, -1);
             }
-            if (stt && act && li == 0) stt[15] = 0;
-            Q.alpha = alpha;
+            q = gmax_i(q);
+            const bool have = q >= 0;
+            if (!fk_any(have))
+            {
+                int d = fk_lane() == 0 ? fk_ld_volatile(A.rr_ctr + 2) : 0;
+                d = fk_any(d >= A.nbatch) ? 1 : 0;
+                if (d) break;                                        // every QP has stopped
+                fk_nanosleep(nap);
+                if (nap < 128000) nap *= 2;
+                continue;
+            }
+            nap = 4000;
+            fk_threadfence();
+            if (!have) q = 0;
+            bind(q, have);
+            cuipm_info *info = A.info + q;
+            double *stat = A.stat ? A.stat + (size_t) q * SM * (A.o.stat_max + 1) : nullptr;
+            QpState Q;
+            int kk = rr_load(q, Q);
+            fk_sync();
+            iteration(q, kk, Q, info, stat);
+            kk++;
+            { FK_PROF_T0(); res_pass(1, Q.alpha, Q); FK_PROF_ADD(0); }
+            close_pass(kk, Q, info, stat);
+            rr_publish(q, have, kk, Q);
         }
     }
 

@@ -50,6 +50,12 @@ static inline fk_double2 fk_ld2(const double *p)
 static inline void fk_dmma(double &c0, double &c1, double a, double b) { simt::dmma(c0, c1, a, b); }
 static inline double fk_rsqrt(double x) { return 1.0 / std::sqrt(x); }
 static inline int fk_atomic_inc(int *p) { return (*p)++; }
+static inline int fk_atomic_add(int *p, int v) { const int o = *p; *p += v; return o; }
+static inline int fk_atomic_cas(int *p, int cmp, int v) { const int o = *p; if (o == cmp) *p = v; return o; }
+static inline int fk_ld_volatile(const int *p) { return *p; }
+static inline void fk_st_volatile(int *p, int v) { *p = v; }
+static inline void fk_threadfence() {}
+static inline void fk_nanosleep(unsigned) {}
 using std::fabs;
 using std::fmax;
 using std::fmin;
@@ -59,6 +65,8 @@ using std::sqrt;
 #include "cuipm_plan.h"
 
 namespace {
+
+int g_rr = 0;      // 1: iteration-sliced scheduling (rr_first for every warp, then rr_loop)
 
 template <int NX, int NU, int G>
 int run(cuipm::FastArgs F, int order)
@@ -73,19 +81,37 @@ int run(cuipm::FastArgs F, int order)
     double *base = smem.data();
     while ((size_t) base & 15) base++;
     const int nwarp = (F.nbatch + K::QPW - 1) / K::QPW;
+    std::vector<double> rr_state((size_t) 12 * F.nbatch, std::nan(""));
+    std::vector<int> rr_ring(F.nbatch, -1), rr_ctr(4, 0);
+    F.rr_state = rr_state.data(); F.rr_ring = rr_ring.data(); F.rr_ctr = rr_ctr.data();
     for (int w = 0; w < nwarp; w++)
     {
         for (double &x : smem) x = std::nan("");      // uninitialised shared memory
         simt::MBar bars[6];
         simt::run_warp([&]() {
             K k(F, base, bars);
-            k.run(w * K::QPW);
+            if (g_rr) k.rr_first(w * K::QPW);
+            else k.run(w * K::QPW);
         }, order);
     }
+    if (g_rr)
+        // the warps of the second launch run one after the other here: the first one finds the whole ring and works it off alone
+        // (pops of an empty ring with QPs alive cannot occur), the others see every QP stopped
+        for (int w = 0; w < (nwarp < 3 ? nwarp : 3); w++)
+        {
+            for (double &x : smem) x = std::nan("");
+            simt::MBar bars[6];
+            simt::run_warp([&]() {
+                K k(F, base, bars);
+                k.rr_loop();
+            }, order);
+        }
     return 0;
 }
 
 }  // namespace
+
+extern "C" void fast_emul_set_rr(int on) { g_rr = on; }
 
 // Solves nbatch QPs of `shape` (records in the layout of cuipm_layout_create) with the throughput kernel body; QPs the
 // kernel hands back are listed in redo[0..*nredo) and keep status CUIPM_FAST_REDO.  g = lanes per QP.

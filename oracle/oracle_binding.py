@@ -174,7 +174,7 @@ def emul_expand(batch: Batch, cond_N: int, sol2: np.ndarray, nthreads: int = 128
 FAST_EMUL_LIB = os.path.join(_HERE, "libfast_emul.so")
 
 
-def fast_emul_solve(batch: Batch, opts: CuipmOpts, g: int = 8, order: int = 0, sol0=None, want_stat=False):
+def fast_emul_solve(batch: Batch, opts: CuipmOpts, g: int = 8, order: int = 0, sol0=None, want_stat=False, rr: bool = False):
     """The product's throughput kernel body (acados_b200/csrc/cuipm_fast_core.h) executed on the host emulation of a
     warp (oracle/simt_emul.h).  Returns (sol, info[, stat], redo) with redo = indices of the QPs the kernel hands back
     to the generic kernel (cold paths)."""
@@ -186,11 +186,13 @@ def fast_emul_solve(batch: Batch, opts: CuipmOpts, g: int = 8, order: int = 0, s
     redo = np.zeros(nb + 1, dtype=np.int32)
     nredo = C.c_int(0)
     lib.fast_emul_solve.restype = C.c_int
+    lib.fast_emul_set_rr(C.c_int(1 if rr else 0))      # iteration-sliced scheduling (rr_first / rr_loop) instead of one warp per QP group
     rc = lib.fast_emul_solve(C.byref(batch.shape.as_ctypes()), C.c_int(nb), C.c_void_p(batch.qp.ctypes.data),
                              C.c_void_p(sol.ctypes.data), C.c_void_p(info.ctypes.data),
                              C.c_void_p(stat.ctypes.data if want_stat else None), C.byref(opts), C.c_int(g), C.c_int(order),
                              C.c_void_p(redo.ctypes.data), C.byref(nredo))
     if rc != 0:
         raise RuntimeError(f"fast_emul_solve: rc={rc} (-1 shape not eligible, -2 no instance for this (nx, nu, g))")
+    lib.fast_emul_set_rr(C.c_int(0))
     redo = np.sort(redo[:nredo.value])
     return (sol, info, stat, redo) if want_stat else (sol, info, redo)

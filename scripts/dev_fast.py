@@ -29,15 +29,16 @@ def timing(b, name, steps=3):
     d_qp = torch.from_numpy(b.qp).cuda()
     d_sol = torch.zeros((nb, b.layout.sol_stride), dtype=torch.float64, device="cuda")
     d_info = torch.zeros(nb * INFO_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
-    for fast in (1, 0):
+    for fast, rr in ((1, 1), (1, 0), (0, 0)):
         s.set_tuning("fast", fast)
+        s.set_tuning("rr", rr)
         s.solve_device(nb, d_qp.data_ptr(), d_sol.data_ptr(), d_info.data_ptr(), o, sync=True)
         ms = []
         for _ in range(steps):
             s.solve_device(nb, d_qp.data_ptr(), d_sol.data_ptr(), d_info.data_ptr(), o, sync=True)
             ms.append(s.last_kernel_ms)
         info = np.frombuffer(d_info.cpu().numpy().tobytes(), dtype=INFO_DTYPE)
-        print(f"{name} batch {nb} fast={fast}: {min(ms):.2f} ms -> {nb/min(ms)*1e3:.0f} QP/s  iters {info['iter'].mean():.2f} status {np.bincount(info['status'])}", flush=True)
+        print(f"{name} batch {nb} fast={fast} rr={rr} launches {s.last_launch_count}: {min(ms):.2f} ms -> {nb/min(ms)*1e3:.0f} QP/s  iters {info['iter'].mean():.2f} status {np.bincount(info['status'])}", flush=True)
     s.close()
 
 if __name__ == "__main__":
@@ -89,6 +90,26 @@ if __name__ == "__main__":
     if what == "time3":
         timing(problems.chain_mass(4096, N=40, seed=1234), "c2")
         timing(problems.named_config("c3", 16384), "c3")
+    if what == "rr":
+        # iteration-sliced scheduling on / off: bit identity and timing
+        for nbq in (4096, 8192, 2048):
+            b = problems.chain_mass(nbq, N=40, seed=1234)
+            o = default_opts()
+            s = CuipmSolver(b.shape, nbq)
+            d_qp = torch.from_numpy(b.qp).cuda()
+            outs = {}
+            for rr in (1, 0, 1, 0):
+                s.set_tuning("rr", rr)
+                d_sol = torch.zeros((nbq, b.layout.sol_stride), dtype=torch.float64, device="cuda")
+                d_info = torch.zeros(nbq * INFO_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+                ms = []
+                for _ in range(3):
+                    s.solve_device(nbq, d_qp.data_ptr(), d_sol.data_ptr(), d_info.data_ptr(), o, sync=True)
+                    ms.append(s.last_kernel_ms)
+                outs[rr] = (d_sol.cpu().numpy(), d_info.cpu().numpy().copy())
+                print(f"c2 batch {nbq} rr={rr}: {min(ms):.2f} ms -> {nbq/min(ms)*1e3:.0f} QP/s launches {s.last_launch_count}", flush=True)
+            print("   bit-identical:", np.array_equal(outs[0][0], outs[1][0]), np.array_equal(outs[0][1], outs[1][1]), flush=True)
+            s.close()
     if what == "time5":
         timing(problems.named_config("c5", 1024), "c5")
     if what == "par5":

@@ -96,6 +96,24 @@ def test_warm_start():
         _check(b, 8, sol0=osol, warm_start=ws, tol_u=1e-9 if ws == 2 else 1e-7, check_stat=False)
 
 
+@pytest.mark.parametrize("g,order", [(8, 0), (8, 1), (4, 1)])
+def test_iteration_sliced_scheduling_is_bit_identical(g, order):
+    """rr_first / rr_loop (a QP bound to a warp for one iteration, the unfinished ones circulating through a ring) against the
+    one-warp-per-group schedule: same arithmetic on the same records, hence bit-identical solutions, summaries and statistics
+    whatever the order in which the QPs meet in a warp; QPs with different iteration counts, a QP that is handed back."""
+    b = problems.chain_mass(7, N=8, seed=4) if g == 8 else problems.mass_spring(11, seed=2, x0_scale=0.5)
+    if g == 8:
+        for k in range(b.shape.N + 1):
+            b.layout.view(b.qp, "dmask", k)[5] = 0.0           # QP 5 has no active constraint: handed back by the first launch
+    o = default_opts()
+    s0, i0, st0, r0 = ob.fast_emul_solve(b, o, g=g, order=order, want_stat=True)
+    s1, i1, st1, r1 = ob.fast_emul_solve(b, o, g=g, order=order, want_stat=True, rr=True)
+    assert np.array_equal(r0, r1) and len(set(i0["iter"].tolist())) > 1
+    assert np.array_equal(s0, s1) and np.array_equal(st0, st1)
+    for f in ("status", "iter", "mu", "obj", "dual_gap", "res_max"):
+        assert np.array_equal(i0[f], i1[f]), f
+
+
 def test_hand_back_when_no_constraint_is_active():
     b = problems.chain_mass(2, N=6, seed=2)
     for k in range(b.shape.N + 1):
