@@ -457,7 +457,7 @@ def main():
         frac_hbm, frac_fp64 = achieved / hbm_peak, tflops / fp64_peak
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": max(frac_hbm, frac_fp64),
                     "frac_hbm_algorithmic": frac_hbm, "frac_fp64_algorithmic": frac_fp64, "frac_is": "fp64" if frac_fp64 > frac_hbm else "hbm",
-                    "traffic": traffic, "kernel": "cuipm_fast_kernel" if args.fast and launches_per_step > 1 else "cuipm_solve_kernel",
+                    "traffic": traffic, "kernel": ("cuipm_fast_kernel (ring loop + first launch of the iteration-sliced scheduling)" if launches_per_step > 3 else "cuipm_fast_kernel") if args.fast and launches_per_step > 1 else "cuipm_solve_kernel",
                     "kernel_ms": kernel_ms, "solve_ms_all_kernels": solve_ms,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
                     "algorithmic_bytes_per_qp": ab["B_min"], "mean_ipm_iterations": iters_mean,

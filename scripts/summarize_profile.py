@@ -40,8 +40,8 @@ if os.path.exists(rep):
             "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
             "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
     out = {}
-    with open(os.path.join(pr, f"{tag}_ncu_full_summary.md"), "w") as f:
-        f.write(f"# {tag}: `ncu --set full --clock-control none --import-source on -k regex:cuipm_solve -s 1 -c 1 python bench.py --steps 2 --warmup 1 --no-cpu`\n\n| metric | unit | value |\n|---|---|---|\n")
+    with open(os.path.join(pr, f"{tag}_ncu_capture_table.md"), "w") as f:
+        f.write(f"# {tag}: `ncu --set full --clock-control none --import-source on` of the kernel scripts/collect_profiles.sh selected\n\n| metric | unit | value |\n|---|---|---|\n")
         for w in want:
             if w in hdr:
                 i = hdr.index(w); f.write(f"| {w} | {unit[i]} | {val[i]} |\n"); out[w] = (unit[i], val[i])
@@ -50,6 +50,5 @@ if os.path.exists(rep):
         return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "Tbyte": 1e12}.get(u, 1)
     if "dram__bytes_read.sum" in out:
         tr = tobytes(*out["dram__bytes_read.sum"]) + tobytes(*out["dram__bytes_write.sum"])
-        json.dump({"dram_bytes_per_launch": tr, "source": f"profiles/{tag}_ncu_full_summary.md (dram__bytes_read.sum + dram__bytes_write.sum, one launch of cuipm_solve_kernel, batch 4096)"},
-                  open(os.path.join(pr, "traffic.json"), "w"), indent=1)
-    print(open(os.path.join(pr, f"{tag}_ncu_full_summary.md")).read())
+        print("dram bytes per launch", tr)
+    print(open(os.path.join(pr, f"{tag}_ncu_capture_table.md")).read())
