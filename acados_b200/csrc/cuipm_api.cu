@@ -93,8 +93,8 @@ static int build_desc(cuipm_solver *s, const cuipm_shape *sh)
         if (s->rr_ok)
         {
             CK(cudaMalloc(&s->d_rr_state, sizeof(double) * 12 * (size_t) s->max_batch));
-            CK(cudaMalloc(&s->d_rr_ring, sizeof(int) * (size_t) s->max_batch));
-            CK(cudaMalloc(&s->d_rr_ctr, sizeof(int) * 4 * cuipm_solver::kPipe));
+            CK(cudaMalloc(&s->d_rr_ring, sizeof(int) * CUIPM_RR_RINGS * (size_t) s->max_batch));
+            CK(cudaMalloc(&s->d_rr_ctr, sizeof(int) * CUIPM_RR_CTR * cuipm_solver::kPipe));
         }
     }
     return CUIPM_OK;
@@ -131,9 +131,9 @@ static int launch_batch(cuipm_solver *s, const LaunchArgs &a0, int slot, size_t 
         const bool rr = s->rr_ok && s->use_rr && (s->use_rr > 1 || (s->rr_resident > 0 && a.nbatch > s->rr_resident));
         if (rr)
         {
-            F.rr_state = s->d_rr_state + 12 * lo; F.rr_ring = s->d_rr_ring + lo; F.rr_ctr = s->d_rr_ctr + 4 * slot;
-            e = cudaMemsetAsync(F.rr_ring, 0xff, sizeof(int) * (size_t) a.nbatch, stream);
-            if (e == cudaSuccess) e = cudaMemsetAsync(F.rr_ctr, 0, 4 * sizeof(int), stream);
+            F.rr_state = s->d_rr_state + 12 * lo; F.rr_ring = s->d_rr_ring + CUIPM_RR_RINGS * lo; F.rr_ctr = s->d_rr_ctr + CUIPM_RR_CTR * slot;
+            e = cudaMemsetAsync(F.rr_ring, 0xff, sizeof(int) * CUIPM_RR_RINGS * (size_t) a.nbatch, stream);
+            if (e == cudaSuccess) e = cudaMemsetAsync(F.rr_ctr, 0, CUIPM_RR_CTR * sizeof(int), stream);
             if (e != cudaSuccess) { set_error(std::string("cudaMemsetAsync: ") + cudaGetErrorString(e)); return CUIPM_ERR_CUDA; }
             rc = launch_fast(F, (void *) stream, 1);
             if (rc == 0) { (*launches)++; rc = launch_fast(F, (void *) stream, 2); }

@@ -102,13 +102,17 @@ struct FastArgs
     int *redo_list;                // QPs that need a cold path (LQ refactorisation, iterative refinement, no active constraint):
     int *redo_count;               //   handed to the generic kernel, which solves them from scratch
     int *next_qp;                  // work counter of the persistent warps (zero at launch)
-    // iteration-sliced scheduling (cuipm_fast_core.h, rr_first / rr_loop): scalar state of every QP between iterations, the ring of
-    // QPs that go on (nbatch slots, -1 = empty) and its counters {head, tail, stopped, -}
+    // iteration-sliced scheduling (cuipm_fast_core.h, rr_first / rr_loop): scalar state of every QP between iterations, the
+    // CUIPM_RR_RINGS rings of QPs that go on (one per decade of mu, nbatch slots each, -1 = empty) and their counters
+    // {heads, tails, stopped}: CUIPM_RR_CTR ints
     double *rr_state;
     int *rr_ring;
     int *rr_ctr;
     cuipm_opts o;
 };
+
+#define CUIPM_RR_RINGS 8
+#define CUIPM_RR_CTR 32
 
 // status value the throughput kernel leaves in cuipm_info::status of a QP it hands back (never seen by callers)
 #define CUIPM_FAST_REDO 100

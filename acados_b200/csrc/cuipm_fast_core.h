@@ -2047,9 +2047,24 @@ FK_VLOOP
     // that are not finished circulate through a FIFO ring -- every group pops one QP per pass, runs the iteration and the residual
     // sweep, and pushes the QP back unless it stopped.  All QPs advance at the same rate, the slots stay filled until fewer QPs
     // than slots are alive.  Two launches: rr_first (initial point + residual sweep 0 of every QP, fills the ring), rr_loop.
-    //   rr_ctr[0] head, [1] tail (positions, monotonic; ring slot = position mod nbatch, -1 = empty), [2] QPs that stopped
+    // Which QP next: the launch ends with the slowest QP, and how far a QP is from the end shows in its duality measure (on the
+    // benchmark batch log mu after three iterations correlates 0.7-0.77 with the final iteration count), so the ring is RRK rings,
+    // one per decade of mu, and a warp takes the QPs with the largest mu first -- "longest remaining first" with mu as the estimate.
+    // A simulation on the measured per-iteration statistics gives 19 passes for the 4096 batch against 22-23 for one FIFO ring
+    // (17 with the true remaining counts, 16.3 = work / slots).
+    //   rr_ctr[b], b < RRK: head of ring b; rr_ctr[RRK + b]: tail (positions, monotonic; slot = b*nbatch + position mod nbatch,
+    //   -1 = empty); rr_ctr[2 RRK]: QPs that stopped
     // ---------------------------------------------------------------------------------------------
     static constexpr int RRS = 12;             // doubles of a QP's scalar state
+    static constexpr int RRK = CUIPM_RR_RINGS; // rings: mu >= 1e-1, >= 1e-2, ..., the rest (a NaN goes first)
+    FK_DEV static int rr_bucket(double mu)
+    {
+        int b = 0;
+        double th = 0.1;
+#pragma unroll
+        for (int i = 0; i < RRK - 1; i++) { b += mu < th; th *= 0.1; }
+        return b;
+    }
     FK_DEV void rr_save(int q, int kk, const QpState &Q) const
     {
         double *r = A.rr_state + (size_t) q * RRS;
@@ -2094,13 +2109,14 @@ FK_VLOOP
         if (have && li == 0)
         {
             if (!act)
-                fk_atomic_add(A.rr_ctr + 2, 1);
+                fk_atomic_add(A.rr_ctr + 2 * RRK, 1);
             else
             {
                 rr_save(q, kk, Q);
                 fk_threadfence();
-                const int pos = fk_atomic_add(A.rr_ctr + 1, 1);
-                int *slot = A.rr_ring + (pos % A.nbatch);
+                const int b = rr_bucket(Q.mu);
+                const int pos = fk_atomic_add(A.rr_ctr + RRK + b, 1);
+                int *slot = A.rr_ring + ((size_t) b * A.nbatch + pos % A.nbatch);
                 while (fk_ld_volatile(slot) >= 0) {}          // (the previous lap's entry has been popped; its reader clears it at once)
                 fk_st_volatile(slot, q);
             }
@@ -2139,21 +2155,34 @@ FK_VLOOP
         {
             // one lane reserves positions for all groups of the warp (a compare-and-swap per group made thousands of lanes retry
             // against each other on shapes with many QPs per warp); a position below the tail counter has a writer on its way
-            int base = -1, cnt = 0;
-            if (fk_lane() == 0)
-                for (;;)
-                {
-                    const int h = fk_ld_volatile(A.rr_ctr), t = fk_ld_volatile(A.rr_ctr + 1);
-                    if (h >= t) break;                               // nothing queued right now
-                    const int want = t - h < QPW ? t - h : QPW;
-                    if (fk_atomic_cas(A.rr_ctr, h, h + want) == h) { base = h; cnt = want; break; }
-                }
-            base = wmax_i(base);
-            cnt = wmax_i(cnt);
-            int q = -1;
-            if (li == 0 && gq < cnt)
+            // (the rings are visited from the largest mu down until every group has a QP)
+            int cnt = 0;
+            size_t myslot = 0;
+            bool mine = false;
+            for (int b = 0; b < RRK && cnt < QPW; b++)
             {
-                int *slot = A.rr_ring + ((base + gq) % A.nbatch);
+                int base = -1, got = 0;
+                if (fk_lane() == 0)
+                    for (;;)
+                    {
+                        const int h = fk_ld_volatile(A.rr_ctr + b), t = fk_ld_volatile(A.rr_ctr + RRK + b);
+                        if (h >= t) break;                               // nothing queued here right now
+                        const int want = t - h < QPW - cnt ? t - h : QPW - cnt;
+                        if (fk_atomic_cas(A.rr_ctr + b, h, h + want) == h) { base = h; got = want; break; }
+                    }
+                base = wmax_i(base);
+                got = wmax_i(got);
+                if (got > 0 && gq >= cnt && gq < cnt + got)
+                {
+                    mine = true;
+                    myslot = (size_t) b * A.nbatch + (base + gq - cnt) % A.nbatch;
+                }
+                cnt += got;
+            }
+            int q = -1;
+            if (li == 0 && mine)
+            {
+                int *slot = A.rr_ring + myslot;
                 while ((q = fk_ld_volatile(slot)) < 0) {}
                 fk_st_volatile(slot, -1);
             }
@@ -2161,7 +2190,7 @@ FK_VLOOP
             const bool have = q >= 0;
             if (!fk_any(have))
             {
-                int d = fk_lane() == 0 ? fk_ld_volatile(A.rr_ctr + 2) : 0;
+                int d = fk_lane() == 0 ? fk_ld_volatile(A.rr_ctr + 2 * RRK) : 0;
                 d = fk_any(d >= A.nbatch) ? 1 : 0;
                 if (d) break;                                        // every QP has stopped
                 fk_nanosleep(nap);

@@ -82,7 +82,7 @@ int run(cuipm::FastArgs F, int order)
     while ((size_t) base & 15) base++;
     const int nwarp = (F.nbatch + K::QPW - 1) / K::QPW;
     std::vector<double> rr_state((size_t) 12 * F.nbatch, std::nan(""));
-    std::vector<int> rr_ring(F.nbatch, -1), rr_ctr(4, 0);
+    std::vector<int> rr_ring((size_t) CUIPM_RR_RINGS * F.nbatch, -1), rr_ctr(CUIPM_RR_CTR, 0);
     F.rr_state = rr_state.data(); F.rr_ring = rr_ring.data(); F.rr_ctr = rr_ctr.data();
     for (int w = 0; w < nwarp; w++)
     {
