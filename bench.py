@@ -175,7 +175,7 @@ def main():
     ap.add_argument("--fast", type=int, default=1, help="0: keep the throughput kernel off (generic one-warp-per-QP kernel only)")
     ap.add_argument("--target-batch", type=int, default=0, help="QPs per GPU of the extra target-point measurement (default: 8192 when the job has 8 ranks)")
     ap.add_argument("--e2e-pipe", type=int, default=1, help="chunks per host call in the e2e leg (0: the solver's default of 8, best for one blocking call; "
-                    "1: the whole batch per call, best when two solver objects alternate -- measured 98.0 k vs 88.1 k QP/s)")
+                    "1: the whole batch per call, best when two solver objects alternate -- measured 107 k vs 88 k QP/s)")
     ap.add_argument("--no-scatter", action="store_true", help="N > 1: skip the scatter / solve / gather leg over NCCL")
     ap.add_argument("--no-plugin", action="store_true", help="skip the end-to-end leg through the plugin's batched entry")
     ap.add_argument("--no-tight", action="store_true", help="skip the second parity pass (all tolerances 1e-12)")
