@@ -114,6 +114,20 @@ def test_iteration_sliced_scheduling_is_bit_identical(g, order):
         assert np.array_equal(i0[f], i1[f]), f
 
 
+@pytest.mark.parametrize("shape", ["pendulum_g2", "legged_g32"])
+def test_iteration_sliced_scheduling_other_mappings(shape):
+    """The same with 16 QPs per warp (two lanes per QP) and with one QP per warp (the tensor-core instance)."""
+    if shape == "pendulum_g2":
+        b, g = problems.named_config("c3", 21), 2
+    else:
+        b, g = problems.random_qp(problems.random_shape(3, 48, 12, nbx=12, ns=12), 3, seed=3, umax=0.5, xmax=1.0, x0_scale=1.0), 32
+    o = default_opts()
+    s0, i0, r0 = ob.fast_emul_solve(b, o, g=g)
+    s1, i1, r1 = ob.fast_emul_solve(b, o, g=g, rr=True)
+    assert np.array_equal(r0, r1) and np.array_equal(s0, s1)
+    assert np.array_equal(i0["iter"], i1["iter"]) and np.array_equal(i0["status"], i1["status"])
+
+
 def test_hand_back_when_no_constraint_is_active():
     b = problems.chain_mass(2, N=6, seed=2)
     for k in range(b.shape.N + 1):
